@@ -1,0 +1,287 @@
+"""Python host-side mirror of the reference's KmerGuts interface, bound to libckm.so through ctypes.
+
+The class and method names follow the reference (kguts.h:334-372) so that tests read like the
+reference's call sites; the unit of work is a *batch* of sequences (one request body chunk) instead
+of one sequence.  There is no CPU path here: if libckm.so cannot be loaded, or no sm_100 device is
+present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+WANT_CALLS, WANT_HITS, WANT_OTU, WANT_BEST = 1, 2, 4, 8
+BEST_HAS_CALLS, BEST_AMBIG = 1, 2
+MAX_ENCODED = 20**8
+
+CALL_DT = np.dtype([("start", "<u4"), ("end", "<u4"), ("count", "<i4"), ("function_index", "<u4"),
+                    ("weighted_hits", "<f4")])
+HIT_DT = np.dtype([("which_kmer", "<u8"), ("offset", "<u4"), ("otu_index", "<i4"), ("function_index", "<i4"),
+                   ("function_wt", "<f4"), ("avg_from_end", "<u2"), ("pad_", "<u2"), ("pad2_", "<u4")])
+OTU_DT = np.dtype([("otu_index", "<i4"), ("count", "<i4")])
+BEST_DT = np.dtype([("function_index", "<i4"), ("ambig_a", "<i4"), ("ambig_b", "<i4"), ("flags", "<u4"),
+                    ("score", "<f4"), ("weighted_score", "<f4"), ("score_offset", "<f4")])
+SLOT_DT = np.dtype([("which_kmer", "<u8"), ("otu_index", "<i4"), ("avg_from_end", "<u2"), ("pad_", "<u2"),
+                    ("function_index", "<i4"), ("function_wt", "<f4")])
+
+
+class CkmError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__(f"libckm error {code}: {text}")
+        self.code = code
+
+
+class BatchOutC(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("call_offsets", C.c_void_p), ("calls", C.c_void_p), ("hit_offsets", C.c_void_p),
+                ("hits", C.c_void_p), ("otu_offsets", C.c_void_p), ("otus", C.c_void_p), ("best", C.c_void_p),
+                ("n_probes", C.c_uint64), ("n_hits", C.c_uint64)]
+
+
+class DeviceOutC(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("d_n_hits", C.c_void_p), ("d_n_calls", C.c_void_p), ("d_calls", C.c_void_p),
+                ("min_hits_for_call_base", C.c_int32), ("d_best", C.c_void_p), ("d_totals", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load (building first if the sources are newer) libckm.so.  Fails loudly; never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.build()
+    L = C.CDLL(path)
+    L.ckm_last_error.restype = C.c_char_p
+    L.ckm_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.ckm_open_image.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                 C.POINTER(C.c_void_p)]
+    L.ckm_close.argtypes = [C.c_void_p]
+    L.ckm_function_at_index.restype = C.c_char_p
+    L.ckm_function_at_index.argtypes = [C.c_void_p, C.c_int32]
+    L.ckm_otu_at_index.restype = C.c_char_p
+    L.ckm_otu_at_index.argtypes = [C.c_void_p, C.c_int32]
+    L.ckm_function_count.argtypes = [C.c_void_p]
+    L.ckm_otu_count.argtypes = [C.c_void_p]
+    L.ckm_num_sigs.restype = C.c_uint64
+    L.ckm_num_sigs.argtypes = [C.c_void_p]
+    L.ckm_table_slot_bytes.argtypes = [C.c_void_p]
+    L.ckm_set_default_params.argtypes = [C.c_void_p]
+    L.ckm_set_params.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.ckm_get_params.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
+    L.ckm_encoded_aa_kmer.restype = C.c_uint64
+    L.ckm_encoded_aa_kmer.argtypes = [C.c_char_p]
+    L.ckm_decoded_kmer.argtypes = [C.c_uint64, C.c_char_p]
+    L.ckm_call_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(BatchOutC)]
+    L.ckm_call_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32]
+    L.ckm_device_results.argtypes = [C.c_void_p, C.POINTER(DeviceOutC)]
+    L.ckm_read_totals.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.ckm_stream.restype = C.c_void_p
+    L.ckm_stream.argtypes = [C.c_void_p]
+    L.ckm_launch_count.restype = C.c_uint64
+    L.ckm_launch_count.argtypes = [C.c_void_p]
+    L.ckm_synchronize.argtypes = [C.c_void_p]
+    L.ckm_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    L.ckm_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    L.ckm_image_build.argtypes = [C.c_uint64, C.c_uint64] + [C.c_void_p] * 6 + [C.c_size_t]
+    L.ckm_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    L.ckm_host_free.argtypes = [C.c_void_p]
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise CkmError(rc, lib().ckm_last_error().decode(errors="replace"))
+
+
+def _arr(ptr, count, dtype):
+    if not ptr or count == 0:
+        return np.zeros(0, dtype=dtype)
+    buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype).copy()
+
+
+def encoded_aa_kmer(kmer: bytes) -> int:
+    """KmerGuts::encoded_aa_kmer (kguts.cc:457-471)."""
+    return lib().ckm_encoded_aa_kmer(kmer)
+
+
+def decoded_kmer(key: int) -> bytes:
+    """KmerGuts::decoded_kmer (kguts.cc:473-483)."""
+    b = C.create_string_buffer(9)
+    lib().ckm_decoded_kmer(key, b)
+    return b.value
+
+
+def build_image(nbuckets: int, keys, fI, oI, avg, wt) -> np.ndarray:
+    """KmerGuts(dir, nbuckets) + insert_kmer + save_kmer_hash_table (kguts.cc:77-115, 188-234): returns the
+    file bytes (header + slots) as a uint8 array."""
+    keys = np.ascontiguousarray(keys, np.uint64)
+    fI = np.ascontiguousarray(fI, np.int32)
+    oI = np.ascontiguousarray(oI, np.int32)
+    avg = np.ascontiguousarray(avg, np.uint16)
+    wt = np.ascontiguousarray(wt, np.float32)
+    img = np.empty(24 + 24 * nbuckets, dtype=np.uint8)
+    _check(lib().ckm_image_build(nbuckets, len(keys), keys.ctypes.data, fI.ctypes.data, oI.ctypes.data, avg.ctypes.data,
+                                 wt.ctypes.data, img.ctypes.data, img.nbytes))
+    return img
+
+
+def save_kmer_hash_table(image: np.ndarray, kmer_dir: str) -> None:
+    image.tofile(os.path.join(kmer_dir, "kmer.table.mem_map"))
+
+
+class KmerGuts:
+    """Batch mirror of ``KmerGuts(kmer_dir, image)`` (kguts.cc:34-58)."""
+
+    def __init__(self, kmer_dir: str | None = None, image: np.ndarray | None = None, device: int = 0,
+                 function_names=None, otu_names=None):
+        L = lib()
+        h = C.c_void_p()
+        if image is not None:
+            fn = [s.encode() for s in (function_names or [])]
+            on = [s.encode() for s in (otu_names or [])]
+            fa = (C.c_char_p * len(fn))(*fn)
+            oa = (C.c_char_p * len(on))(*on)
+            _check(L.ckm_open_image(image.ctypes.data, image.nbytes, device, fa, len(fn), oa, len(on), C.byref(h)))
+        else:
+            _check(L.ckm_open(kmer_dir.encode(), device, C.byref(h)))
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ckm_close(self._h)
+            self._h = None
+
+    __del__ = close
+
+    # -- Q1 ------------------------------------------------------------------------------------------
+    _PARAM_NAMES = ("order_constraint", "min_hits", "min_weighted_hits", "max_gap")
+
+    def set_default_parameters(self):
+        lib().ckm_set_default_params(self._h)
+
+    def set_parameters(self, params: dict):
+        """KmerGuts::set_parameters (kguts.cc:244-268): reset to defaults, then apply the integer-valued
+        entries whose key is one of the four engine parameters; non-integers are warned about and ignored."""
+        cur = dict(order_constraint=0, min_hits=5, min_weighted_hits=0, max_gap=200)
+        for k, v in params.items():
+            if k in cur:
+                try:
+                    cur[k] = _stoi(v)
+                except ValueError:
+                    import sys
+                    print(f"Warning: invalid integer '{v}' passed for parameter {k}", file=sys.stderr)
+        _check(lib().ckm_set_params(self._h, cur["order_constraint"], cur["min_hits"], cur["min_weighted_hits"], cur["max_gap"]))
+
+    def get_parameters(self) -> dict:
+        v = [C.c_int() for _ in range(4)]
+        lib().ckm_get_params(self._h, *[C.byref(x) for x in v])
+        return dict(zip(self._PARAM_NAMES, (x.value for x in v)))
+
+    # -- metadata --------------------------------------------------------------------------------------
+    def function_at_index(self, i: int) -> str:
+        return lib().ckm_function_at_index(self._h, i).decode()
+
+    def otu_at_index(self, i: int) -> str:
+        return lib().ckm_otu_at_index(self._h, i).decode()
+
+    @property
+    def function_count(self) -> int:
+        return lib().ckm_function_count(self._h)
+
+    @property
+    def num_sigs(self) -> int:
+        return lib().ckm_num_sigs(self._h)
+
+    @property
+    def slot_bytes(self) -> int:
+        return lib().ckm_table_slot_bytes(self._h)
+
+    @property
+    def stream(self) -> int:
+        return lib().ckm_stream(self._h) or 0
+
+    @property
+    def launch_count(self) -> int:
+        return lib().ckm_launch_count(self._h)
+
+    def profile_enable(self, on: bool = True):
+        lib().ckm_profile_enable(self._h, int(on))
+
+    def profile_read(self):
+        """(probe_ms, scan_ms, batches) summed since the last read; device-timed with CUDA events."""
+        p, s, n = C.c_double(), C.c_double(), C.c_uint64()
+        _check(lib().ckm_profile_read(self._h, C.byref(p), C.byref(s), C.byref(n)))
+        return p.value, s.value, n.value
+
+    def synchronize(self):
+        _check(lib().ckm_synchronize(self._h))
+
+    # -- S4 (+B1) over a batch ---------------------------------------------------------------------------
+    def process_aa_seq_batch(self, residues: np.ndarray, offsets: np.ndarray, flags: int) -> dict:
+        """process_aa_seq / process_aa_seq_hits (+ find_best_call) for every sequence of the batch
+        (kguts.cc:879-908, 1008-1199).  Host arrays in, numpy copies of the CSR results out."""
+        residues = np.ascontiguousarray(residues, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        n = len(offsets) - 1
+        o = BatchOutC()
+        _check(lib().ckm_call_batch(self._h, residues.ctypes.data, offsets.ctypes.data, n, flags, C.byref(o)))
+        r = {"n": n, "n_probes": o.n_probes, "n_hits": o.n_hits}
+        for name, dt in (("call", CALL_DT), ("hit", HIT_DT), ("otu", OTU_DT)):
+            offp = getattr(o, f"{name}_offsets")
+            if offp:
+                off = _arr(offp, n + 1, np.uint64)
+                r[f"{name}_offsets"] = off
+                r[f"{name}s"] = _arr(getattr(o, f"{name}s"), int(off[-1]), dt)
+        if o.best:
+            r["best"] = _arr(o.best, n, BEST_DT)
+        return r
+
+    def call_batch_raw(self, residues_ptr: int, offsets_ptr: int, n: int, flags: int) -> BatchOutC:
+        """Same call with caller-owned (ideally pinned) host pointers and no result copies: for timing."""
+        o = BatchOutC()
+        _check(lib().ckm_call_batch(self._h, residues_ptr, offsets_ptr, n, flags, C.byref(o)))
+        return o
+
+    def call_batch_device(self, d_residues: int, d_offsets: int, n: int, total: int, max_len: int, flags: int):
+        _check(lib().ckm_call_batch_device(self._h, d_residues, d_offsets, n, total, max_len, flags))
+
+    def device_results(self) -> DeviceOutC:
+        o = DeviceOutC()
+        _check(lib().ckm_device_results(self._h, C.byref(o)))
+        return o
+
+    def read_totals(self):
+        """(probes, hits, calls) of the last batch."""
+        t = (C.c_uint64 * 3)()
+        _check(lib().ckm_read_totals(self._h, t))
+        return int(t[0]), int(t[1]), int(t[2])
+
+    def best_function(self, best_rec) -> str:
+        """The `function` string find_best_call returns (kguts.cc:1160, 1176-1196)."""
+        if best_rec["flags"] & BEST_AMBIG:
+            f1 = self.function_at_index(int(best_rec["ambig_a"]))
+            f2 = self.function_at_index(int(best_rec["ambig_b"]))
+            if f2.encode() > f1.encode():
+                f1, f2 = f2, f1
+            return f1 + " ?? " + f2
+        if best_rec["function_index"] >= 0:
+            return self.function_at_index(int(best_rec["function_index"]))
+        return ""
+
+
+def _stoi(v) -> int:
+    """std::stoi semantics for the cases set_parameters meets: leading whitespace, optional sign, digits,
+    trailing junk ignored; nothing parseable -> ValueError."""
+    import re
+    m = re.match(r"\s*([+-]?\d+)", str(v))
+    if not m:
+        raise ValueError(v)
+    return int(m.group(1))

@@ -1,0 +1,669 @@
+// libckm.so -- context, table loader and the C ABI declared in include/ckm.h.
+//
+// Host side of the drop-in boundary: what a request handler used to do through a per-thread KmerGuts
+// (kguts.h:334-372) it now does with one batch call on a ckm_ctx.  No CPU fallback exists: every
+// compute entry point launches the sm_100a kernels or fails with CKM_ECUDA.
+#include <cuda_runtime.h>
+#include <fcntl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "ckm_common.cuh"
+#include "ckm_ctx.h"
+#include "ckm_probe.cuh"
+#include "ckm_scan.cuh"
+#include "ckm_util.cuh"
+
+using namespace ckm;
+
+// ---------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+int ckm_fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" const char *ckm_last_error(void) { return g_err; }
+
+// ---------------------------------------------------------------------------------------------------
+// buffers
+// ---------------------------------------------------------------------------------------------------
+int DevBuf::ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        e = cudaMalloc(&p, bytes);
+        want = bytes;
+    }
+    if (e != cudaSuccess) return ckm_fail(CKM_ENOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    cap = want;
+    return 0;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+int PinBuf::ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess) return ckm_fail(CKM_ENOMEM, "cudaMallocHost(%zu): %s", want, cudaGetErrorString(e));
+    cap = want;
+    return 0;
+}
+void PinBuf::release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// table load: verbatim upload, then repack on the device (see ckm_common.cuh for the layout)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_table_kernel(const uint64_t *__restrict__ raw /* 3 x u64 per slot */, uint64_t num_sigs, uint4 *__restrict__ packed,
+                  unsigned int *__restrict__ misfit) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= num_sigs) return;
+    const uint64_t k = raw[3 * i], a = raw[3 * i + 1], b = raw[3 * i + 2];
+    uint4 v;
+    if (k > CKM_MAX_ENCODED) {  // empty (kguts.cc:587, 596)
+        v.x = 0;
+        v.y = 0x8u;
+        v.z = 0;
+        v.w = 0;
+    } else {
+        const int32_t oI = (int32_t)(uint32_t)a;
+        const uint32_t avg = (uint32_t)(a >> 32) & 0xFFFFu;
+        const uint32_t fI = (uint32_t)b;
+        const uint32_t wt = (uint32_t)(b >> 32);
+        const uint32_t o1 = (uint32_t)(oI + 1);
+        if (fI >= kPackedFieldLimit || oI < -1 || o1 >= kPackedFieldLimit) atomicOr(misfit, 1u);
+        v.x = (uint32_t)k;
+        v.y = (uint32_t)(k >> 32) | (avg << 4) | ((o1 & 0xFFFu) << 20);
+        v.z = wt;
+        v.w = (fI & (kPackedFieldLimit - 1)) | ((o1 >> 12) << 22);
+    }
+    packed[i] = v;
+}
+
+static int check_cuda(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return 0;
+    return ckm_fail(CKM_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+#define CU(x)                                  \
+    do {                                       \
+        int rc_ = check_cuda((x), #x);         \
+        if (rc_) return rc_;                   \
+    } while (0)
+#define RC(x)                \
+    do {                     \
+        int rc_ = (x);       \
+        if (rc_) return rc_; \
+    } while (0)
+
+static int select_device(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        (void)cudaGetLastError();
+        return ckm_fail(CKM_ECUDA, "no CUDA device available (%s); libckm has no CPU fallback",
+                        e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= count) return ckm_fail(CKM_EINVAL, "device %d out of range (0..%d)", device, count - 1);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return ckm_fail(CKM_ECUDA, "device %d is sm_%d%d; libckm is built for sm_100a only", device, prop.major, prop.minor);
+    return 0;
+}
+
+static int upload_table(ckm_ctx *c, const ckm_image_header_t *hdr) {
+    const uint64_t n = hdr->num_sigs;
+    const uint8_t *src = reinterpret_cast<const uint8_t *>(hdr + 1);
+    const size_t raw_bytes = (size_t)n * kRawSlotBytes;
+    DevBuf raw;
+    RC(raw.ensure(raw_bytes + 64));
+    const size_t chunk = (size_t)1 << 28;
+    for (size_t o = 0; o < raw_bytes; o += chunk)
+        CU(cudaMemcpyAsync((uint8_t *)raw.p + o, src + o, std::min(chunk, raw_bytes - o), cudaMemcpyHostToDevice, c->stream));
+    DevBuf packed, flag;
+    RC(packed.ensure((size_t)n * kPackedSlotBytes + 64));
+    RC(flag.ensure(256));
+    CU(cudaMemsetAsync(flag.p, 0, 4, c->stream));
+    if (n) {
+        const uint64_t blocks = (n + 255) / 256;
+        pack_table_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>((const uint64_t *)raw.p, n, (uint4 *)packed.p,
+                                                                    (unsigned int *)flag.p);
+        c->launches++;
+    }
+    unsigned int misfit = 0;
+    CU(cudaMemcpyAsync(&misfit, flag.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    flag.release();
+    if (misfit || c->force_raw) {
+        packed.release();
+        c->table = raw;
+        c->slot_bytes = kRawSlotBytes;
+    } else {
+        raw.release();
+        c->table = packed;
+        c->slot_bytes = kPackedSlotBytes;
+    }
+    c->num_sigs = n;
+    c->magic = n ? (uint64_t)((((unsigned __int128)1) << 64) / n) : 0;
+    return 0;
+}
+
+// T2: kmer_image.cc:87-105
+static int validate_image(const void *image, size_t bytes, const char *name) {
+    if (!image || bytes < sizeof(ckm_image_header_t))
+        return ckm_fail(CKM_EFORMAT, "Version mismatch for file %s: file size does not match", name);
+    const ckm_image_header_t *h = (const ckm_image_header_t *)image;
+    if ((unsigned long long)bytes != sizeof(ckm_sig_kmer_t) * (unsigned long long)h->num_sigs + sizeof(ckm_image_header_t))
+        return ckm_fail(CKM_EFORMAT, "Version mismatch for file %s: file size does not match", name);
+    if (h->version != 1)
+        return ckm_fail(CKM_EFORMAT, "Version mismatch for file %s: file has %lld code has %lld", name, (long long)h->version, 1LL);
+    if (h->entry_size != sizeof(ckm_sig_kmer_t))
+        return ckm_fail(CKM_EFORMAT, "Version mismatch for file %s: file has entry size %lld code has %lld", name,
+                        (long long)h->entry_size, (long long)sizeof(ckm_sig_kmer_t));
+    if (h->num_sigs == 0) return ckm_fail(CKM_EFORMAT, "image %s has zero buckets", name);
+    return 0;
+}
+
+static int ctx_create(int device, ckm_ctx **out) {
+    RC(select_device(device));
+    ckm_ctx *c = new ckm_ctx();
+    c->device = device;
+    const char *fr = getenv("CKM_FORCE_RAW_SLOTS");
+    c->force_raw = fr && fr[0] == '1';
+    if (check_cuda(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
+        delete c;
+        return CKM_ECUDA;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    c->sm_count = prop.multiProcessorCount;
+    ckm_set_default_params(c);
+    *out = c;
+    return 0;
+}
+
+extern "C" int ckm_open_image(const void *image, size_t image_bytes, int device, const char *const *function_names,
+                              int32_t n_functions, const char *const *otu_names, int32_t n_otus, ckm_ctx **out) {
+    if (!out) return ckm_fail(CKM_EINVAL, "out is NULL");
+    *out = nullptr;
+    RC(validate_image(image, image_bytes, "<memory>"));
+    ckm_ctx *c = nullptr;
+    RC(ctx_create(device, &c));
+    int rc = upload_table(c, (const ckm_image_header_t *)image);
+    if (rc) {
+        ckm_close(c);
+        return rc;
+    }
+    for (int32_t i = 0; i < n_functions; i++) c->functions.emplace_back(function_names[i]);
+    for (int32_t i = 0; i < n_otus; i++) c->otu_names.emplace_back(otu_names[i]);
+    *out = c;
+    return 0;
+}
+
+// load_indexed_ar, kguts.cc:544-575: "<idx>\t<text>\n", dense and in order; the last character of
+// every line (the newline fgets leaves) is dropped.
+static int load_index_file(const std::string &path, std::vector<std::string> &out) {
+    FILE *fp = fopen(path.c_str(), "r");
+    if (!fp) return ckm_fail(CKM_EIO, "could not open %s", path.c_str());
+    char line[1000];
+    int j;
+    while (fscanf(fp, "%d\t", &j) == 1 && fgets(line, 1000, fp)) {
+        if ((int)out.size() != j) {
+            fclose(fp);
+            return ckm_fail(CKM_EFORMAT, "Your index must be dense and in order (%s, should be %d)", path.c_str(), (int)out.size());
+        }
+        size_t l = strlen(line);
+        out.emplace_back(line, l ? l - 1 : 0);
+        if (out.size() >= 1000000) {  // MAX_FUNC_OI_INDEX, kguts.cc:541
+            fclose(fp);
+            return ckm_fail(CKM_EFORMAT, "index %s has more than 1000000 entries", path.c_str());
+        }
+    }
+    fclose(fp);
+    return 0;
+}
+
+extern "C" int ckm_open(const char *kmer_dir, int device, ckm_ctx **out) {
+    if (!out || !kmer_dir) return ckm_fail(CKM_EINVAL, "NULL argument");
+    *out = nullptr;
+    const std::string dir(kmer_dir), file = dir + "/kmer.table.mem_map";
+    int fd = open(file.c_str(), O_RDONLY);
+    if (fd < 0) return ckm_fail(CKM_EIO, "open %s: %s", file.c_str(), strerror(errno));
+    struct stat sb;
+    if (fstat(fd, &sb) < 0) {
+        close(fd);
+        return ckm_fail(CKM_EIO, "stat %s failed: %s", file.c_str(), strerror(errno));
+    }
+    void *img = mmap(0, (size_t)sb.st_size, PROT_READ, MAP_SHARED, fd, 0);
+    close(fd);
+    if (img == MAP_FAILED) return ckm_fail(CKM_EIO, "mmap of kmer_table %s failed: %s", file.c_str(), strerror(errno));
+    int rc = validate_image(img, (size_t)sb.st_size, file.c_str());
+    ckm_ctx *c = nullptr;
+    if (!rc) rc = ctx_create(device, &c);
+    if (!rc) rc = upload_table(c, (const ckm_image_header_t *)img);
+    munmap(img, (size_t)sb.st_size);
+    if (!rc) rc = load_index_file(dir + "/function.index", c->functions);
+    if (!rc) rc = load_index_file(dir + "/otu.index", c->otu_names);
+    if (rc) {
+        if (c) ckm_close(c);
+        return rc;
+    }
+    *out = c;
+    return 0;
+}
+
+extern "C" void ckm_close(ckm_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    c->free_all();
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" const char *ckm_function_at_index(const ckm_ctx *c, int32_t i) {
+    if (i < 0 || (size_t)i >= c->functions.size()) return "INVALID_OFFSET";
+    return c->functions[i].c_str();
+}
+extern "C" const char *ckm_otu_at_index(const ckm_ctx *c, int32_t i) {
+    if (i < 0 || (size_t)i >= c->otu_names.size()) return "INVALID_OFFSET";
+    return c->otu_names[i].c_str();
+}
+extern "C" int32_t ckm_function_count(const ckm_ctx *c) { return (int32_t)c->functions.size(); }
+extern "C" int32_t ckm_otu_count(const ckm_ctx *c) { return (int32_t)c->otu_names.size(); }
+extern "C" uint64_t ckm_num_sigs(const ckm_ctx *c) { return c->num_sigs; }
+extern "C" int ckm_table_slot_bytes(const ckm_ctx *c) { return c->slot_bytes; }
+extern "C" void *ckm_stream(ckm_ctx *c) { return (void *)c->stream; }
+extern "C" uint64_t ckm_launch_count(const ckm_ctx *c) { return c->launches; }
+extern "C" int ckm_synchronize(ckm_ctx *c) {
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// parameters (Q1)
+// ---------------------------------------------------------------------------------------------------
+extern "C" void ckm_set_default_params(ckm_ctx *c) {
+    c->prm.order_constraint = 0;
+    c->prm.min_hits = 5;
+    c->prm.min_weighted_hits = 0;
+    c->prm.max_gap = 200;
+}
+extern "C" int ckm_set_params(ckm_ctx *c, int order_constraint, int min_hits, int min_weighted_hits, int max_gap) {
+    // min_hits < 1 makes the reference read before its hit buffer (kguts.cc:772 with num_hits == 0):
+    // undefined there, rejected here.
+    if (min_hits < 1) return ckm_fail(CKM_EINVAL, "min_hits=%d: the reference's behaviour is undefined below 1", min_hits);
+    c->prm.order_constraint = order_constraint;
+    c->prm.min_hits = min_hits;
+    c->prm.min_weighted_hits = min_weighted_hits;
+    c->prm.max_gap = max_gap;
+    return 0;
+}
+extern "C" void ckm_get_params(const ckm_ctx *c, int *oc, int *mh, int *mwh, int *mg) {
+    if (oc) *oc = c->prm.order_constraint;
+    if (mh) *mh = c->prm.min_hits;
+    if (mwh) *mwh = c->prm.min_weighted_hits;
+    if (mg) *mg = c->prm.max_gap;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// statics (E1/E2 on the host, for formatters and builders)
+// ---------------------------------------------------------------------------------------------------
+static const char kProtAlpha[21] = "ACDEFGHIKLMNPQRSTVWY";
+static inline int aa_off(char ch) {
+    const char *p = ch ? strchr(kProtAlpha, ch) : nullptr;
+    return p ? (int)(p - kProtAlpha) : 20;
+}
+extern "C" uint64_t ckm_encoded_aa_kmer(const char *p) {
+    uint64_t k = 0;
+    for (int j = 0; j < CKM_KMER_SIZE; j++) {
+        const int o = aa_off(p[j]);
+        if (o >= 20) return CKM_MAX_ENCODED + 1;
+        k = k * 20 + (uint64_t)o;
+    }
+    return k;
+}
+extern "C" void ckm_decoded_kmer(uint64_t k, char decoded[9]) {
+    decoded[CKM_KMER_SIZE] = 0;
+    for (int i = CKM_KMER_SIZE - 1; i >= 0; i--) {
+        decoded[i] = kProtAlpha[k % 20];
+        k /= 20;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// image builder: KmerGuts(dir, nbuckets) + insert_kmer + save_kmer_hash_table (kguts.cc:77-115,
+// 166-171, 188-234) on the host.  Produces the reference's file bytes; not part of the query path.
+// ---------------------------------------------------------------------------------------------------
+extern "C" int ckm_image_build(uint64_t nbuckets, uint64_t n, const uint64_t *keys, const int32_t *fI, const int32_t *oI,
+                               const uint16_t *avg, const float *wt, void *image_out, size_t image_bytes) {
+    const size_t need = sizeof(ckm_image_header_t) + (size_t)nbuckets * sizeof(ckm_sig_kmer_t);
+    if (!image_out || image_bytes != need) return ckm_fail(CKM_EINVAL, "image buffer must be exactly %zu bytes", need);
+    memset(image_out, 0, need);
+    ckm_image_header_t *h = (ckm_image_header_t *)image_out;
+    h->num_sigs = nbuckets;
+    h->entry_size = sizeof(ckm_sig_kmer_t);
+    h->version = 1;
+    ckm_sig_kmer_t *s = (ckm_sig_kmer_t *)(h + 1);
+    for (uint64_t i = 0; i < nbuckets; i++) s[i].which_kmer = CKM_MAX_ENCODED + 1;
+    uint64_t loaded = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        if (keys[i] > CKM_MAX_ENCODED) continue;  // kguts.cc:206-210
+        uint64_t e = keys[i] % nbuckets;
+        while (s[e].which_kmer <= CKM_MAX_ENCODED) e = (e + 1) % nbuckets;
+        loaded++;
+        if ((long long)loaded >= (long long)nbuckets / 2)  // kguts.cc:213-216 (the reference exits)
+            return ckm_fail(CKM_EINVAL, "Your Kmer hash is half-full; use a larger bucket count");
+        s[e].which_kmer = keys[i];
+        s[e].avg_from_end = avg[i];
+        s[e].function_index = fI[i];
+        s[e].otu_index = oI[i];
+        s[e].function_wt = wt[i];
+    }
+    return 0;
+}
+
+extern "C" int ckm_host_alloc(void **p, size_t bytes) {
+    cudaError_t e = cudaMallocHost(p, bytes);
+    if (e != cudaSuccess) return ckm_fail(CKM_ENOMEM, "cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(e));
+    return 0;
+}
+extern "C" void ckm_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the calling path
+// ---------------------------------------------------------------------------------------------------
+static int prefix_sum(ckm_ctx *c, const uint32_t *d_in, uint64_t n, uint64_t *d_out /* n+1 */) {
+    const uint64_t nb = std::max<uint64_t>(1, (n + kPsTile - 1) / kPsTile);
+    RC(c->ps_blocks.ensure(nb * 8));
+    ps_block_sums<<<(unsigned)nb, kPsThreads, 0, c->stream>>>(d_in, n, (uint64_t *)c->ps_blocks.p);
+    ps_spine<<<1, kPsThreads, 0, c->stream>>>((uint64_t *)c->ps_blocks.p, nb);
+    ps_finish<<<(unsigned)nb, kPsThreads, 0, c->stream>>>(d_in, n, (const uint64_t *)c->ps_blocks.p, d_out);
+    c->launches += 3;
+    return 0;
+}
+
+// K1 + K2 over a batch that is already in HBM.  Leaves regions / per-protein counters on the device.
+static int run_device(ckm_ctx *c, const uint8_t *d_res, const uint64_t *d_off, uint32_t n, uint64_t total, uint32_t max_len,
+                      uint32_t flags) {
+    c->cur_n = n;
+    c->cur_total = total;
+    c->cur_flags = flags;
+    c->cur_off = d_off;
+    const bool want_scan = flags & (CKM_WANT_CALLS | CKM_WANT_OTU | CKM_WANT_BEST);
+    const bool general = want_scan && (c->prm.order_constraint != 0 || max_len == 0 || max_len > kHitCap + CKM_KMER_SIZE);
+    const bool want_keys = flags & CKM_WANT_HITS;
+    const bool want_avg = (flags & CKM_WANT_HITS) || (want_scan && c->prm.order_constraint != 0);
+    const uint64_t ncall_slots = total / (uint64_t)std::max(1, c->prm.min_hits) + n + 1;
+
+    RC(c->totals.ensure(64));
+    RC(c->hits.ensure((total + 1) * sizeof(HitRec)));
+    RC(c->n_hits.ensure(((size_t)n + 1) * 4));
+    if (want_keys) RC(c->hit_keys.ensure((total + 1) * 8));
+    if (want_avg) RC(c->hit_avg.ensure((total + 1) * 2));
+    if (want_scan) {
+        RC(c->calls.ensure(ncall_slots * sizeof(ckm_call_t)));
+        RC(c->n_calls.ensure(((size_t)n + 1) * 4));
+        if (general) RC(c->stored_idx.ensure((total + 1) * 4));
+        if (flags & CKM_WANT_BEST) {
+            RC(c->calls_work.ensure(ncall_slots * sizeof(ckm_call_t)));
+            RC(c->best.ensure(((size_t)n + 1) * sizeof(ckm_best_t)));
+        }
+        if (flags & CKM_WANT_OTU) {
+            RC(c->otus.ensure((total + 1) * sizeof(ckm_otu_t)));
+            RC(c->n_otus.ensure(((size_t)n + 1) * 4));
+        }
+    }
+    CU(cudaMemsetAsync(c->totals.p, 0, 64, c->stream));
+    if (n == 0) return 0;
+
+    ckm_ctx::ProfEv pe = {nullptr, nullptr, nullptr, false};
+    if (c->profiling) {
+        CU(cudaEventCreate(&pe.e0));
+        CU(cudaEventCreate(&pe.e1));
+        CU(cudaEventCreate(&pe.e2));
+        CU(cudaEventRecord(pe.e0, c->stream));
+    }
+    TableView tv;
+    tv.slots = c->table.p;
+    tv.num_sigs = c->num_sigs;
+    tv.magic = c->magic;
+    {
+        const uint32_t warps_per_block = kProbeThreads / 32;
+        uint64_t blocks = ((uint64_t)n + warps_per_block - 1) / warps_per_block;
+        blocks = std::min<uint64_t>(blocks, (uint64_t)c->sm_count * 8);
+        if (c->slot_bytes == kPackedSlotBytes)
+            probe_kernel<true><<<(unsigned)blocks, kProbeThreads, 0, c->stream>>>(
+                tv, d_res, d_off, n, (HitRec *)c->hits.p, want_keys ? (uint64_t *)c->hit_keys.p : nullptr,
+                want_avg ? (uint16_t *)c->hit_avg.p : nullptr, (uint32_t *)c->n_hits.p, (unsigned long long *)c->totals.p);
+        else
+            probe_kernel<false><<<(unsigned)blocks, kProbeThreads, 0, c->stream>>>(
+                tv, d_res, d_off, n, (HitRec *)c->hits.p, want_keys ? (uint64_t *)c->hit_keys.p : nullptr,
+                want_avg ? (uint16_t *)c->hit_avg.p : nullptr, (uint32_t *)c->n_hits.p, (unsigned long long *)c->totals.p);
+        c->launches++;
+    }
+    if (c->profiling) CU(cudaEventRecord(pe.e1, c->stream));
+    if (want_scan) {
+        ScanArgs a;
+        a.offsets = d_off;
+        a.hits = (const HitRec *)c->hits.p;
+        a.hit_avg = (c->prm.order_constraint != 0) ? (const uint16_t *)c->hit_avg.p : nullptr;
+        a.n_hits = (const uint32_t *)c->n_hits.p;
+        a.stored_idx = general ? (uint32_t *)c->stored_idx.p : nullptr;
+        a.calls = (ckm_call_t *)c->calls.p;
+        a.calls_work = (flags & CKM_WANT_BEST) ? (ckm_call_t *)c->calls_work.p : nullptr;
+        a.n_calls = (uint32_t *)c->n_calls.p;
+        a.otus = (flags & CKM_WANT_OTU) ? (ckm_otu_t *)c->otus.p : nullptr;
+        a.n_otus = (flags & CKM_WANT_OTU) ? (uint32_t *)c->n_otus.p : nullptr;
+        a.best = (flags & CKM_WANT_BEST) ? (ckm_best_t *)c->best.p : nullptr;
+        a.totals = (unsigned long long *)c->totals.p;
+        a.n = n;
+        a.prm = c->prm;
+        const unsigned blocks = (n + kScanThreads - 1) / kScanThreads;
+        if (general)
+            scan_kernel<true><<<blocks, kScanThreads, 0, c->stream>>>(a);
+        else
+            scan_kernel<false><<<blocks, kScanThreads, 0, c->stream>>>(a);
+        c->launches++;
+    }
+    if (c->profiling) {
+        CU(cudaEventRecord(pe.e2, c->stream));
+        pe.has_scan = want_scan;
+        c->prof.push_back(pe);
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" void ckm_profile_enable(ckm_ctx *c, int on) { c->profiling = on != 0; }
+
+extern "C" int ckm_profile_read(ckm_ctx *c, double *probe_ms, double *scan_ms, uint64_t *batches) {
+    CU(cudaStreamSynchronize(c->stream));
+    double p = 0, s = 0;
+    for (auto &e : c->prof) {
+        float a = 0, b = 0;
+        CU(cudaEventElapsedTime(&a, e.e0, e.e1));
+        CU(cudaEventElapsedTime(&b, e.e1, e.e2));
+        p += a;
+        if (e.has_scan) s += b;
+        cudaEventDestroy(e.e0);
+        cudaEventDestroy(e.e1);
+        cudaEventDestroy(e.e2);
+    }
+    if (probe_ms) *probe_ms = p;
+    if (scan_ms) *scan_ms = s;
+    if (batches) *batches = c->prof.size();
+    c->prof.clear();
+    return 0;
+}
+
+extern "C" int ckm_call_batch_device(ckm_ctx *c, const void *d_residues, const uint64_t *d_offsets, uint32_t n,
+                                     uint64_t total_residues, uint32_t max_len, uint32_t flags) {
+    if (!c) return ckm_fail(CKM_EINVAL, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    return run_device(c, (const uint8_t *)d_residues, d_offsets, n, total_residues, max_len, flags);
+}
+
+extern "C" int ckm_device_results(ckm_ctx *c, ckm_device_out_t *out) {
+    if (!c || !out) return ckm_fail(CKM_EINVAL, "NULL argument");
+    memset(out, 0, sizeof *out);
+    out->n = c->cur_n;
+    out->d_n_hits = (const uint32_t *)c->n_hits.p;
+    out->d_n_calls = (const uint32_t *)c->n_calls.p;
+    out->d_calls = (const ckm_call_t *)c->calls.p;
+    out->d_best = (const ckm_best_t *)c->best.p;
+    out->d_totals = (const uint64_t *)c->totals.p;
+    out->min_hits_for_call_base = c->prm.min_hits;
+    return 0;
+}
+
+extern "C" int ckm_read_totals(ckm_ctx *c, uint64_t totals[3]) {
+    if (!c || !totals) return ckm_fail(CKM_EINVAL, "NULL argument");
+    if (!c->totals.p) return ckm_fail(CKM_ESTATE, "no batch has been run on this ctx");
+    CU(cudaMemcpyAsync(totals, c->totals.p, 24, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int ckm_call_batch(ckm_ctx *c, const char *residues, const uint64_t *offsets, uint32_t n, uint32_t flags,
+                              ckm_batch_out_t *out) {
+    if (!c || !out || !offsets || (n && !residues && offsets[n] != 0)) return ckm_fail(CKM_EINVAL, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    memset(out, 0, sizeof *out);
+    out->n = n;
+    uint64_t total = offsets[n];
+    uint32_t max_len = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (offsets[i + 1] < offsets[i]) return ckm_fail(CKM_EINVAL, "offsets must be non-decreasing (at %u)", i);
+        const uint64_t l = offsets[i + 1] - offsets[i];
+        if (l > 500000000ull) return ckm_fail(CKM_EINVAL, "sequence %u longer than MAX_SEQ_LEN", i);  // kmer_params.h:6
+        max_len = std::max<uint32_t>(max_len, (uint32_t)l);
+    }
+    total -= offsets[0];
+    // H2D: residues (+16 B of slack, zeroed) and offsets rebased to 0
+    RC(c->in_res.ensure(total + 32));
+    RC(c->in_off.ensure(((size_t)n + 1) * 8));
+    if (total) CU(cudaMemcpyAsync(c->in_res.p, residues + offsets[0], total, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync((uint8_t *)c->in_res.p + total, 0, 32, c->stream));
+    const uint64_t *h_off = offsets;
+    if (offsets[0] != 0) {
+        RC(c->h_off.ensure(((size_t)n + 1) * 8));
+        uint64_t *t = (uint64_t *)c->h_off.p;
+        for (uint32_t i = 0; i <= n; i++) t[i] = offsets[i] - offsets[0];
+        h_off = t;
+    }
+    CU(cudaMemcpyAsync(c->in_off.p, h_off, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    RC(run_device(c, (const uint8_t *)c->in_res.p, (const uint64_t *)c->in_off.p, n, total, std::max(max_len, 1u), flags));
+
+    // totals decide the size of the compacted outputs
+    RC(c->h_totals.ensure(64));
+    uint64_t *ht = (uint64_t *)c->h_totals.p;
+    CU(cudaMemcpyAsync(ht, c->totals.p, 24, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    out->n_probes = ht[0];
+    out->n_hits = ht[1];
+    const uint64_t n_calls_total = ht[2];
+    const bool want_scan = flags & (CKM_WANT_CALLS | CKM_WANT_OTU | CKM_WANT_BEST);
+    const unsigned tb = 256;
+
+    if (flags & CKM_WANT_HITS) {
+        RC(c->hit_off.ensure(((size_t)n + 1) * 8));
+        RC(prefix_sum(c, (const uint32_t *)c->n_hits.p, n, (uint64_t *)c->hit_off.p));
+        RC(c->hits_out.ensure((out->n_hits + 1) * sizeof(ckm_hit_t)));
+        if (n) {
+            export_hits_kernel<<<(unsigned)(((uint64_t)n * 32 + tb - 1) / tb), tb, 0, c->stream>>>(
+                (const uint64_t *)c->in_off.p, (const HitRec *)c->hits.p, (const uint64_t *)c->hit_keys.p,
+                (const uint16_t *)c->hit_avg.p, (const uint64_t *)c->hit_off.p, n, (ckm_hit_t *)c->hits_out.p);
+            c->launches++;
+        }
+        RC(c->h_hit_off.ensure(((size_t)n + 1) * 8));
+        RC(c->h_hits.ensure((out->n_hits + 1) * sizeof(ckm_hit_t)));
+        CU(cudaMemcpyAsync(c->h_hit_off.p, c->hit_off.p, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (out->n_hits)
+            CU(cudaMemcpyAsync(c->h_hits.p, c->hits_out.p, out->n_hits * sizeof(ckm_hit_t), cudaMemcpyDeviceToHost, c->stream));
+        out->hit_offsets = (const uint64_t *)c->h_hit_off.p;
+        out->hits = (const ckm_hit_t *)c->h_hits.p;
+    }
+    if (flags & CKM_WANT_CALLS) {
+        RC(c->call_off.ensure(((size_t)n + 1) * 8));
+        RC(prefix_sum(c, (const uint32_t *)c->n_calls.p, n, (uint64_t *)c->call_off.p));
+        RC(c->calls_out.ensure((n_calls_total + 1) * sizeof(ckm_call_t)));
+        if (n) {
+            export_calls_kernel<<<(n + tb - 1) / tb, tb, 0, c->stream>>>((const uint64_t *)c->in_off.p,
+                                                                         (const ckm_call_t *)c->calls.p,
+                                                                         (const uint64_t *)c->call_off.p, n, c->prm.min_hits,
+                                                                         (ckm_call_t *)c->calls_out.p);
+            c->launches++;
+        }
+        RC(c->h_call_off.ensure(((size_t)n + 1) * 8));
+        RC(c->h_calls.ensure((n_calls_total + 1) * sizeof(ckm_call_t)));
+        CU(cudaMemcpyAsync(c->h_call_off.p, c->call_off.p, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (n_calls_total)
+            CU(cudaMemcpyAsync(c->h_calls.p, c->calls_out.p, n_calls_total * sizeof(ckm_call_t), cudaMemcpyDeviceToHost, c->stream));
+        out->call_offsets = (const uint64_t *)c->h_call_off.p;
+        out->calls = (const ckm_call_t *)c->h_calls.p;
+    }
+    if (flags & CKM_WANT_OTU) {
+        RC(c->otu_off.ensure(((size_t)n + 1) * 8));
+        RC(prefix_sum(c, (const uint32_t *)c->n_otus.p, n, (uint64_t *)c->otu_off.p));
+        RC(c->h_otu_off.ensure(((size_t)n + 1) * 8));
+        CU(cudaMemcpyAsync(c->h_otu_off.p, c->otu_off.p, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        const uint64_t n_otus_total = ((const uint64_t *)c->h_otu_off.p)[n];
+        RC(c->otus_out.ensure((n_otus_total + 1) * sizeof(ckm_otu_t)));
+        if (n) {
+            export_otus_kernel<<<(n + tb - 1) / tb, tb, 0, c->stream>>>((const uint64_t *)c->in_off.p, (const ckm_otu_t *)c->otus.p,
+                                                                        (const uint64_t *)c->otu_off.p, n, (ckm_otu_t *)c->otus_out.p);
+            c->launches++;
+        }
+        RC(c->h_otus.ensure((n_otus_total + 1) * sizeof(ckm_otu_t)));
+        if (n_otus_total)
+            CU(cudaMemcpyAsync(c->h_otus.p, c->otus_out.p, n_otus_total * sizeof(ckm_otu_t), cudaMemcpyDeviceToHost, c->stream));
+        out->otu_offsets = (const uint64_t *)c->h_otu_off.p;
+        out->otus = (const ckm_otu_t *)c->h_otus.p;
+    }
+    if (flags & CKM_WANT_BEST) {
+        RC(c->h_best.ensure(((size_t)n + 1) * sizeof(ckm_best_t)));
+        if (n) CU(cudaMemcpyAsync(c->h_best.p, c->best.p, (size_t)n * sizeof(ckm_best_t), cudaMemcpyDeviceToHost, c->stream));
+        out->best = (const ckm_best_t *)c->h_best.p;
+    }
+    (void)want_scan;
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,82 @@
+// Shared device-side definitions for the signature-k-mer calling path (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ckm.h"
+
+namespace ckm {
+
+// ---------------------------------------------------------------------------------------------------
+// Table layouts in HBM.  The reference file stores 24-byte slots behind a 24-byte header
+// (kmer_image.h:11-23), so half of them straddle a 32-byte DRAM sector.  At load time the slots are
+// repacked, in the SAME order and bucket count (so probe sequences and therefore results are
+// unchanged), into 16-byte slots -- two per sector, never straddling:
+//
+//   w0 (u64): [0,35)  which_kmer      (valid keys are < 20^8 < 2^35)
+//             [35]    empty flag      (reference: which_kmer > MAX_ENCODED, kguts.cc:587,596)
+//             [36,52) avg_from_end
+//             [52,64) (otu_index+1) low 12 bits
+//   w1 (u64): [0,32)  function_wt (f32 bits)
+//             [32,54) function_index  (22 bits; function.index holds < 1e6 entries, kguts.cc:541)
+//             [54,64) (otu_index+1) high 10 bits
+//
+// If any occupied slot does not fit (function_index outside [0,2^22) or otu_index outside
+// [-1,2^22-1)) the loader keeps the verbatim 24-byte slots and the kernels run their RAW
+// instantiation; results are identical either way.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kPackedSlotBytes = 16;
+constexpr int kRawSlotBytes = 24;
+constexpr uint32_t kPackedFieldLimit = 1u << 22;
+
+struct TableView {
+    const void *slots;   // packed: uint4[num_sigs]; raw: 24-byte ckm_sig_kmer_t[num_sigs] (8-byte aligned)
+    uint64_t num_sigs;
+    uint64_t magic;      // floor(2^64 / num_sigs), for key % num_sigs without a divide
+};
+
+// One table hit as the ordered scoring scan consumes it (KmerHit, kguts.h:154-163, minus the key).
+struct __align__(16) HitRec {
+    uint32_t pos;  // from0_in_prot
+    uint32_t fI;
+    float wt;
+    int32_t oI;
+};
+
+struct Params {  // kguts.h:290-293
+    int order_constraint, min_hits, min_weighted_hits, max_gap;
+};
+
+// key % d with d = num_sigs: q = mulhi(key, floor(2^64/d)) is floor(key/d) or one less.
+__device__ __forceinline__ uint64_t fast_mod(uint64_t key, uint64_t d, uint64_t magic) {
+    uint64_t q = __umul64hi(key, magic);
+    uint64_t r = key - q * d;
+    return r >= d ? r - d : r;
+}
+
+// ASCII -> 0..19 for ACDEFGHIKLMNPQRSTVWY, everything else invalid (kguts.cc:273-339).
+// Invalid is encoded as 0x80 so that "any invalid residue in a word" is one AND with 0x80808080.
+constexpr uint8_t kInvalidCode = 0x80;
+
+__device__ __forceinline__ void fill_aa_lut(uint8_t *lut /*256 B shared*/) {
+    for (int c = threadIdx.x; c < 256; c += blockDim.x) {
+        uint8_t v = kInvalidCode;
+        switch (c) {
+            case 'A': v = 0; break;  case 'C': v = 1; break;  case 'D': v = 2; break;  case 'E': v = 3; break;
+            case 'F': v = 4; break;  case 'G': v = 5; break;  case 'H': v = 6; break;  case 'I': v = 7; break;
+            case 'K': v = 8; break;  case 'L': v = 9; break;  case 'M': v = 10; break; case 'N': v = 11; break;
+            case 'P': v = 12; break; case 'Q': v = 13; break; case 'R': v = 14; break; case 'S': v = 15; break;
+            case 'T': v = 16; break; case 'V': v = 17; break; case 'W': v = 18; break; case 'Y': v = 19; break;
+            default: break;
+        }
+        lut[c] = v;
+    }
+}
+
+// four ASCII bytes -> four codes
+__device__ __forceinline__ uint32_t codes_of_word(const uint8_t *lut, uint32_t w) {
+    uint32_t c0 = lut[w & 0xFF], c1 = lut[(w >> 8) & 0xFF], c2 = lut[(w >> 16) & 0xFF], c3 = lut[w >> 24];
+    return c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+}
+
+}  // namespace ckm

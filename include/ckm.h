@@ -1,0 +1,211 @@
+/*
+ * ckm.h -- C ABI of the B200-native signature-k-mer calling path (libckm.so).
+ *
+ * This is the drop-in boundary for the hot path of olsonanl/close_kmers: the calls that the
+ * reference's request handlers make, one sequence at a time, into a per-thread KmerGuts
+ * (query_request.cc:103-152, add_request.cc:116-170, matrix_request.cc:82-94,
+ * fq_process_request.cc:298-365, family_mapper.cc:46-205) are replaced by ONE batch call per body
+ * chunk.  Plain pointers and sizes only; no C++ or torch types cross this boundary.
+ *
+ * Every entry point returns 0 on success or a negative CKM_E* code; ckm_last_error() gives the text.
+ * The library never calls exit() (the reference does: kmer_image.cc:46-104, kguts.cc:550-553) and has
+ * NO CPU fallback: without a usable sm_100 device every compute entry point fails with CKM_ECUDA.
+ *
+ * Threading: one ckm_ctx per GPU per host thread (the reference keeps one KmerGuts per worker thread,
+ * threadpool.h:42).  Calls on one ctx are serialised on the ctx's CUDA stream.  Result pointers
+ * returned through ckm_batch_out_t & co. point into ctx-owned pinned host memory and stay valid until
+ * the next compute call on the same ctx.
+ */
+#ifndef CKM_H
+#define CKM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* kmer_params.h:5,12,18,20 */
+#define CKM_KMER_SIZE 8
+#define CKM_CORE 1280000000ULL          /* 20^7 */
+#define CKM_MAX_ENCODED 25600000000ULL  /* 20^8; which_kmer > MAX_ENCODED marks an empty slot */
+#define CKM_MAX_HITS_PER_SEQ 40000
+
+enum {
+    CKM_OK = 0,
+    CKM_EINVAL = -1,  /* bad argument */
+    CKM_EIO = -2,     /* file missing / unreadable */
+    CKM_EFORMAT = -3, /* image fails the reference's validation (kmer_image.cc:87-105) or index file not dense */
+    CKM_ECUDA = -4,   /* CUDA error or no device; there is no CPU fallback */
+    CKM_ENOMEM = -5,
+    CKM_ESTATE = -6   /* call order violated (e.g. family batch before ckm_family_load) */
+};
+
+typedef struct ckm_ctx ckm_ctx;
+
+/* ---- on-disk / in-memory image format, read unchanged (kmer_image.h:11-23) ---------------------- */
+typedef struct {
+    uint64_t num_sigs;   /* number of hash buckets */
+    uint64_t entry_size; /* must be 24 */
+    int64_t version;     /* must be 1 */
+} ckm_image_header_t;
+
+typedef struct {
+    uint64_t which_kmer; /* > CKM_MAX_ENCODED => empty */
+    int32_t otu_index;
+    uint16_t avg_from_end;
+    uint16_t pad_;
+    int32_t function_index;
+    float function_wt;
+} ckm_sig_kmer_t; /* 24 bytes == sizeof(sig_kmer_t) */
+
+/* ---- result records ------------------------------------------------------------------------------ */
+/* KmerCall, kguts.h:166-183 */
+typedef struct {
+    uint32_t start;
+    uint32_t end;
+    int32_t count;
+    uint32_t function_index;
+    float weighted_hits;
+} ckm_call_t; /* 20 bytes */
+
+/* hit_in_sequence_t, kguts.h:228-233: a copy of the table slot plus the k-mer's offset in the protein */
+typedef struct {
+    uint64_t which_kmer;
+    uint32_t offset;
+    int32_t otu_index;
+    int32_t function_index;
+    float function_wt;
+    uint16_t avg_from_end;
+    uint16_t pad_;
+    uint32_t pad2_;
+} ckm_hit_t; /* 32 bytes */
+
+/* one entry of KmerOtuStats::otu_map (kguts.h:191), emitted in ascending otu_index (std::map order) */
+typedef struct {
+    int32_t otu_index;
+    int32_t count;
+} ckm_otu_t;
+
+/* outputs of KmerGuts::find_best_call, kguts.cc:1008-1199, with names left as indices */
+#define CKM_BEST_HAS_CALLS 1u /* calls.size() > 0, i.e. score_offset was assigned (kguts.cc:1015-1018) */
+#define CKM_BEST_AMBIG 2u     /* function is "F1 ?? F2" built from function_index_a / _b (kguts.cc:1176-1196) */
+typedef struct {
+    int32_t function_index; /* -1 when no confident call */
+    int32_t ambig_a;        /* vec[0].first when CKM_BEST_AMBIG, else -1 */
+    int32_t ambig_b;        /* vec[1].first when CKM_BEST_AMBIG, else -1 */
+    uint32_t flags;
+    float score;
+    float weighted_score;
+    float score_offset; /* 0 when !CKM_BEST_HAS_CALLS (the reference leaves the caller's variable untouched) */
+} ckm_best_t;     /* 28 bytes */
+
+/* what to compute / copy back; mirrors which arguments the handlers pass as non-null to process_aa_seq */
+#define CKM_WANT_CALLS 1u /* vector<KmerCall> */
+#define CKM_WANT_HITS 2u  /* hit callback list (details=1, /add, /matrix) */
+#define CKM_WANT_OTU 4u   /* KmerOtuStats */
+#define CKM_WANT_BEST 8u  /* find_best_call on the calls */
+
+typedef struct {
+    uint32_t n;                   /* sequences in the batch */
+    const uint64_t *call_offsets; /* n+1, CSR into calls; NULL unless CKM_WANT_CALLS */
+    const ckm_call_t *calls;
+    const uint64_t *hit_offsets; /* n+1; NULL unless CKM_WANT_HITS */
+    const ckm_hit_t *hits;
+    const uint64_t *otu_offsets; /* n+1; NULL unless CKM_WANT_OTU */
+    const ckm_otu_t *otus;
+    const ckm_best_t *best; /* n; NULL unless CKM_WANT_BEST */
+    uint64_t n_probes;      /* table probes issued for this batch (valid windows) */
+    uint64_t n_hits;        /* table hits */
+} ckm_batch_out_t;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------ */
+
+/* Replaces KmerImage(dir) + KmerGuts(dir, image) (kmer_image.cc:41-108, kguts.cc:34-58, 659-679):
+ * maps <kmer_dir>/kmer.table.mem_map, applies the reference's three validations, uploads the table to
+ * HBM, loads <kmer_dir>/function.index and otu.index. */
+int ckm_open(const char *kmer_dir, int device, ckm_ctx **out);
+
+/* Same from an image already in memory in the file format (what KmerImage::image() points at).
+ * function/otu names may be NULL (count 0) when only indices are needed. */
+int ckm_open_image(const void *image, size_t image_bytes, int device, const char *const *function_names,
+                   int32_t n_functions, const char *const *otu_names, int32_t n_otus, ckm_ctx **out);
+
+void ckm_close(ckm_ctx *ctx);
+
+/* thread-local text of the last error (also valid when ctx creation failed) */
+const char *ckm_last_error(void);
+
+/* KmerGuts::function_at_index, kguts.h:361-366: "INVALID_OFFSET" when out of range */
+const char *ckm_function_at_index(const ckm_ctx *ctx, int32_t i);
+const char *ckm_otu_at_index(const ckm_ctx *ctx, int32_t i);
+int32_t ckm_function_count(const ckm_ctx *ctx);
+int32_t ckm_otu_count(const ckm_ctx *ctx);
+uint64_t ckm_num_sigs(const ckm_ctx *ctx);
+/* 16 = packed sector-friendly slots, 24 = verbatim slots (chosen at load, results identical) */
+int ckm_table_slot_bytes(const ckm_ctx *ctx);
+
+/* ---- parameters (KmerGuts::set_default_parameters / set_parameters, kguts.cc:236-268) -------------- */
+void ckm_set_default_params(ckm_ctx *ctx); /* order_constraint 0, min_hits 5, min_weighted_hits 0, max_gap 200 */
+int ckm_set_params(ckm_ctx *ctx, int order_constraint, int min_hits, int min_weighted_hits, int max_gap);
+void ckm_get_params(const ckm_ctx *ctx, int *order_constraint, int *min_hits, int *min_weighted_hits, int *max_gap);
+
+/* ---- static helpers (KmerGuts::encoded_aa_kmer / decoded_kmer, kguts.cc:457-483) ------------------- */
+uint64_t ckm_encoded_aa_kmer(const char *p);              /* MAX_ENCODED+1 if any invalid char */
+void ckm_decoded_kmer(uint64_t encoded, char decoded[9]); /* NUL-terminated */
+
+/* ---- the hot path: process_aa_seq[_hits] (+ find_best_call) over a batch --------------------------- */
+
+/* residues: the n amino-acid strings concatenated (no separators); offsets[i]..offsets[i+1] is
+ * sequence i.  Host pointers; the call does H2D, the kernels and D2H of what `flags` asks for. */
+int ckm_call_batch(ckm_ctx *ctx, const char *residues, const uint64_t *offsets, uint32_t n, uint32_t flags,
+                   ckm_batch_out_t *out);
+
+/* Device-resident form for pipelines that already hold the batch in HBM: d_residues must have 16
+ * readable bytes after offsets[n] and offsets[0] must be 0; max_len is the longest sequence (0 = unknown,
+ * which selects the general scan kernel).  Results stay on the device (ckm_device_results); the call
+ * only enqueues work on ckm_stream(ctx). */
+int ckm_call_batch_device(ckm_ctx *ctx, const void *d_residues, const uint64_t *d_offsets, uint32_t n,
+                          uint64_t total_residues, uint32_t max_len, uint32_t flags);
+
+typedef struct {
+    uint32_t n;
+    const uint32_t *d_n_hits;      /* n   : hits per sequence */
+    const uint32_t *d_n_calls;     /* n   : calls per sequence */
+    const ckm_call_t *d_calls;     /* sequence i's calls start at d_calls[offsets[i] / max(1,min_hits) + i] */
+    int32_t min_hits_for_call_base;
+    const ckm_best_t *d_best;      /* n */
+    const uint64_t *d_totals;      /* [0] probes, [1] hits, [2] calls */
+} ckm_device_out_t;
+int ckm_device_results(ckm_ctx *ctx, ckm_device_out_t *out);
+/* synchronises and copies {probes, hits, calls} of the last batch to the host */
+int ckm_read_totals(ckm_ctx *ctx, uint64_t totals[3]);
+
+/* ---- image builder: KmerGuts(dir, nbuckets) + insert_kmer + save_kmer_hash_table (kguts.cc:77-115, 188-234).
+ * Host-side; writes the reference's file bytes (header + nbuckets slots) into image_out, which must be
+ * exactly 24 + 24*nbuckets bytes.  keys > MAX_ENCODED are skipped like kguts.cc:206-210. */
+int ckm_image_build(uint64_t nbuckets, uint64_t n, const uint64_t *keys, const int32_t *function_index,
+                    const int32_t *otu_index, const uint16_t *avg_from_end, const float *function_wt, void *image_out,
+                    size_t image_bytes);
+
+/* page-locked host memory for batch assembly (fast H2D) */
+int ckm_host_alloc(void **p, size_t bytes);
+void ckm_host_free(void *p);
+
+/* the CUDA stream (cudaStream_t) all work of this ctx is launched on, for event timing by the caller */
+void *ckm_stream(ckm_ctx *ctx);
+/* number of kernel launches issued by this ctx so far */
+uint64_t ckm_launch_count(const ckm_ctx *ctx);
+int ckm_synchronize(ckm_ctx *ctx);
+
+/* Per-kernel device timing for roofline reports: when enabled, every batch records CUDA events around
+ * the probe kernel (K1) and the scan kernel (K2) on ckm_stream(ctx); ckm_profile_read synchronises,
+ * returns the summed durations (ms) and the number of batches since the last read, and resets. */
+void ckm_profile_enable(ckm_ctx *ctx, int on);
+int ckm_profile_read(ckm_ctx *ctx, double *probe_ms, double *scan_ms, uint64_t *batches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CKM_H */

@@ -1,0 +1,488 @@
+// TEST INFRASTRUCTURE -- NOT PRODUCT CODE.
+//
+// C-ABI driver around the UNMODIFIED reference translation units (compiled where they lie under
+// /root/reference by oracle/Makefile into oracle/_ref/libckm_ref.so).  Only tests/, bench.py's
+// cpu_baseline / --impl reference legs and __graft_entry__.smoke() may load it.  Nothing of the
+// reference is copied here: the engine (KmerGuts, KmerImage, KmerEncoder, TranslationTable,
+// DNASequence, FamilyMapper) is the reference's own object code; this file only
+//   * flattens its std::vector / std::string results into the ckm.h record layout, and
+//   * restates the INNER LOOPS of the request handlers that cannot be compiled here because they are
+//     welded to Boost.Asio (query_request.cc:103-152, add_request.cc:116-170, matrix_request.cc:82-94,
+//     130-161, 163-189, fq_process_request.cc:298-365), each marked with the lines it follows.
+#define DEFINE_GLOBALS 1
+#include "global.h"
+#include <boost/program_options.hpp>
+
+#include "kguts.h"
+#include "kmer_image.h"
+#include "kmer_encoder.h"
+#include "trans_table.h"
+#include "dna_seq.h"
+#include "kmer.h"
+#include "family_mapper.h"
+
+#include <chrono>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../include/ckm.h"
+
+static boost::program_options::variables_map g_vm;
+static void ensure_globals() { g_parameters = &g_vm; }
+
+// kmer.cc is not linked (Boost.Iostreams / parallel_read); the three members of KmerPegMapping that
+// family_mapper.cc and this driver need are given here.  ctor follows kmer.cc:40-47, decode_id
+// kmer.cc:288-295, encode_id kmer.cc:272-286 + kmer.h:109-116, add_mapping kmer.cc:174-214.
+KmerPegMapping::KmerPegMapping() : next_peg_id_(0), next_family_id_(0), kcount_(0), next_genome_id_(0) {}
+KmerPegMapping::~KmerPegMapping() {}
+std::string KmerPegMapping::decode_id(encoded_id_t id) {
+    auto x = id_to_peg_.find(id);
+    return x != id_to_peg_.end() ? x->second : std::string();
+}
+KmerPegMapping::encoded_id_t KmerPegMapping::encode_id(const std::string &peg) {
+    auto x = peg_to_id_.find(peg);
+    if (x != peg_to_id_.end()) return x->second;
+    encoded_id_t id = next_peg_id_++;
+    peg_to_id_[peg] = id;
+    id_to_peg_[id] = peg;
+    return id;
+}
+void KmerPegMapping::add_mapping(encoded_id_t enc, unsigned long kmer) { kmer_to_id_[kmer].push_back(enc); }
+
+namespace {
+
+struct RefHandle {
+    std::string dir;
+    std::shared_ptr<KmerImage> image;
+    std::vector<KmerGuts *> guts;  // one per worker thread, like threadpool.cc:18-45
+    std::shared_ptr<KmerPegMapping> mapping;
+    std::map<std::string, std::string> params;
+};
+
+struct RefOut {
+    ckm_batch_out_t o;
+    std::vector<uint64_t> call_off, hit_off, otu_off;
+    std::vector<ckm_call_t> calls;
+    std::vector<ckm_hit_t> hits;
+    std::vector<ckm_otu_t> otus;       // ascending otu_index (otu_map order)
+    std::vector<ckm_otu_t> otus_sorted; // KmerOtuStats::finalize order (otus_by_count)
+    std::vector<ckm_best_t> best;
+    std::vector<std::string> best_fn;
+};
+
+void run_one(KmerGuts *g, const std::string &id, const std::string &seq, uint32_t flags, RefOut *out) {
+    auto calls = std::make_shared<std::vector<KmerCall>>();
+    std::shared_ptr<KmerOtuStats> stats;
+    if (flags & CKM_WANT_OTU) stats = std::make_shared<KmerOtuStats>();
+    std::shared_ptr<std::vector<KmerGuts::hit_in_sequence_t>> hits;
+    // calls are requested whenever calls or best are wanted; a hits-only run passes null calls + null
+    // stats exactly like matrix_request.cc:92-94
+    std::shared_ptr<std::vector<KmerCall>> calls_arg;
+    if (flags & (CKM_WANT_CALLS | CKM_WANT_BEST)) calls_arg = calls;
+    if (flags & CKM_WANT_HITS) {
+        hits = std::make_shared<std::vector<KmerGuts::hit_in_sequence_t>>();
+        g->process_aa_seq_hits(id, seq, calls_arg, hits, stats);
+    } else {
+        g->process_aa_seq(id, seq, calls_arg, nullptr, stats);
+    }
+    if (!out) return;
+    if (flags & CKM_WANT_CALLS) {
+        for (auto &c : *calls) out->calls.push_back({c.start, c.end, c.count, c.function_index, c.weighted_hits});
+        out->call_off.push_back(out->calls.size());
+    }
+    if (flags & CKM_WANT_HITS) {
+        for (auto &h : *hits) {
+            ckm_hit_t r;
+            memset(&r, 0, sizeof r);
+            r.which_kmer = h.hit.which_kmer;
+            r.offset = h.offset;
+            r.otu_index = h.hit.otu_index;
+            r.function_index = h.hit.function_index;
+            r.function_wt = h.hit.function_wt;
+            r.avg_from_end = h.hit.avg_from_end;
+            out->hits.push_back(r);
+        }
+        out->hit_off.push_back(out->hits.size());
+    }
+    if (flags & CKM_WANT_OTU) {
+        for (auto &e : stats->otu_map) out->otus.push_back({e.first, e.second});
+        for (auto &e : stats->otus_by_count) out->otus_sorted.push_back({e.first, e.second});
+        out->otu_off.push_back(out->otus.size());
+    }
+    if (flags & CKM_WANT_BEST) {
+        int fi;
+        float score, wscore, offset = 0.0f;
+        std::string fn;
+        g->find_best_call(*calls, fi, fn, score, wscore, offset);
+        ckm_best_t b;
+        memset(&b, 0, sizeof b);
+        b.function_index = fi;
+        b.ambig_a = b.ambig_b = -1;
+        b.flags = (calls->empty() ? 0u : CKM_BEST_HAS_CALLS) | (fn.find(" ?? ") != std::string::npos ? CKM_BEST_AMBIG : 0u);
+        b.score = score;
+        b.weighted_score = wscore;
+        b.score_offset = calls->empty() ? 0.0f : offset;
+        out->best.push_back(b);
+        out->best_fn.push_back(fn);
+    }
+}
+
+std::string seq_at(const char *residues, const uint64_t *offsets, uint32_t i) {
+    return std::string(residues + offsets[i], residues + offsets[i + 1]);
+}
+
+char *dup_text(const std::string &s) {
+    char *p = (char *)malloc(s.size() + 1);
+    memcpy(p, s.data(), s.size());
+    p[s.size()] = 0;
+    return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- image builder: the reference's own KmerGuts(dir, nbuckets) + insert_kmer + save_kmer_hash_table
+// (kguts.cc:77-115, 188-234); the object is leaked as build_signature_kmers.cc:860-898 does.
+int ref_build_image(const char *dir, long long nbuckets, uint64_t n, const uint64_t *keys, const int32_t *fI,
+                    const int32_t *oI, const uint16_t *avg, const float *wt) {
+    ensure_globals();
+    KmerGuts *b = new KmerGuts(dir, nbuckets);
+    for (uint64_t i = 0; i < n; i++) b->insert_kmer((unsigned long long)keys[i], fI[i], oI[i], avg[i], wt[i]);
+    b->save_kmer_hash_table(std::string(dir) + "/kmer.table.mem_map");
+    return 0;
+}
+
+// same, k-mers given as text (8 chars each, concatenated) so the KmerEncoder path is exercised
+int ref_build_image_str(const char *dir, long long nbuckets, uint64_t n, const char *kmers, const int32_t *fI,
+                        const int32_t *oI, const uint16_t *avg, const float *wt) {
+    ensure_globals();
+    KmerGuts *b = new KmerGuts(dir, nbuckets);
+    for (uint64_t i = 0; i < n; i++) b->insert_kmer(std::string(kmers + 8 * i, 8), fI[i], oI[i], avg[i], wt[i]);
+    b->save_kmer_hash_table(std::string(dir) + "/kmer.table.mem_map");
+    return 0;
+}
+
+uint64_t ref_encoded_aa_kmer(const char *p) { return KmerGuts::encoded_aa_kmer(p); }
+void ref_decoded_kmer(uint64_t k, char *out9) { KmerGuts::decoded_kmer(k, out9); }
+uint64_t ref_encoder_encoded_aa_kmer(const char *p) {
+    KmerEncoder e;
+    return e.encoded_aa_kmer(p);
+}
+
+// ---- engine handle: KmerImage(dir) + n_threads x KmerGuts(dir, image) ------------------------------
+void *ref_open(const char *dir, int n_threads) {
+    ensure_globals();
+    RefHandle *h = new RefHandle;
+    h->dir = dir;
+    h->image = std::make_shared<KmerImage>(dir);
+    if (n_threads < 1) n_threads = 1;
+    for (int i = 0; i < n_threads; i++) h->guts.push_back(new KmerGuts(dir, h->image));
+    return h;
+}
+
+void ref_close(void *hv) {
+    // The engines are leaked on purpose: kser never destroys its per-thread KmerGuts (threadpool.cc:33), and
+    // ~KmerGuts (kguts.cc:172-191) is not safe to run on an instance built by the (dir, image) constructor.
+    RefHandle *h = (RefHandle *)hv;
+    h->image.reset();
+    delete h;
+}
+
+int ref_function_count(void *hv) { return ((RefHandle *)hv)->guts[0]->kmersH->function_count; }
+const char *ref_function_at_index(void *hv, int i) { return ((RefHandle *)hv)->guts[0]->function_at_index(i); }
+
+// Q1: set_parameters(map<string,string>) -- resets to defaults first (kguts.cc:244-268)
+void ref_set_params_kv(void *hv, int n, const char *const *keys, const char *const *vals) {
+    RefHandle *h = (RefHandle *)hv;
+    h->params.clear();
+    for (int i = 0; i < n; i++) h->params[keys[i]] = vals[i];
+    for (auto g : h->guts) g->set_parameters(h->params);
+}
+void ref_get_params(void *hv, int *oc, int *mh, int *mwh, int *mg) {
+    KmerGuts *g = ((RefHandle *)hv)->guts[0];
+    *oc = g->order_constraint;
+    *mh = g->min_hits;
+    *mwh = g->min_weighted_hits;
+    *mg = g->max_gap;
+}
+
+// ---- S4 + B1 over a batch ---------------------------------------------------------------------------
+void *ref_call_batch(void *hv, const char *residues, const uint64_t *offsets, uint32_t n, uint32_t flags) {
+    RefHandle *h = (RefHandle *)hv;
+    RefOut *out = new RefOut;
+    memset(&out->o, 0, sizeof out->o);
+    out->call_off.push_back(0);
+    out->hit_off.push_back(0);
+    out->otu_off.push_back(0);
+    for (uint32_t i = 0; i < n; i++) run_one(h->guts[0], "seq", seq_at(residues, offsets, i), flags, out);
+    out->o.n = n;
+    if (flags & CKM_WANT_CALLS) { out->o.call_offsets = out->call_off.data(); out->o.calls = out->calls.data(); }
+    if (flags & CKM_WANT_HITS) { out->o.hit_offsets = out->hit_off.data(); out->o.hits = out->hits.data(); }
+    if (flags & CKM_WANT_OTU) { out->o.otu_offsets = out->otu_off.data(); out->o.otus = out->otus.data(); }
+    if (flags & CKM_WANT_BEST) out->o.best = out->best.data();
+    out->o.n_hits = out->hits.size();
+    return out;
+}
+const ckm_batch_out_t *ref_out_view(void *ov) { return &((RefOut *)ov)->o; }
+const char *ref_out_best_function(void *ov, uint32_t i) { return ((RefOut *)ov)->best_fn[i].c_str(); }
+const ckm_otu_t *ref_out_otus_sorted(void *ov) { return ((RefOut *)ov)->otus_sorted.data(); }
+void ref_out_free(void *ov) { delete (RefOut *)ov; }
+
+// ---- CPU baseline: same shape as ThreadPool (threadpool.cc:18-45): one KmerGuts per std::thread, one
+// shared KmerImage, static contiguous sharding; times only the process_aa_seq (+find_best_call) loop.
+double ref_bench_calls(void *hv, const char *residues, const uint64_t *offsets, uint32_t n, int want_best,
+                       uint64_t *total_calls) {
+    RefHandle *h = (RefHandle *)hv;
+    int T = (int)h->guts.size();
+    std::vector<uint64_t> ncalls(T, 0);
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++) {
+        th.emplace_back([=, &ncalls]() {
+            uint32_t lo = (uint32_t)((uint64_t)n * t / T), hi = (uint32_t)((uint64_t)n * (t + 1) / T);
+            KmerGuts *g = h->guts[t];
+            uint64_t c = 0;
+            for (uint32_t i = lo; i < hi; i++) {
+                auto calls = std::make_shared<std::vector<KmerCall>>();
+                g->process_aa_seq("seq", seq_at(residues, offsets, i), calls, nullptr, nullptr);
+                c += calls->size();
+                if (want_best) {
+                    int fi;
+                    float s, w, o;
+                    std::string fn;
+                    g->find_best_call(*calls, fi, fn, s, w, o);
+                    c += (fi >= 0);
+                }
+            }
+            ncalls[t] = c;
+        });
+    }
+    for (auto &x : th) x.join();
+    auto t1 = std::chrono::steady_clock::now();
+    uint64_t tot = 0;
+    for (auto c : ncalls) tot += c;
+    if (total_calls) *total_calls = tot;
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// ---- response text of POST /query for one chunk: restates query_request.cc:103-152 ------------------
+char *ref_query_text(void *hv, const char *const *ids, const char *residues, const uint64_t *offsets, uint32_t n,
+                     int details, int find_best_call) {
+    RefHandle *h = (RefHandle *)hv;
+    KmerGuts *kguts = h->guts[0];
+    std::ostringstream os;
+    for (uint32_t i = 0; i < n; i++) {
+        std::string id = ids[i], seq = seq_at(residues, offsets, i);
+        auto calls = std::make_shared<std::vector<KmerCall>>();
+        auto stats = std::make_shared<KmerOtuStats>();
+        std::shared_ptr<std::vector<KmerGuts::hit_in_sequence_t>> hits;
+        if (details) {
+            hits = std::make_shared<std::vector<KmerGuts::hit_in_sequence_t>>();
+            kguts->process_aa_seq_hits(id, seq, calls, hits, stats);
+        } else {
+            kguts->process_aa_seq(id, seq, calls, 0, stats);
+        }
+        if (find_best_call) {
+            int fi;
+            float score, wscore, off;
+            std::string fn;
+            kguts->find_best_call(*calls, fi, fn, score, wscore, off);
+            if (!fn.empty()) os << id << "\t" << fn << "\t" << score << "\t" << wscore << "\n";
+        } else {
+            os << "PROTEIN-ID\t" << id << "\t" << seq.size() << "\n";
+            for (auto c : *calls) os << kguts->format_call(c);
+            if (details)
+                for (auto hh : *hits) os << kguts->format_hit(hh);
+            os << kguts->format_otu_stats(id, seq.size(), *stats);
+        }
+    }
+    return dup_text(os.str());
+}
+
+// ---- response text of POST /add (non-silent) for one chunk: restates add_request.cc:116-170 ---------
+// and records the k-mer -> peg postings exactly as add_request.cc:164-170 / kmer.cc:174-214 do.
+void ref_mapping_new(void *hv) { ((RefHandle *)hv)->mapping = std::make_shared<KmerPegMapping>(); }
+
+char *ref_add_text(void *hv, const char *const *ids, const char *residues, const uint64_t *offsets, uint32_t n,
+                   int silent) {
+    RefHandle *h = (RefHandle *)hv;
+    KmerGuts *kguts = h->guts[0];
+    KmerPegMapping &m = *h->mapping;
+    std::ostringstream os;
+    for (uint32_t i = 0; i < n; i++) {
+        std::string id = ids[i], seq = seq_at(residues, offsets, i);
+        auto hits = std::make_shared<std::vector<KmerGuts::hit_in_sequence_t>>();
+        auto calls = std::make_shared<std::vector<KmerCall>>();
+        auto stats = std::make_shared<KmerOtuStats>();
+        kguts->process_aa_seq_hits(id, seq, calls, hits, stats);
+        if (!silent) {
+            os << "PROTEIN-ID\t" << id << "\t" << seq.size() << "\n";
+            for (auto c : *calls) os << kguts->format_call(c);
+            os << kguts->format_otu_stats(id, seq.size(), *stats);
+            int fi;
+            float score, off = 0, wscore;
+            std::string fn;
+            kguts->find_best_call(*calls, fi, fn, score, wscore, off);
+            if (fn.empty())
+                fn = "hypothetical protein";
+            else if (fn.find(" ?? ") != std::string::npos)
+                fn = "hypothetical protein";
+            // score_offset is printed uninitialised by the reference when there are no calls
+            // (add_request.cc:143-146); the driver pins it to 0 so the text is reproducible.
+            os << "BEST-CALL\t" << id << "\t" << fn << "\t" << score << "\t" << wscore << "\t" << off << "\n";
+        }
+        KmerPegMapping::encoded_id_t enc = m.encode_id(id);
+        for (auto hit : *hits) m.add_mapping(enc, hit.hit.which_kmer);
+    }
+    return dup_text(os.str());
+}
+
+// ---- POST /matrix: restates matrix_request.cc:82-94 (worker loop), 130-161 (on_hit), 163-189 --------
+char *ref_matrix_text(void *hv, const char *const *ids, const char *residues, const uint64_t *offsets, uint32_t n,
+                      uint64_t *n_pairs) {
+    RefHandle *h = (RefHandle *)hv;
+    KmerGuts *kguts = h->guts[0];
+    KmerPegMapping &m = *h->mapping;
+    typedef KmerPegMapping::encoded_id_t eid_t;
+    std::map<eid_t, size_t> matrix_proteins;
+    std::map<std::pair<eid_t, eid_t>, unsigned long> distance;
+    for (uint32_t i = 0; i < n; i++) {
+        std::string id = ids[i], seq = seq_at(residues, offsets, i);
+        eid_t eid = m.encode_id(id);
+        matrix_proteins[eid] = seq.size();
+        kguts->process_aa_seq(id, seq, 0, [&](KmerGuts::hit_in_sequence_t kmer) {
+            auto ki = m.kmer_to_id_.find(kmer.hit.which_kmer);
+            if (ki != m.kmer_to_id_.end()) {
+                for (auto e : ki->second)
+                    if (e != eid && matrix_proteins.find(e) != matrix_proteins.end()) distance[std::make_pair(eid, e)]++;
+            }
+        }, 0);
+    }
+    std::ostringstream os;
+    for (auto it = distance.begin(); it != distance.end(); it++) {
+        eid_t e1 = it->first.first, e2 = it->first.second;
+        size_t l1 = matrix_proteins[e1], l2 = matrix_proteins[e2];
+        float score = (float)it->second / ((float)(l1 + l2));
+        os << m.decode_id(e1) << "\t" << m.decode_id(e2) << "\t" << it->second << "\t" << score << "\n";
+    }
+    if (n_pairs) *n_pairs = distance.size();
+    return dup_text(os.str());
+}
+
+// ---- family side tables (what NRLoader / load_families leave in KmerPegMapping) ---------------------
+// kmer_to_family_id_: CSR; family_data_: per family id (pgf, plf, function, genus_id, total_size, count)
+void ref_family_load(void *hv, uint64_t n_kmers, const uint64_t *kmers, const uint64_t *fam_off, const uint32_t *fam_ids,
+                     uint32_t n_fams, const char *const *pgf, const char *const *plf, const char *const *function) {
+    RefHandle *h = (RefHandle *)hv;
+    if (!h->mapping) h->mapping = std::make_shared<KmerPegMapping>();
+    KmerPegMapping &m = *h->mapping;
+    for (uint64_t k = 0; k < n_kmers; k++) {
+        auto &v = m.kmer_to_family_id_[kmers[k]];
+        v.assign(fam_ids + fam_off[k], fam_ids + fam_off[k + 1]);
+    }
+    for (uint32_t f = 0; f < n_fams; f++) {
+        KmerPegMapping::family_data_t d;
+        d.pgf = pgf[f];
+        d.plf = plf[f];
+        d.function = function[f];
+        d.genus_id = 0;
+        d.family_id = f;
+        d.total_size = 0;
+        d.count = 0;
+        m.family_data_[f] = d;
+    }
+}
+
+static void put_match(std::ostringstream &os, const FamilyMapper::best_match_t &b) { os << b; }
+
+// FamilyMapper::find_best_family_match over a block with ONE mapper, like fq_process_request.cc:241-242
+char *ref_family_text(void *hv, const char *residues, const uint64_t *offsets, uint32_t n) {
+    RefHandle *h = (RefHandle *)hv;
+    FamilyMapper mapper(h->guts[0], h->mapping);
+    std::ostringstream os;
+    for (uint32_t i = 0; i < n; i++) {
+        auto b = mapper.find_best_family_match("seq", seq_at(residues, offsets, i));
+        put_match(os, b);
+        os << "\n";
+    }
+    return dup_text(os.str());
+}
+
+// POST /fq_lookup inner loop: restates fq_process_request.cc:298-365 over reference DNASequence /
+// TranslationTable / FamilyMapper objects; one mapper per block (fq_process_request.cc:241-242).
+char *ref_fq_text(void *hv, const char *const *ids, const char *bases, const uint64_t *offsets, uint32_t n) {
+    RefHandle *h = (RefHandle *)hv;
+    FamilyMapper mapper(h->guts[0], h->mapping);
+    TranslationTable trans_table = TranslationTable::make_table(11);
+    std::ostringstream os;
+    for (uint32_t r = 0; r < n; r++) {
+        std::string id = ids[r], seq = seq_at(bases, offsets, r);
+        if (id.empty()) continue;
+        DNASequence dna(id, seq);
+        auto prots = dna.get_possible_proteins(trans_table);
+        double best_score = 0.0;
+        int best_frame = 0;
+        std::vector<std::pair<size_t, FamilyMapper::best_match_t>> best_matches;
+        for (auto iter = prots.begin(); iter != prots.end(); iter++) {
+            int frame = iter->first;
+            std::list<std::string> &proteins = iter->second;
+            double score = 0.0;
+            std::vector<std::pair<size_t, FamilyMapper::best_match_t>> matches;
+            for (auto prot : proteins) {
+                if (prot.length() > 10) {
+                    matches.emplace_back(std::make_pair(prot.length(), mapper.find_best_family_match(id, prot)));
+                    score += matches.back().second.score;
+                }
+                if (score > best_score) {
+                    best_score = score;
+                    best_frame = frame;
+                    best_matches = matches;
+                }
+            }
+        }
+        if (best_score > 0.0) {
+            os << id << "\t" << best_frame << "\t" << best_score << "\t";
+            auto it = best_matches.begin();
+            os << it->first << "\t" << it->second;
+            ++it;
+            while (it != best_matches.end()) {
+                os << "\t" << it->first << "\t" << it->second;
+                ++it;
+            }
+            os << std::endl;
+        }
+    }
+    return dup_text(os.str());
+}
+
+// 6-frame translation alone (D1, D2): frames joined as "frame\tfrag,frag,...\n" for inspection
+char *ref_six_frames(const char *bases) {
+    TranslationTable trans_table = TranslationTable::make_table(11);
+    std::string id = "r", seq = bases;
+    DNASequence dna(id, seq);
+    auto prots = dna.get_possible_proteins(trans_table);
+    std::ostringstream os;
+    for (auto &fr : prots) {
+        os << fr.first << "\t";
+        bool first = true;
+        for (auto &p : fr.second) {
+            if (!first) os << ",";
+            os << p;
+            first = false;
+        }
+        os << "\n";
+    }
+    return dup_text(os.str());
+}
+
+void ref_free_text(char *p) { free(p); }
+
+}  // extern "C"

@@ -1,0 +1,351 @@
+"""ctypes bindings of the two CPU checkers (TEST INFRASTRUCTURE):
+
+* ``Ref``    -- oracle/_ref/libckm_ref.so: the reference's own object code behind ref_driver.cc.
+* ``Oracle`` -- oracle/libckm_oracle.so: the plain-C restatement (ckm_oracle.c).
+
+Both return results in the ckm.h record layout as numpy structured arrays, so the parity tests compare
+them (and the CUDA path) field by field.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libckm_ref.so")
+ORACLE_SO = os.path.join(ROOT, "oracle", "libckm_oracle.so")
+
+WANT_CALLS, WANT_HITS, WANT_OTU, WANT_BEST = 1, 2, 4, 8
+BEST_HAS_CALLS, BEST_AMBIG = 1, 2
+
+CALL_DT = np.dtype([("start", "<u4"), ("end", "<u4"), ("count", "<i4"), ("function_index", "<u4"),
+                    ("weighted_hits", "<f4")])
+HIT_DT = np.dtype([("which_kmer", "<u8"), ("offset", "<u4"), ("otu_index", "<i4"), ("function_index", "<i4"),
+                   ("function_wt", "<f4"), ("avg_from_end", "<u2"), ("pad_", "<u2"), ("pad2_", "<u4")])
+OTU_DT = np.dtype([("otu_index", "<i4"), ("count", "<i4")])
+BEST_DT = np.dtype([("function_index", "<i4"), ("ambig_a", "<i4"), ("ambig_b", "<i4"), ("flags", "<u4"),
+                    ("score", "<f4"), ("weighted_score", "<f4"), ("score_offset", "<f4")])
+SLOT_DT = np.dtype([("which_kmer", "<u8"), ("otu_index", "<i4"), ("avg_from_end", "<u2"), ("pad_", "<u2"),
+                    ("function_index", "<i4"), ("function_wt", "<f4")])
+assert CALL_DT.itemsize == 20 and HIT_DT.itemsize == 32 and BEST_DT.itemsize == 28 and SLOT_DT.itemsize == 24
+
+
+class BatchOutC(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("call_offsets", C.c_void_p), ("calls", C.c_void_p), ("hit_offsets", C.c_void_p),
+                ("hits", C.c_void_p), ("otu_offsets", C.c_void_p), ("otus", C.c_void_p), ("best", C.c_void_p),
+                ("n_probes", C.c_uint64), ("n_hits", C.c_uint64)]
+
+
+def _arr(ptr, count, dtype):
+    if not ptr or count == 0:
+        return np.zeros(0, dtype=dtype)
+    buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype).copy()
+
+
+def unpack_batch_out(o: BatchOutC) -> dict:
+    """Copy a ckm_batch_out_t into numpy arrays (the C side may free / reuse its buffers afterwards)."""
+    n = o.n
+    r = {"n": n, "n_probes": o.n_probes, "n_hits": o.n_hits}
+    for name, dt in (("call", CALL_DT), ("hit", HIT_DT), ("otu", OTU_DT)):
+        offp = getattr(o, f"{name}_offsets")
+        if offp:
+            off = _arr(offp, n + 1, np.uint64)
+            r[f"{name}_offsets"] = off
+            r[f"{name}s"] = _arr(getattr(o, f"{name}s"), int(off[-1]) if n + 1 else 0, dt)
+    if o.best:
+        r["best"] = _arr(o.best, n, BEST_DT)
+    return r
+
+
+def ensure_built() -> None:
+    """(Re)build the checkers when sources are newer; the reference .so only when /root/reference exists."""
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "all"], check=True, stdout=subprocess.DEVNULL)
+
+
+def _p(a, ct):
+    return a.ctypes.data_as(C.POINTER(ct))
+
+
+def _cstr_array(strs):
+    bs = [s.encode() if isinstance(s, str) else s for s in strs]
+    arr = (C.c_char_p * len(bs))(*bs)
+    return arr
+
+
+class Ref:
+    """The reference's own code.  Chatty on stdout/stderr (its own prints)."""
+
+    def __init__(self):
+        if not os.path.exists(REF_SO):
+            raise FileNotFoundError(REF_SO)
+        L = self.L = C.CDLL(REF_SO)
+        L.ref_open.restype = C.c_void_p
+        L.ref_open.argtypes = [C.c_char_p, C.c_int]
+        L.ref_close.argtypes = [C.c_void_p]
+        L.ref_call_batch.restype = C.c_void_p
+        L.ref_call_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.ref_out_view.restype = C.POINTER(BatchOutC)
+        L.ref_out_view.argtypes = [C.c_void_p]
+        L.ref_out_best_function.restype = C.c_char_p
+        L.ref_out_best_function.argtypes = [C.c_void_p, C.c_uint32]
+        L.ref_out_otus_sorted.restype = C.c_void_p
+        L.ref_out_otus_sorted.argtypes = [C.c_void_p]
+        L.ref_out_free.argtypes = [C.c_void_p]
+        L.ref_encoded_aa_kmer.restype = C.c_uint64
+        L.ref_encoded_aa_kmer.argtypes = [C.c_char_p]
+        L.ref_encoder_encoded_aa_kmer.restype = C.c_uint64
+        L.ref_encoder_encoded_aa_kmer.argtypes = [C.c_char_p]
+        L.ref_decoded_kmer.argtypes = [C.c_uint64, C.c_char_p]
+        L.ref_build_image.argtypes = [C.c_char_p, C.c_longlong, C.c_uint64] + [C.c_void_p] * 5
+        L.ref_build_image_str.argtypes = [C.c_char_p, C.c_longlong, C.c_uint64] + [C.c_void_p] * 5
+        L.ref_set_params_kv.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_get_params.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
+        L.ref_function_count.argtypes = [C.c_void_p]
+        L.ref_function_at_index.restype = C.c_char_p
+        L.ref_function_at_index.argtypes = [C.c_void_p, C.c_int]
+        L.ref_bench_calls.restype = C.c_double
+        L.ref_bench_calls.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]
+        for f in ("ref_query_text", "ref_add_text"):
+            getattr(L, f).restype = C.c_void_p
+            getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int] + (
+                [C.c_int] if f == "ref_query_text" else [])
+        L.ref_matrix_text.restype = C.c_void_p
+        L.ref_matrix_text.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]
+        L.ref_mapping_new.argtypes = [C.c_void_p]
+        L.ref_family_load.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]
+        L.ref_family_text.restype = C.c_void_p
+        L.ref_family_text.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.ref_fq_text.restype = C.c_void_p
+        L.ref_fq_text.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.ref_six_frames.restype = C.c_void_p
+        L.ref_six_frames.argtypes = [C.c_char_p]
+        L.ref_free_text.argtypes = [C.c_void_p]
+        self.h = None
+
+    # -- builder / statics
+    def build_image(self, kmer_dir, nbuckets, sig):
+        keys = np.ascontiguousarray(sig.keys, np.uint64)
+        self.L.ref_build_image(kmer_dir.encode(), nbuckets, len(keys), keys.ctypes.data,
+                               np.ascontiguousarray(sig.fI, np.int32).ctypes.data,
+                               np.ascontiguousarray(sig.oI, np.int32).ctypes.data,
+                               np.ascontiguousarray(sig.avg, np.uint16).ctypes.data,
+                               np.ascontiguousarray(sig.wt, np.float32).ctypes.data)
+
+    def build_image_str(self, kmer_dir, nbuckets, kmers: bytes, fI, oI, avg, wt):
+        n = len(kmers) // 8
+        self.L.ref_build_image_str(kmer_dir.encode(), nbuckets, n, kmers,
+                                   np.ascontiguousarray(fI, np.int32).ctypes.data,
+                                   np.ascontiguousarray(oI, np.int32).ctypes.data,
+                                   np.ascontiguousarray(avg, np.uint16).ctypes.data,
+                                   np.ascontiguousarray(wt, np.float32).ctypes.data)
+
+    def encoded_aa_kmer(self, s: bytes) -> int:
+        return self.L.ref_encoded_aa_kmer(s)
+
+    def encoder_encoded_aa_kmer(self, s: bytes) -> int:
+        return self.L.ref_encoder_encoded_aa_kmer(s)
+
+    def decoded_kmer(self, k: int) -> bytes:
+        b = C.create_string_buffer(9)
+        self.L.ref_decoded_kmer(k, b)
+        return b.value
+
+    # -- engine
+    def open(self, kmer_dir, threads=1):
+        self.h = self.L.ref_open(kmer_dir.encode(), threads)
+        return self
+
+    def close(self):
+        if self.h:
+            self.L.ref_close(self.h)
+            self.h = None
+
+    def set_params(self, **kv):
+        keys = _cstr_array(list(kv.keys()))
+        vals = _cstr_array([str(v) for v in kv.values()])
+        self.L.ref_set_params_kv(self.h, len(kv), keys, vals)
+
+    def get_params(self):
+        v = [C.c_int() for _ in range(4)]
+        self.L.ref_get_params(self.h, *[C.byref(x) for x in v])
+        return tuple(x.value for x in v)
+
+    def function_at_index(self, i):
+        return self.L.ref_function_at_index(self.h, i).decode()
+
+    def call_batch(self, batch, flags):
+        res = np.ascontiguousarray(batch.residues, np.uint8)
+        off = np.ascontiguousarray(batch.offsets, np.uint64)
+        o = self.L.ref_call_batch(self.h, res.ctypes.data, off.ctypes.data, batch.n, flags)
+        r = unpack_batch_out(self.L.ref_out_view(o).contents)
+        if flags & WANT_BEST:
+            r["best_function"] = [self.L.ref_out_best_function(o, i).decode() for i in range(batch.n)]
+        if flags & WANT_OTU:
+            r["otus_sorted"] = _arr(self.L.ref_out_otus_sorted(o), len(r["otus"]), OTU_DT)
+        self.L.ref_out_free(o)
+        return r
+
+    def bench_calls(self, batch, want_best=True):
+        res = np.ascontiguousarray(batch.residues, np.uint8)
+        off = np.ascontiguousarray(batch.offsets, np.uint64)
+        tot = C.c_uint64()
+        return self.L.ref_bench_calls(self.h, res.ctypes.data, off.ctypes.data, batch.n, int(want_best), C.byref(tot))
+
+    def _text(self, p):
+        s = C.string_at(p).decode()
+        self.L.ref_free_text(p)
+        return s
+
+    def query_text(self, ids, batch, details=0, find_best_call=0):
+        res = np.ascontiguousarray(batch.residues, np.uint8)
+        off = np.ascontiguousarray(batch.offsets, np.uint64)
+        return self._text(self.L.ref_query_text(self.h, _cstr_array(ids), res.ctypes.data, off.ctypes.data, batch.n,
+                                                details, find_best_call))
+
+    def mapping_new(self):
+        self.L.ref_mapping_new(self.h)
+
+    def add_text(self, ids, batch, silent=0):
+        res = np.ascontiguousarray(batch.residues, np.uint8)
+        off = np.ascontiguousarray(batch.offsets, np.uint64)
+        return self._text(self.L.ref_add_text(self.h, _cstr_array(ids), res.ctypes.data, off.ctypes.data, batch.n, silent))
+
+    def matrix_text(self, ids, batch):
+        res = np.ascontiguousarray(batch.residues, np.uint8)
+        off = np.ascontiguousarray(batch.offsets, np.uint64)
+        npairs = C.c_uint64()
+        return self._text(self.L.ref_matrix_text(self.h, _cstr_array(ids), res.ctypes.data, off.ctypes.data, batch.n,
+                                                 C.byref(npairs)))
+
+    def family_load(self, kmers, fam_off, fam_ids, pgf, plf, function):
+        kmers = np.ascontiguousarray(kmers, np.uint64)
+        fam_off = np.ascontiguousarray(fam_off, np.uint64)
+        fam_ids = np.ascontiguousarray(fam_ids, np.uint32)
+        self.L.ref_family_load(self.h, len(kmers), kmers.ctypes.data, fam_off.ctypes.data, fam_ids.ctypes.data, len(pgf),
+                               _cstr_array(pgf), _cstr_array(plf), _cstr_array(function))
+
+    def family_text(self, batch):
+        res = np.ascontiguousarray(batch.residues, np.uint8)
+        off = np.ascontiguousarray(batch.offsets, np.uint64)
+        return self._text(self.L.ref_family_text(self.h, res.ctypes.data, off.ctypes.data, batch.n))
+
+    def fq_text(self, ids, batch):
+        res = np.ascontiguousarray(batch.residues, np.uint8)
+        off = np.ascontiguousarray(batch.offsets, np.uint64)
+        return self._text(self.L.ref_fq_text(self.h, _cstr_array(ids), res.ctypes.data, off.ctypes.data, batch.n))
+
+    def six_frames(self, bases: bytes) -> str:
+        return self._text(self.L.ref_six_frames(bases))
+
+
+class ParamsC(C.Structure):
+    _fields_ = [("order_constraint", C.c_int), ("min_hits", C.c_int), ("min_weighted_hits", C.c_int), ("max_gap", C.c_int)]
+
+
+class Oracle:
+    def __init__(self):
+        L = self.L = C.CDLL(ORACLE_SO)
+        L.orc_open_image.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.orc_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.orc_close.argtypes = [C.c_void_p]
+        L.orc_num_sigs.restype = C.c_uint64
+        L.orc_num_sigs.argtypes = [C.c_void_p]
+        L.orc_to_amino_acid_off.restype = C.c_uint8
+        L.orc_to_amino_acid_off.argtypes = [C.c_char]
+        L.orc_encoded_aa_kmer.restype = C.c_uint64
+        L.orc_encoded_aa_kmer.argtypes = [C.c_char_p]
+        L.orc_decoded_kmer.argtypes = [C.c_uint64, C.c_char_p]
+        L.orc_lookup_hash_entry.restype = C.c_int64
+        L.orc_lookup_hash_entry.argtypes = [C.c_void_p, C.c_uint64]
+        L.orc_call_batch.restype = C.POINTER(BatchOutC)
+        L.orc_call_batch.argtypes = [C.c_void_p, C.POINTER(ParamsC), C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.orc_out_free.argtypes = [C.c_void_p]
+        L.orc_find_best_call.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        L.orc_bench_calls.restype = C.c_double
+        L.orc_bench_calls.argtypes = [C.c_void_p, C.POINTER(ParamsC), C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int,
+                                      C.POINTER(C.c_uint64)]
+        self.t = None
+        self.params = ParamsC(0, 5, 0, 200)
+        self._keep = None
+
+    def open(self, kmer_dir):
+        t = C.c_void_p()
+        rc = self.L.orc_open(kmer_dir.encode(), C.byref(t))
+        if rc:
+            raise RuntimeError(f"orc_open rc={rc}")
+        self.t = t
+        return self
+
+    def open_image(self, image: np.ndarray):
+        t = C.c_void_p()
+        rc = self.L.orc_open_image(image.ctypes.data, image.nbytes, C.byref(t))
+        if rc:
+            raise RuntimeError(f"orc_open_image rc={rc}")
+        self._keep = image
+        self.t = t
+        return self
+
+    def try_open_image(self, image: np.ndarray) -> int:
+        t = C.c_void_p()
+        rc = self.L.orc_open_image(image.ctypes.data, image.nbytes, C.byref(t))
+        if rc == 0:
+            self.L.orc_close(t)
+        return rc
+
+    def close(self):
+        if self.t:
+            self.L.orc_close(self.t)
+            self.t = None
+
+    def set_params(self, order_constraint=0, min_hits=5, min_weighted_hits=0, max_gap=200):
+        self.params = ParamsC(order_constraint, min_hits, min_weighted_hits, max_gap)
+
+    def encoded_aa_kmer(self, s: bytes) -> int:
+        return self.L.orc_encoded_aa_kmer(s)
+
+    def decoded_kmer(self, k: int) -> bytes:
+        b = C.create_string_buffer(9)
+        self.L.orc_decoded_kmer(k, b)
+        return b.value
+
+    def lookup(self, key: int) -> int:
+        return self.L.orc_lookup_hash_entry(self.t, key)
+
+    def call_batch(self, batch, flags):
+        res = np.ascontiguousarray(batch.residues, np.uint8)
+        off = np.ascontiguousarray(batch.offsets, np.uint64)
+        o = self.L.orc_call_batch(self.t, C.byref(self.params), res.ctypes.data, off.ctypes.data, batch.n, flags)
+        r = unpack_batch_out(o.contents)
+        self.L.orc_out_free(o)
+        return r
+
+    def find_best_call(self, calls: np.ndarray):
+        calls = np.ascontiguousarray(calls, CALL_DT)
+        out = np.zeros(1, BEST_DT)
+        self.L.orc_find_best_call(calls.ctypes.data, len(calls), out.ctypes.data)
+        return out[0]
+
+    def bench_calls(self, batch, threads, want_best=True):
+        res = np.ascontiguousarray(batch.residues, np.uint8)
+        off = np.ascontiguousarray(batch.offsets, np.uint64)
+        tot = C.c_uint64()
+        return self.L.orc_bench_calls(self.t, C.byref(self.params), res.ctypes.data, off.ctypes.data, batch.n,
+                                      int(want_best), threads, C.byref(tot))
+
+
+def best_function_string(best_rec, function_at_index) -> str:
+    """Host-side naming of a ckm_best_t (kguts.cc:1160, 1176-1196): 'F1 ?? F2' with the greater string first."""
+    if best_rec["flags"] & BEST_AMBIG:
+        f1 = function_at_index(int(best_rec["ambig_a"]))
+        f2 = function_at_index(int(best_rec["ambig_b"]))
+        if f2 > f1:
+            f1, f2 = f2, f1
+        return f1 + " ?? " + f2
+    if best_rec["function_index"] >= 0:
+        return function_at_index(int(best_rec["function_index"]))
+    return ""

@@ -1,0 +1,140 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (libckm.so), must agree bit for bit
+with the plain-C oracle -- and with the reference's own object code when oracle/_ref is present."""
+import os
+
+import numpy as np
+import pytest
+
+import workloads as wl
+from close_kmers_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+ALL = api.WANT_CALLS | api.WANT_HITS | api.WANT_OTU | api.WANT_BEST
+PARAM_SETS = [
+    dict(),
+    dict(order_constraint=1),
+    dict(min_hits=3, max_gap=50),
+    dict(min_hits=2, min_weighted_hits=20, max_gap=10),
+    dict(order_constraint=1, min_hits=2, max_gap=600),
+]
+
+
+@pytest.fixture(scope="module")
+def world(checkers):
+    protos, sig, img = wl.small_world()
+    orc = checkers.Oracle().open_image(img)
+    names = synth.function_names(sig.n_functions)
+    guts = api.KmerGuts(image=img, function_names=names)
+    os.environ["CKM_FORCE_RAW_SLOTS"] = "1"
+    guts_raw = api.KmerGuts(image=img, function_names=names)
+    del os.environ["CKM_FORCE_RAW_SLOTS"]
+    assert guts.slot_bytes == 16 and guts_raw.slot_bytes == 24
+    yield protos, sig, img, orc, guts, guts_raw
+    guts.close()
+    guts_raw.close()
+    orc.close()
+
+
+@pytest.mark.parametrize("prm", PARAM_SETS)
+def test_call_batch_bit_exact(checkers, world, prm):
+    protos, sig, _, orc, guts, guts_raw = world
+    batch = wl.concat_batches(wl.edge_batch(protos), synth.make_proteins(2, protos, 3000))
+    orc.set_params(**prm)
+    want = orc.call_batch(batch, ALL)
+    for g, nm in ((guts, "packed16"), (guts_raw, "raw24")):
+        g.set_parameters(prm)
+        got = g.process_aa_seq_batch(batch.residues, batch.offsets, ALL)
+        wl.assert_results_equal(got, want, f"cuda[{nm}] vs oracle {prm}")
+        assert got["n_probes"] == want["n_probes"]
+        assert got["n_hits"] == len(want["hits"])
+    assert len(want["calls"]) > 100
+
+
+def test_each_flag_alone(checkers, world):
+    """The handlers pass different subsets of (calls, hit_cb, otu_stats): every subset must agree."""
+    protos, _, _, orc, guts, _ = world
+    batch = synth.make_proteins(9, protos, 500)
+    orc.set_params()
+    guts.set_default_parameters()
+    for flags in (api.WANT_CALLS, api.WANT_HITS, api.WANT_OTU, api.WANT_BEST, api.WANT_CALLS | api.WANT_OTU,
+                  api.WANT_HITS | api.WANT_BEST):
+        want = orc.call_batch(batch, flags)
+        got = guts.process_aa_seq_batch(batch.residues, batch.offsets, flags)
+        wl.assert_results_equal(got, want, f"flags={flags}")
+
+
+def test_empty_and_degenerate_batches(checkers, world):
+    protos, _, _, orc, guts, _ = world
+    guts.set_default_parameters()
+    orc.set_params()
+    for seqs in ([], [b""], [b"", b"", b"A"], [b"ACDEFGHIK"]):
+        batch = synth.batch_from_strings(seqs)
+        want = orc.call_batch(batch, ALL)
+        got = guts.process_aa_seq_batch(batch.residues, batch.offsets, ALL)
+        wl.assert_results_equal(got, want, f"degenerate {seqs}")
+
+
+def test_against_reference_object_code(checkers, world, tmp_path):
+    if not os.path.exists(checkers.REF_SO):
+        pytest.skip("oracle/_ref/libckm_ref.so absent")
+    protos, sig, img, _, guts, _ = world
+    d = str(tmp_path)
+    api.save_kmer_hash_table(img, d)
+    synth.write_index_files(d, sig.n_functions, 12)
+    ref = checkers.Ref().open(d)
+    ref.set_params()
+    guts.set_default_parameters()
+    batch = wl.concat_batches(wl.edge_batch(protos), synth.make_proteins(4, protos, 2000))
+    want = ref.call_batch(batch, ALL)
+    got = guts.process_aa_seq_batch(batch.residues, batch.offsets, ALL)
+    wl.assert_results_equal(got, want, "cuda vs reference object code", check_ambig_indices=False)
+    assert [guts.best_function(r) for r in got["best"]] == want["best_function"]
+    ref.close()
+
+
+def test_open_from_directory_and_validation(checkers, world, tmp_path):
+    """T2: ckm_open reads the reference's files unchanged and applies its three validations."""
+    protos, sig, img, orc, _, _ = world
+    d = str(tmp_path)
+    api.save_kmer_hash_table(img, d)
+    synth.write_index_files(d, sig.n_functions, 3)
+    g = api.KmerGuts(kmer_dir=d)
+    assert g.num_sigs == synth.bucket_count(len(sig.keys))
+    assert g.function_at_index(5) == "function 5" and g.function_at_index(-1) == "INVALID_OFFSET"
+    assert g.function_at_index(10**7) == "INVALID_OFFSET" and g.otu_at_index(2) == "otu 2"
+    batch = synth.make_proteins(12, protos, 300)
+    orc.set_params()
+    wl.assert_results_equal(g.process_aa_seq_batch(batch.residues, batch.offsets, ALL), orc.call_batch(batch, ALL), "dir-open")
+    g.close()
+    for mutate in ("size", "version", "entry"):
+        bad = img.copy()
+        hdr = bad[:24].view(np.uint64)
+        if mutate == "size":
+            bad = bad[:-24]
+        elif mutate == "version":
+            hdr[2] = 2
+        else:
+            hdr[1] = 32
+        with pytest.raises(api.CkmError) as ei:
+            api.KmerGuts(image=bad)
+        assert ei.value.code == -3
+        assert orc.try_open_image(bad) == -3
+
+
+def test_window_saturation_long_protein(checkers):
+    """> 39998 stored hits in one run (kguts.cc:850-851): single-function image, one 45k-residue protein."""
+    protos, sig, img = wl.small_world(seed=21, n_protos=200, n_sigs=58_000, n_functions=1, otu_mode="minus1")
+    orc = checkers.Oracle().open_image(img)
+    guts = api.KmerGuts(image=img)
+    seq = synth.AA[protos.codes[:45_000]].tobytes()
+    batch = synth.batch_from_strings([seq, seq[:500], seq[100:41_000]])
+    for prm in (dict(), dict(order_constraint=1), dict(max_gap=3)):
+        orc.set_params(**prm)
+        guts.set_parameters(prm)
+        want = orc.call_batch(batch, ALL)
+        got = guts.process_aa_seq_batch(batch.residues, batch.offsets, ALL)
+        assert want["n_hits"] > 40_000
+        wl.assert_results_equal(got, want, f"saturation {prm}")
+    guts.close()
+    orc.close()
