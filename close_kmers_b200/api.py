@@ -70,6 +70,7 @@ def lib() -> C.CDLL:
     L.ckm_num_sigs.restype = C.c_uint64
     L.ckm_num_sigs.argtypes = [C.c_void_p]
     L.ckm_table_slot_bytes.argtypes = [C.c_void_p]
+    L.ckm_l2_fetch_granularity.argtypes = [C.c_void_p]
     L.ckm_set_default_params.argtypes = [C.c_void_p]
     L.ckm_set_params.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     L.ckm_get_params.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
@@ -87,6 +88,7 @@ def lib() -> C.CDLL:
     L.ckm_synchronize.argtypes = [C.c_void_p]
     L.ckm_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.ckm_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    L.ckm_calibrate_gather.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.ckm_image_build.argtypes = [C.c_uint64, C.c_uint64] + [C.c_void_p] * 6 + [C.c_size_t]
     L.ckm_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
     L.ckm_host_free.argtypes = [C.c_void_p]
@@ -205,6 +207,10 @@ class KmerGuts:
         return lib().ckm_table_slot_bytes(self._h)
 
     @property
+    def l2_fetch_granularity(self) -> int:
+        return lib().ckm_l2_fetch_granularity(self._h)
+
+    @property
     def stream(self) -> int:
         return lib().ckm_stream(self._h) or 0
 
@@ -220,6 +226,12 @@ class KmerGuts:
         p, s, n = C.c_double(), C.c_double(), C.c_uint64()
         _check(lib().ckm_profile_read(self._h, C.byref(p), C.byref(s), C.byref(n)))
         return p.value, s.value, n.value
+
+    def calibrate_gather(self, nbytes=16, unroll=4, rounds=64, blocks_per_sm=8):
+        """Independent random reads over the resident table: (accesses/s, ms)."""
+        r, ms = C.c_double(), C.c_double()
+        _check(lib().ckm_calibrate_gather(self._h, nbytes, unroll, rounds, blocks_per_sm, C.byref(r), C.byref(ms)))
+        return r.value, ms.value
 
     def synchronize(self):
         _check(lib().ckm_synchronize(self._h))

@@ -210,6 +210,19 @@ static int ctx_create(int device, ckm_ctx **out) {
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     c->sm_count = prop.multiProcessorCount;
+    // The probe is a random 16-byte gather: with the default L2 fetch granularity every miss drags a whole
+    // 128-byte line out of HBM (measured: 132 B of DRAM reads per probe, profiles/r1a).  Ask for single
+    // 32-byte sectors instead.  It is a device-wide hint; CKM_L2_FETCH=64|128 restores coarser fetches.
+    {
+        size_t gran = 32;
+        if (const char *g = getenv("CKM_L2_FETCH")) gran = (size_t)atoi(g);
+        if (gran == 32 || gran == 64 || gran == 128) {
+            if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran) != cudaSuccess) (void)cudaGetLastError();
+        }
+        size_t got = 0;
+        if (cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity) == cudaSuccess) c->l2_fetch = (int)got;
+        else (void)cudaGetLastError();
+    }
     ckm_set_default_params(c);
     *out = c;
     return 0;
@@ -306,6 +319,7 @@ extern "C" int32_t ckm_function_count(const ckm_ctx *c) { return (int32_t)c->fun
 extern "C" int32_t ckm_otu_count(const ckm_ctx *c) { return (int32_t)c->otu_names.size(); }
 extern "C" uint64_t ckm_num_sigs(const ckm_ctx *c) { return c->num_sigs; }
 extern "C" int ckm_table_slot_bytes(const ckm_ctx *c) { return c->slot_bytes; }
+extern "C" int ckm_l2_fetch_granularity(const ckm_ctx *c) { return c->l2_fetch; }
 extern "C" void *ckm_stream(ckm_ctx *c) { return (void *)c->stream; }
 extern "C" uint64_t ckm_launch_count(const ckm_ctx *c) { return c->launches; }
 extern "C" int ckm_synchronize(ckm_ctx *c) {
@@ -665,5 +679,92 @@ extern "C" int ckm_call_batch(ckm_ctx *c, const char *residues, const uint64_t *
     (void)want_scan;
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Calibration: what this GPU sustains for INDEPENDENT random sector reads over the resident table --
+// the physical ceiling of the hash probe, reported beside the streaming-copy roofline.
+// Each thread issues `UNROLL` independent loads per round at hashed slot indices; nothing depends on
+// the loaded values except a final XOR that keeps the loads alive.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return x;
+}
+
+template <int UNROLL, int BYTES>
+__global__ void __launch_bounds__(256)
+gather_calib_kernel(const uint8_t *__restrict__ base, uint64_t n_units /* BYTES-sized units */, uint32_t rounds,
+                    uint64_t magic, unsigned long long *__restrict__ sink) {
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t acc = 0;
+    for (uint32_t r = 0; r < rounds; r++) {
+        uint64_t idx[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const uint64_t h = mix64((tid * rounds + r) * UNROLL + u + 0x9e3779b97f4a7c15ull) >> 28;  // < 2^36
+            idx[u] = fast_mod(h, n_units, magic);
+        }
+        if (BYTES == 16) {
+            uint4 v[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) v[u] = __ldg(reinterpret_cast<const uint4 *>(base) + idx[u]);
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) acc ^= v[u].x ^ v[u].w;
+        } else {  // 32 B = one whole sector as two 16 B halves
+            uint4 v[UNROLL], w[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                v[u] = __ldg(reinterpret_cast<const uint4 *>(base) + 2 * idx[u]);
+                w[u] = __ldg(reinterpret_cast<const uint4 *>(base) + 2 * idx[u] + 1);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) acc ^= v[u].x ^ w[u].w;
+        }
+    }
+    if ((uint32_t)acc == 0x12345678u) atomicAdd(sink, 1ull);  // never true in practice; keeps the loads alive
+}
+
+// returns accesses/s through *rate; unroll in {1,4,8}, bytes in {16,32}
+extern "C" int ckm_calibrate_gather(ckm_ctx *c, int bytes, int unroll, uint32_t rounds, int blocks_per_sm, double *rate,
+                                    double *ms_out) {
+    if (!c || !c->table.p) return ckm_fail(CKM_ESTATE, "no table loaded");
+    CU(cudaSetDevice(c->device));
+    RC(c->totals.ensure(64));
+    const uint64_t table_bytes = c->num_sigs * (uint64_t)c->slot_bytes;
+    const uint64_t n_units = table_bytes / (uint64_t)bytes;
+    if (n_units == 0) return ckm_fail(CKM_EINVAL, "table too small");
+    const uint64_t magic = (uint64_t)((((unsigned __int128)1) << 64) / n_units);
+    const unsigned blocks = (unsigned)(c->sm_count * std::max(1, blocks_per_sm));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    auto launch = [&]() {
+#define CKM_CAL(U, B)                                                                                        \
+    gather_calib_kernel<U, B><<<blocks, 256, 0, c->stream>>>((const uint8_t *)c->table.p, n_units, rounds, magic, \
+                                                             (unsigned long long *)c->totals.p + 4)
+        if (bytes == 16 && unroll == 1) CKM_CAL(1, 16);
+        else if (bytes == 16 && unroll == 4) CKM_CAL(4, 16);
+        else if (bytes == 16 && unroll == 8) CKM_CAL(8, 16);
+        else if (bytes == 32 && unroll == 1) CKM_CAL(1, 32);
+        else if (bytes == 32 && unroll == 4) CKM_CAL(4, 32);
+        else CKM_CAL(8, 32);
+#undef CKM_CAL
+        c->launches++;
+    };
+    launch();  // warm-up
+    CU(cudaEventRecord(e0, c->stream));
+    launch();
+    CU(cudaEventRecord(e1, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double accesses = (double)blocks * 256.0 * rounds * (double)(unroll == 1 || unroll == 4 || unroll == 8 ? unroll : 8);
+    if (rate) *rate = accesses / (ms * 1e-3);
+    if (ms_out) *ms_out = ms;
     return 0;
 }

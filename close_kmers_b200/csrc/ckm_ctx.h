@@ -28,6 +28,7 @@ struct ckm_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     bool force_raw = false;
+    int l2_fetch = 0;  // cudaLimitMaxL2FetchGranularity in effect
 
     // signature table in HBM
     DevBuf table;

@@ -145,6 +145,8 @@ int32_t ckm_otu_count(const ckm_ctx *ctx);
 uint64_t ckm_num_sigs(const ckm_ctx *ctx);
 /* 16 = packed sector-friendly slots, 24 = verbatim slots (chosen at load, results identical) */
 int ckm_table_slot_bytes(const ckm_ctx *ctx);
+/* cudaLimitMaxL2FetchGranularity in effect on the ctx's device (the loader asks for 32-byte sectors) */
+int ckm_l2_fetch_granularity(const ckm_ctx *ctx);
 
 /* ---- parameters (KmerGuts::set_default_parameters / set_parameters, kguts.cc:236-268) -------------- */
 void ckm_set_default_params(ckm_ctx *ctx); /* order_constraint 0, min_hits 5, min_weighted_hits 0, max_gap 200 */
@@ -188,6 +190,12 @@ int ckm_read_totals(ckm_ctx *ctx, uint64_t totals[3]);
 int ckm_image_build(uint64_t nbuckets, uint64_t n, const uint64_t *keys, const int32_t *function_index,
                     const int32_t *otu_index, const uint16_t *avg_from_end, const float *function_wt, void *image_out,
                     size_t image_bytes);
+
+/* Calibration for roofline reports: independent random `bytes`-sized (16 or 32) reads over the resident
+ * table, `unroll` (1, 4 or 8) in flight per thread, `rounds` rounds, blocks_per_sm x SM-count blocks of 256
+ * threads.  Returns accesses per second -- the gather ceiling this GPU sustains at this table size. */
+int ckm_calibrate_gather(ckm_ctx *ctx, int bytes, int unroll, uint32_t rounds, int blocks_per_sm, double *accesses_per_s,
+                         double *ms);
 
 /* page-locked host memory for batch assembly (fast H2D) */
 int ckm_host_alloc(void **p, size_t bytes);
