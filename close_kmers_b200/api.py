@@ -23,6 +23,8 @@ CALL_DT = np.dtype([("start", "<u4"), ("end", "<u4"), ("count", "<i4"), ("functi
 HIT_DT = np.dtype([("which_kmer", "<u8"), ("offset", "<u4"), ("otu_index", "<i4"), ("function_index", "<i4"),
                    ("function_wt", "<f4"), ("avg_from_end", "<u2"), ("pad_", "<u2"), ("pad2_", "<u4")])
 OTU_DT = np.dtype([("otu_index", "<i4"), ("count", "<i4")])
+FAMILY_DT = np.dtype([("gfam", "<i4"), ("lfam", "<i4"), ("gfam_score", "<f4"), ("lfam_score", "<f4"), ("score", "<f4"),
+                      ("function_index", "<i4")])
 BEST_DT = np.dtype([("function_index", "<i4"), ("ambig_a", "<i4"), ("ambig_b", "<i4"), ("flags", "<u4"),
                     ("score", "<f4"), ("weighted_score", "<f4"), ("score_offset", "<f4")])
 SLOT_DT = np.dtype([("which_kmer", "<u8"), ("otu_index", "<i4"), ("avg_from_end", "<u2"), ("pad_", "<u2"),
@@ -89,6 +91,17 @@ def lib() -> C.CDLL:
     L.ckm_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.ckm_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.ckm_calibrate_gather.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.ckm_family_load.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                  C.c_void_p]
+    L.ckm_family_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
+    for f in ("ckm_family_pgf_name", "ckm_family_plf_name"):
+        getattr(L, f).restype = C.c_char_p
+        getattr(L, f).argtypes = [C.c_void_p, C.c_int32]
+    L.ckm_family_function_name.restype = C.c_char_p
+    L.ckm_family_function_name.argtypes = [C.c_void_p, C.c_void_p]
+    L.ckm_query_text.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int,
+                                 C.POINTER(C.c_void_p)]
+    L.ckm_free_text.argtypes = [C.c_void_p]
     L.ckm_image_build.argtypes = [C.c_uint64, C.c_uint64] + [C.c_void_p] * 6 + [C.c_size_t]
     L.ckm_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
     L.ckm_host_free.argtypes = [C.c_void_p]
@@ -275,6 +288,48 @@ class KmerGuts:
         t = (C.c_uint64 * 3)()
         _check(lib().ckm_read_totals(self._h, t))
         return int(t[0]), int(t[1]), int(t[2])
+
+    # -- request handlers (include/ckm_handlers.h) -----------------------------------------------------
+    def _take_text(self, p) -> str:
+        s = C.string_at(p).decode()
+        lib().ckm_free_text(p)
+        return s
+
+    def query_text(self, ids, residues, offsets, details=0, find_best_call=0) -> str:
+        """Response text of POST /query for one chunk (query_request.cc:103-152)."""
+        residues = np.ascontiguousarray(residues, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        bs = [s.encode() if isinstance(s, str) else s for s in ids]
+        arr = (C.c_char_p * len(bs))(*bs)
+        t = C.c_void_p()
+        _check(lib().ckm_query_text(self._h, arr, residues.ctypes.data, offsets.ctypes.data, len(offsets) - 1, details,
+                                    find_best_call, C.byref(t)))
+        return self._take_text(t)
+
+    # -- family voting (FamilyMapper) ------------------------------------------------------------------
+    def family_load(self, kmers, fam_off, fam_ids, pgf, plf, function):
+        kmers = np.ascontiguousarray(kmers, np.uint64)
+        fam_off = np.ascontiguousarray(fam_off, np.uint64)
+        fam_ids = np.ascontiguousarray(fam_ids, np.uint32)
+        mk = lambda xs: (C.c_char_p * len(xs))(*[x.encode() for x in xs])
+        _check(lib().ckm_family_load(self._h, len(kmers), kmers.ctypes.data, fam_off.ctypes.data, fam_ids.ctypes.data, len(pgf),
+                                     mk(pgf), mk(plf), mk(function)))
+
+    def find_best_family_match_batch(self, residues, offsets) -> np.ndarray:
+        """FamilyMapper::find_best_family_match (family_mapper.cc:65-205) for every sequence."""
+        residues = np.ascontiguousarray(residues, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        n = len(offsets) - 1
+        p = C.c_void_p()
+        _check(lib().ckm_family_batch(self._h, residues.ctypes.data, offsets.ctypes.data, n, C.byref(p)))
+        return _arr(p.value, n, FAMILY_DT)
+
+    def family_names(self, m) -> tuple:
+        """(gfam_id, lfam_id, function) strings of best_match_t for one FAMILY_DT record."""
+        L = lib()
+        rec = np.array([m], dtype=FAMILY_DT)
+        return (L.ckm_family_pgf_name(self._h, int(m["gfam"])).decode(), L.ckm_family_plf_name(self._h, int(m["lfam"])).decode(),
+                L.ckm_family_function_name(self._h, rec.ctypes.data).decode())
 
     def best_function(self, best_rec) -> str:
         """The `function` string find_best_call returns (kguts.cc:1160, 1176-1196)."""

@@ -9,16 +9,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libckm.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["ckm_api.cu"]
+SOURCES = ["csrc/ckm_api.cu", "host/handlers.cc"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler",
          "-fPIC,-Wall,-Wno-unused-function", "-cudart", "static"]
 
 
 def _newest_source() -> float:
     t = 0.0
-    for root in (CSRC, os.path.join(HERE, "..", "include")):
+    for root in (CSRC, os.path.join(HERE, "host"), os.path.join(HERE, "..", "include")):
         for f in os.listdir(root):
-            if f.endswith((".cu", ".cuh", ".h")):
+            if f.endswith((".cu", ".cuh", ".h", ".cc")):
                 t = max(t, os.path.getmtime(os.path.join(root, f)))
     return t
 
@@ -30,7 +30,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if os.path.exists(LIB):
             return LIB  # GPU box without a toolkit would still carry the prebuilt library
         raise RuntimeError(f"nvcc not found at {NVCC} and {LIB} is missing")
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(HERE, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode:
         sys.stderr.write(r.stdout + r.stderr)

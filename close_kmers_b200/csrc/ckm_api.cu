@@ -574,13 +574,11 @@ extern "C" int ckm_read_totals(ckm_ctx *c, uint64_t totals[3]) {
     return 0;
 }
 
-extern "C" int ckm_call_batch(ckm_ctx *c, const char *residues, const uint64_t *offsets, uint32_t n, uint32_t flags,
-                              ckm_batch_out_t *out) {
-    if (!c || !out || !offsets || (n && !residues && offsets[n] != 0)) return ckm_fail(CKM_EINVAL, "NULL argument");
+// H2D of one batch: residues (+32 zeroed bytes of slack) and offsets rebased to 0
+static int upload_batch(ckm_ctx *c, const char *residues, const uint64_t *offsets, uint32_t n, uint64_t *total_out,
+                        uint32_t *max_len_out) {
+    if (!offsets || (n && !residues && offsets[n] != offsets[0])) return ckm_fail(CKM_EINVAL, "NULL argument");
     CU(cudaSetDevice(c->device));
-    memset(out, 0, sizeof *out);
-    out->n = n;
-    uint64_t total = offsets[n];
     uint32_t max_len = 0;
     for (uint32_t i = 0; i < n; i++) {
         if (offsets[i + 1] < offsets[i]) return ckm_fail(CKM_EINVAL, "offsets must be non-decreasing (at %u)", i);
@@ -588,8 +586,7 @@ extern "C" int ckm_call_batch(ckm_ctx *c, const char *residues, const uint64_t *
         if (l > 500000000ull) return ckm_fail(CKM_EINVAL, "sequence %u longer than MAX_SEQ_LEN", i);  // kmer_params.h:6
         max_len = std::max<uint32_t>(max_len, (uint32_t)l);
     }
-    total -= offsets[0];
-    // H2D: residues (+16 B of slack, zeroed) and offsets rebased to 0
+    const uint64_t total = offsets[n] - offsets[0];
     RC(c->in_res.ensure(total + 32));
     RC(c->in_off.ensure(((size_t)n + 1) * 8));
     if (total) CU(cudaMemcpyAsync(c->in_res.p, residues + offsets[0], total, cudaMemcpyHostToDevice, c->stream));
@@ -602,6 +599,19 @@ extern "C" int ckm_call_batch(ckm_ctx *c, const char *residues, const uint64_t *
         h_off = t;
     }
     CU(cudaMemcpyAsync(c->in_off.p, h_off, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    *total_out = total;
+    *max_len_out = max_len;
+    return 0;
+}
+
+extern "C" int ckm_call_batch(ckm_ctx *c, const char *residues, const uint64_t *offsets, uint32_t n, uint32_t flags,
+                              ckm_batch_out_t *out) {
+    if (!c || !out) return ckm_fail(CKM_EINVAL, "NULL argument");
+    memset(out, 0, sizeof *out);
+    out->n = n;
+    uint64_t total = 0;
+    uint32_t max_len = 0;
+    RC(upload_batch(c, residues, offsets, n, &total, &max_len));
     RC(run_device(c, (const uint8_t *)c->in_res.p, (const uint64_t *)c->in_off.p, n, total, std::max(max_len, 1u), flags));
 
     // totals decide the size of the compacted outputs
@@ -768,3 +778,5 @@ extern "C" int ckm_calibrate_gather(ckm_ctx *c, int bytes, int unroll, uint32_t 
     if (ms_out) *ms_out = ms;
     return 0;
 }
+
+#include "ckm_family.cuh"

@@ -53,6 +53,17 @@ struct ckm_ctx {
     DevBuf in_res, in_off, totals, hits, hit_keys, hit_avg, n_hits, stored_idx, calls, calls_work, n_calls;
     DevBuf otus, n_otus, best, ps_blocks;
     DevBuf hit_off, call_off, otu_off, hits_out, calls_out, otus_out;
+    // family voting (ckm_family.cuh)
+    struct Family {
+        bool loaded = false;
+        DevBuf table, ids, fam_func, fam_pgf, func_sid;  // device images of the side tables
+        uint64_t mask = 0;
+        uint32_t n_fams = 0, n_functions = 0, hypo_sid = 0;
+        std::vector<std::string> pgf_names, plf;         // host strings for the response text
+        DevBuf hit_fam, E, gcap, gofs, gscratch, matches;  // per-batch work buffers
+    } fam;
+    PinBuf h_fam;
+
     // pinned host buffers handed out through ckm_batch_out_t
     PinBuf h_off, h_totals, h_hit_off, h_hits, h_call_off, h_calls, h_otu_off, h_otus, h_best;
 
@@ -61,7 +72,10 @@ struct ckm_ctx {
                        &n_calls, &otus, &n_otus, &best, &ps_blocks, &hit_off, &call_off, &otu_off, &hits_out, &calls_out,
                        &otus_out};
         for (auto b : d) b->release();
-        PinBuf *h[] = {&h_off, &h_totals, &h_hit_off, &h_hits, &h_call_off, &h_calls, &h_otu_off, &h_otus, &h_best};
+        DevBuf *f[] = {&fam.table, &fam.ids, &fam.fam_func, &fam.fam_pgf, &fam.func_sid, &fam.hit_fam, &fam.E, &fam.gcap,
+                       &fam.gofs, &fam.gscratch, &fam.matches};
+        for (auto b : f) b->release();
+        PinBuf *h[] = {&h_off, &h_totals, &h_hit_off, &h_hits, &h_call_off, &h_calls, &h_otu_off, &h_otus, &h_best, &h_fam};
         for (auto b : h) b->release();
     }
 };

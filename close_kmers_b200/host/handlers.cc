@@ -1,0 +1,117 @@
+// Host side of the request handlers, written only against the C ABI (include/ckm.h): one batch call per
+// body chunk, then the reference's response text rebuilt from the flat results.  Floats are printed
+// through std::ostream exactly like the reference (default precision 6), so the text is byte-identical.
+#include "../../include/ckm_handlers.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <sstream>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace {
+
+char *dup_text(const std::string &s) {
+    char *p = (char *)malloc(s.size() + 1);
+    if (!p) return nullptr;
+    memcpy(p, s.data(), s.size());
+    p[s.size()] = 0;
+    return p;
+}
+
+// KmerGuts::format_call, kguts.cc:939-947
+void put_call(std::ostream &os, const ckm_ctx *ctx, const ckm_call_t &c) {
+    os << "CALL\t" << c.start << "\t" << c.end << "\t" << c.count;
+    os << "\t" << c.function_index << "\t" << ckm_function_at_index(ctx, (int32_t)c.function_index);
+    os << "\t" << c.weighted_hits << "\n";
+}
+
+// KmerGuts::format_hit, kguts.cc:949-959
+void put_hit(std::ostream &os, const ckm_ctx *ctx, const ckm_hit_t &h) {
+    char dc[CKM_KMER_SIZE + 1];
+    ckm_decoded_kmer(h.which_kmer, dc);
+    os << "HIT\t" << h.offset << "\t" << dc << "\t" << h.avg_from_end << "\t" << ckm_function_at_index(ctx, h.function_index)
+       << "\t" << h.function_wt << "\t" << h.otu_index << "\n";
+}
+
+// KmerOtuStats::finalize (kguts.h:214-218) + format_otu_stats (kguts.cc:961-973)
+void put_otu_stats(std::ostream &os, const std::string &id, uint64_t size, const ckm_otu_t *otus, uint64_t n) {
+    std::vector<std::pair<int, int>> by_count;
+    by_count.reserve(n);
+    for (uint64_t i = 0; i < n; i++) by_count.emplace_back(otus[i].otu_index, otus[i].count);
+    std::sort(by_count.begin(), by_count.end(),
+              [](const std::pair<int, int> &lhs, const std::pair<int, int> &rhs) { return rhs.second < lhs.second; });
+    os << "OTU-COUNTS\t" << id << "[" << size << "]";
+    const size_t top = std::min(by_count.size(), (size_t)5);
+    for (size_t i = 0; i < top; i++) os << "\t" << by_count[i].second << "-" << by_count[i].first;
+    os << "\n";
+}
+
+// find_best_call's `function` out-parameter, kguts.cc:1160 and 1176-1196
+std::string best_function(const ckm_ctx *ctx, const ckm_best_t &b) {
+    if (b.flags & CKM_BEST_AMBIG) {
+        std::string f1 = ckm_function_at_index(ctx, b.ambig_a);
+        std::string f2 = ckm_function_at_index(ctx, b.ambig_b);
+        if (f2 > f1) std::swap(f1, f2);
+        return f1 + " ?? " + f2;
+    }
+    if (b.function_index >= 0) return ckm_function_at_index(ctx, b.function_index);
+    return "";
+}
+
+}  // namespace
+
+extern "C" {
+
+int ckm_query_text(ckm_ctx *ctx, const char *const *ids, const char *residues, const uint64_t *offsets, uint32_t n,
+                   int details, int find_best_call, char **text) {
+    if (!text) return CKM_EINVAL;
+    *text = nullptr;
+    // the handler always builds calls + OTU stats; hits only with details=1 (query_request.cc:105-119)
+    uint32_t flags = CKM_WANT_CALLS | CKM_WANT_OTU;
+    if (details) flags |= CKM_WANT_HITS;
+    if (find_best_call) flags |= CKM_WANT_BEST;
+    ckm_batch_out_t o;
+    int rc = ckm_call_batch(ctx, residues, offsets, n, flags, &o);
+    if (rc) return rc;
+    std::ostringstream os;
+    for (uint32_t i = 0; i < n; i++) {
+        const std::string id = ids[i];
+        const uint64_t len = offsets[i + 1] - offsets[i];
+        if (find_best_call) {  // query_request.cc:124-135
+            const std::string fn = best_function(ctx, o.best[i]);
+            if (!fn.empty()) os << id << "\t" << fn << "\t" << o.best[i].score << "\t" << o.best[i].weighted_score << "\n";
+        } else {  // 136-151
+            os << "PROTEIN-ID\t" << id << "\t" << len << "\n";
+            for (uint64_t k = o.call_offsets[i]; k < o.call_offsets[i + 1]; k++) put_call(os, ctx, o.calls[k]);
+            if (details)
+                for (uint64_t k = o.hit_offsets[i]; k < o.hit_offsets[i + 1]; k++) put_hit(os, ctx, o.hits[k]);
+            put_otu_stats(os, id, len, o.otus + o.otu_offsets[i], o.otu_offsets[i + 1] - o.otu_offsets[i]);
+        }
+    }
+    *text = dup_text(os.str());
+    return *text ? 0 : CKM_ENOMEM;
+}
+
+char *ckm_format_call(const ckm_ctx *ctx, const ckm_call_t *call) {
+    std::ostringstream os;
+    put_call(os, ctx, *call);
+    return dup_text(os.str());
+}
+char *ckm_format_hit(const ckm_ctx *ctx, const ckm_hit_t *hit) {
+    std::ostringstream os;
+    put_hit(os, ctx, *hit);
+    return dup_text(os.str());
+}
+char *ckm_format_otu_stats(const char *id, uint64_t seq_len, const ckm_otu_t *otus, uint64_t n_otus) {
+    std::ostringstream os;
+    put_otu_stats(os, id, seq_len, otus, n_otus);
+    return dup_text(os.str());
+}
+char *ckm_best_function(const ckm_ctx *ctx, const ckm_best_t *best) { return dup_text(best_function(ctx, *best)); }
+
+void ckm_free_text(char *text) { free(text); }
+
+}  // extern "C"

@@ -199,6 +199,114 @@ def make_proteins_parallel(seed: int, protos: Prototypes, n: int, chunk: int = 3
     return Batch(np.concatenate([p.residues for p in parts]), offsets)
 
 
+@dataclasses.dataclass
+class FamilyTables:
+    """What NRLoader / load_families leave in KmerPegMapping (kmer.h:118-127), plus interned string ids."""
+    kmers: np.ndarray      # uint64, distinct
+    fam_off: np.ndarray    # uint64, len(kmers)+1
+    fam_ids: np.ndarray    # uint32, lists deduped
+    pgf: list
+    plf: list
+    function: list
+    # interning used by the oracle (the product interns on its own in ckm_family_load)
+    fam_func_sid: np.ndarray
+    fam_pgf: np.ndarray
+    pgf_names: list
+    func_sid: np.ndarray
+    hypo_sid: int
+
+    @property
+    def n_fams(self) -> int:
+        return len(self.pgf)
+
+    @property
+    def n_pgf(self) -> int:
+        return len(self.pgf_names)
+
+
+def make_families(seed: int, sig: Signatures, fams_per_function: int = 4, max_list: int = 8, coverage: float = 0.9,
+                  hypothetical_every: int = 17) -> FamilyTables:
+    """each signature k-mer maps to 1+Geom(0.5) families (cap 8) drawn from the families of its own
+    function (4 per function, two PGFs per function); ``coverage`` of the k-mers have a list at all.  Every
+    ``hypothetical_every``-th function's families are annotated "hypothetical protein"."""
+    rng = np.random.default_rng(seed)
+    F = sig.n_functions
+    n_fams = F * fams_per_function
+    fam_function_idx = np.arange(n_fams) // fams_per_function
+    names = function_names(F)
+    function = [("hypothetical protein" if (f % hypothetical_every == 0) else names[f]) for f in fam_function_idx]
+    pgf = [f"PGF_{(f // 2):08d}" for f in range(n_fams)]
+    plf = [f"PLF_{1000 + f % 7}_{f:08d}" for f in range(n_fams)]
+    pick = rng.random(len(sig.keys)) < coverage
+    kmers = sig.keys[pick].astype(np.uint64)
+    kf = sig.fI[pick].astype(np.int64)
+    cnt = np.minimum(rng.geometric(0.5, len(kmers)), max_list).astype(np.int64)
+    fam_off = np.zeros(len(kmers) + 1, dtype=np.uint64)
+    fam_off[1:] = np.cumsum(cnt)
+    owner = np.repeat(np.arange(len(kmers)), cnt)
+    rank = np.arange(int(fam_off[-1])) - fam_off[:-1].astype(np.int64)[owner]
+    # distinct ids within a list: own function's families first, then the neighbouring function's
+    start = rng.integers(0, fams_per_function, len(kmers))[owner]
+    slot = (start + rank) % (2 * fams_per_function)
+    fam_ids = ((kf[owner] * fams_per_function + slot) % n_fams).astype(np.uint32)
+    # interning
+    sid = {"hypothetical protein": 0}
+    func_sid = np.array([sid.setdefault(nm, len(sid)) for nm in names], dtype=np.uint32)
+    fam_func_sid = np.array([sid.setdefault(nm, len(sid)) for nm in function], dtype=np.uint32)
+    pg = {}
+    fam_pgf = np.array([pg.setdefault(nm, len(pg)) for nm in pgf], dtype=np.uint32)
+    return FamilyTables(kmers, fam_off, fam_ids, pgf, plf, function, fam_func_sid, fam_pgf, list(pg.keys()), func_sid, 0)
+
+
+NCBI11_AAS = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"  # NCBI genetic code 11, TCAG order
+
+
+def _codon_tables():
+    """aa code (0..19) -> (codons[6,3] uint8 ASCII, count)."""
+    order = "TCAG"
+    by_aa = {}
+    for pos, aa in enumerate(NCBI11_AAS):
+        codon = order[pos // 16] + order[(pos // 4) % 4] + order[pos % 4]
+        by_aa.setdefault(aa, []).append(codon)
+    cod = np.zeros((20, 6, 3), dtype=np.uint8)
+    cnt = np.zeros(20, dtype=np.int64)
+    for i, a in enumerate(AA.tobytes().decode()):
+        cs = by_aa[a]
+        cnt[i] = len(cs)
+        for k in range(6):
+            cod[i, k] = np.frombuffer(cs[k % len(cs)].encode(), np.uint8)
+    return cod, cnt
+
+
+_COMP = np.arange(256, dtype=np.uint8)
+for _a, _b in zip(b"ACGTacgtN", b"TGCAtgcaN"):
+    _COMP[_a] = _b
+
+
+def make_reads(seed: int, protos: Prototypes, n: int, read_len: int = 150, n_rate: float = 0.005) -> Batch:
+    """Reads cut from back-translated prototypes (synonymous codons uniform), random strand and phase,
+    0.5% N.  All reads have ``read_len`` bases."""
+    rng = np.random.default_rng(seed)
+    cod, cnt = _codon_tables()
+    naa = read_len // 3 + 2
+    P = protos.n
+    p = rng.integers(0, P, n)
+    plen = protos.offsets[p + 1] - protos.offsets[p]
+    start = (rng.random(n) * np.maximum(plen - naa, 1)).astype(np.int64)
+    idx = protos.offsets[p][:, None] + np.minimum(start[:, None] + np.arange(naa)[None, :], (plen - 1)[:, None])
+    aa = protos.codes[idx]                                  # n x naa
+    pick = (rng.random((n, naa)) * cnt[aa]).astype(np.int64)
+    dna = cod[aa, pick].reshape(n, naa * 3)                 # n x 3*naa
+    phase = rng.integers(0, 3, n)
+    cols = phase[:, None] + np.arange(read_len)[None, :]
+    reads = np.take_along_axis(dna, cols, axis=1)
+    rev = rng.random(n) < 0.5
+    reads[rev] = _COMP[reads[rev][:, ::-1]]
+    reads[rng.random(reads.shape) < n_rate] = ord("N")
+    offsets = (np.arange(n + 1, dtype=np.uint64) * np.uint64(read_len))
+    return Batch(reads.reshape(-1).copy(), offsets)
+
+
 def batch_from_strings(seqs) -> Batch:
     bs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
     offsets = np.zeros(len(bs) + 1, dtype=np.uint64)

@@ -184,6 +184,75 @@ int ckm_device_results(ckm_ctx *ctx, ckm_device_out_t *out);
 /* synchronises and copies {probes, hits, calls} of the last batch to the host */
 int ckm_read_totals(ckm_ctx *ctx, uint64_t totals[3]);
 
+/* ---- family voting: FamilyMapper::find_best_family_match (family_mapper.cc:46-205, 287-330) -------------- */
+
+/* The read-only family side tables that NRLoader / load_families leave in KmerPegMapping (kmer.h:118-127):
+ * kmer_to_family_id_ as a CSR (kmers[k] -> fam_ids[fam_offsets[k] .. fam_offsets[k+1]), lists deduped as
+ * kmer.cc:216-230 leaves them) and family_data_ (pgf, plf, function per encoded family id 0..n_families-1).
+ * Uploads device images of both; may be called again to replace them. */
+int ckm_family_load(ckm_ctx *ctx, uint64_t n_kmers, const uint64_t *kmers, const uint64_t *fam_offsets,
+                    const uint32_t *fam_ids, uint32_t n_families, const char *const *pgf, const char *const *plf,
+                    const char *const *function);
+
+/* best_match_t (family_mapper.h:20-28) with names left as ids */
+typedef struct {
+    int32_t gfam;           /* id of the best PGF (ckm_family_pgf_name), -1 if none */
+    int32_t lfam;           /* encoded family id whose PLF is the best (ckm_family_plf_name), -1 if none */
+    float gfam_score;       /* rolled-up weighted_total of the best PGF */
+    float lfam_score;       /* weighted_total of the best family */
+    float score;            /* best_call_score of find_best_call */
+    int32_t function_index; /* confident best call, else -1 ("hypothetical protein", family_mapper.cc:103-123) */
+} ckm_family_match_t;
+
+/* find_best_family_match for every sequence of the batch: hits -> per-family (hit_total, weighted_total +=
+ * 1/|families of the k-mer|, in hit order) -> find_best_call -> families with hit_total >= 3 whose function
+ * equals the called function -> best PLF, best rolled-up PGF.  Exactly tied maxima resolve to the smallest
+ * id (the reference resolves them by std::unordered_map iteration order); PGF roll-ups are f32 sums in
+ * ascending hash-slot order, within 1e-6 relative of the reference's unordered sums. */
+int ckm_family_batch(ckm_ctx *ctx, const char *residues, const uint64_t *offsets, uint32_t n,
+                     const ckm_family_match_t **matches);
+
+const char *ckm_family_pgf_name(const ckm_ctx *ctx, int32_t gfam);   /* "" if out of range */
+const char *ckm_family_plf_name(const ckm_ctx *ctx, int32_t lfam);
+/* best_match_t::function for a match: function.index name or "hypothetical protein" */
+const char *ckm_family_function_name(const ckm_ctx *ctx, const ckm_family_match_t *m);
+
+/* ---- fastq reads: 6-frame translation + calling + family voting + best frame ---------------------------
+ * FqProcessRequest::on_parsed_seq (fq_process_request.cc:298-365) over DNASequence::get_possible_proteins
+ * (dna_seq.cc:9-47, dna_seq.h:28-111) and TranslationTable code 11 (trans_table.cc:8-84). */
+typedef struct {
+    uint32_t length;        /* prot.length() of the fragment (> 10) */
+    ckm_family_match_t m;   /* find_best_family_match of the fragment */
+} ckm_fq_match_t;           /* 28 bytes */
+
+typedef struct {
+    uint32_t n;                    /* reads */
+    const int32_t *best_frame;     /* n: 1,2,3,-1,-2,-3, or 0 when best_score == 0 (no output line) */
+    const double *best_score;      /* n: sum of the winning frame's fragment scores up to the winning fragment */
+    const uint64_t *match_offsets; /* n+1: CSR into matches */
+    const ckm_fq_match_t *matches; /* the winning frame's processed fragments, in order, up to the winning one */
+    uint64_t n_fragments;          /* fragments longer than 10 aa over all reads and frames */
+    uint64_t n_probes;
+} ckm_fq_out_t;
+
+/* bases: the n reads concatenated; offsets[i]..offsets[i+1] is read i (IUPAC letters, either case, U = T).
+ * Needs ckm_family_load.  Every fragment is called with the ctx's current parameters (the reference's fq
+ * path never calls set_parameters: fq_process_request.cc:241). */
+int ckm_fq_batch(ckm_ctx *ctx, const char *bases, const uint64_t *offsets, uint32_t n, ckm_fq_out_t *out);
+
+/* D1/D2 alone: the protein fragments (> min_len aa) of all six frames, as a protein batch.  frag_frame_offsets
+ * has 6n+1 entries: fragments of (read r, frame slot s) are [ffo[6r+s], ffo[6r+s+1]) with slots ordered
+ * {1,2,3,-1,-2,-3}.  Host pointers into ctx-owned pinned memory, valid until the next call. */
+typedef struct {
+    uint32_t n_reads;
+    uint64_t n_fragments;
+    const uint64_t *frag_frame_offsets; /* 6n+1 */
+    const uint64_t *frag_offsets;       /* n_fragments+1, into residues */
+    const char *residues;
+} ckm_fq_fragments_t;
+int ckm_fq_translate(ckm_ctx *ctx, const char *bases, const uint64_t *offsets, uint32_t n, uint32_t min_len,
+                     ckm_fq_fragments_t *out);
+
 /* ---- image builder: KmerGuts(dir, nbuckets) + insert_kmer + save_kmer_hash_table (kguts.cc:77-115, 188-234).
  * Host-side; writes the reference's file bytes (header + nbuckets slots) into image_out, which must be
  * exactly 24 + 24*nbuckets bytes.  keys > MAX_ENCODED are skipped like kguts.cc:206-210. */

@@ -480,6 +480,274 @@ void orc_out_free(orc_out_t *pub) {
     free(o);
 }
 
+/* ---- F1/F2: family voting ---- */
+struct orc_family {
+    uint64_t n_kmers;
+    uint64_t *kmers;    /* sorted */
+    uint64_t *perm_off; /* n_kmers: offset of the list of sorted k-mer i */
+    uint32_t *perm_cnt;
+    uint32_t *fam_ids;
+    uint32_t n_fams, n_pgf, n_functions, hypo_sid;
+    uint32_t *fam_func_sid, *fam_pgf, *func_sid;
+};
+
+typedef struct { uint64_t k, off; uint32_t cnt; } kent_t;
+static int kent_cmp(const void *a, const void *b) {
+    const kent_t *x = a, *y = b;
+    return x->k < y->k ? -1 : x->k > y->k;
+}
+static void *dupmem(const void *p, size_t n) {
+    void *q = malloc(n ? n : 1);
+    if (n) memcpy(q, p, n);
+    return q;
+}
+
+orc_family *orc_family_new(uint64_t n_kmers, const uint64_t *kmers, const uint64_t *fam_off, const uint32_t *fam_ids,
+                           uint32_t n_fams, const uint32_t *fam_func_sid, const uint32_t *fam_pgf, uint32_t n_pgf,
+                           uint32_t n_functions, const uint32_t *func_sid, uint32_t hypo_sid) {
+    orc_family *f = calloc(1, sizeof *f);
+    kent_t *e = malloc(sizeof *e * (n_kmers ? n_kmers : 1));
+    for (uint64_t i = 0; i < n_kmers; i++) e[i] = (kent_t){kmers[i], fam_off[i], (uint32_t)(fam_off[i + 1] - fam_off[i])};
+    qsort(e, n_kmers, sizeof *e, kent_cmp);
+    f->n_kmers = n_kmers;
+    f->kmers = malloc(8 * (n_kmers ? n_kmers : 1));
+    f->perm_off = malloc(8 * (n_kmers ? n_kmers : 1));
+    f->perm_cnt = malloc(4 * (n_kmers ? n_kmers : 1));
+    for (uint64_t i = 0; i < n_kmers; i++) { f->kmers[i] = e[i].k; f->perm_off[i] = e[i].off; f->perm_cnt[i] = e[i].cnt; }
+    free(e);
+    f->fam_ids = dupmem(fam_ids, 4 * (n_kmers ? fam_off[n_kmers] : 0));
+    f->n_fams = n_fams; f->n_pgf = n_pgf; f->n_functions = n_functions; f->hypo_sid = hypo_sid;
+    f->fam_func_sid = dupmem(fam_func_sid, 4 * (size_t)n_fams);
+    f->fam_pgf = dupmem(fam_pgf, 4 * (size_t)n_fams);
+    f->func_sid = dupmem(func_sid, 4 * (size_t)n_functions);
+    return f;
+}
+
+void orc_family_free(orc_family *f) {
+    if (!f) return;
+    free(f->kmers); free(f->perm_off); free(f->perm_cnt); free(f->fam_ids);
+    free(f->fam_func_sid); free(f->fam_pgf); free(f->func_sid); free(f);
+}
+
+static int64_t fam_find(const orc_family *f, uint64_t k) {
+    uint64_t lo = 0, hi = f->n_kmers;
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) / 2;
+        if (f->kmers[mid] < k) lo = mid + 1; else hi = mid;
+    }
+    return (lo < f->n_kmers && f->kmers[lo] == k) ? (int64_t)lo : -1;
+}
+
+void orc_family_batch(const orc_table *t, const orc_params_t *p, const orc_family *f, const char *residues,
+                      const uint64_t *offsets, uint32_t n, ckm_family_match_t *out) {
+    /* sequence_accumulated_score_t per family (family_mapper.h:33-49), dense + touched list */
+    uint32_t *hit_total = calloc(f->n_fams ? f->n_fams : 1, 4);
+    float *weighted = calloc(f->n_fams ? f->n_fams : 1, 4);
+    uint8_t *seen = calloc(f->n_fams ? f->n_fams : 1, 1);
+    float *rollup = calloc(f->n_pgf ? f->n_pgf : 1, 4);
+    uint8_t *pseen = calloc(f->n_pgf ? f->n_pgf : 1, 1);
+    uint32_t flags = CKM_WANT_CALLS | CKM_WANT_HITS | CKM_WANT_BEST;
+    for (uint32_t i = 0; i < n; i++) {
+        /* ingest_protein (46-63): process_aa_seq with calls + on_hit callback, no OTU stats */
+        uint64_t off2[2] = {0, offsets[i + 1] - offsets[i]};
+        orc_out_t *o = orc_call_batch(t, p, residues + offsets[i], off2, 1, flags);
+        for (uint64_t h = 0; h < o->o.hit_offsets[1]; h++) { /* on_hit, 287-330 (family mode) */
+            int64_t ki = fam_find(f, o->o.hits[h].which_kmer);
+            if (ki < 0) continue;
+            uint32_t cnt = f->perm_cnt[ki];
+            float weight = 1.0f / (float)cnt;
+            for (uint32_t e = 0; e < cnt; e++) {
+                uint32_t fam = f->fam_ids[f->perm_off[ki] + e];
+                if (fam >= f->n_fams) continue; /* no family_data_ entry: skipped at 146-148 */
+                seen[fam] = 1;
+                hit_total[fam]++;
+                weighted[fam] += weight;
+            }
+        }
+        const ckm_best_t *b = &o->o.best[0];
+        /* 98-123: empty or ambiguous function -> "hypothetical protein" (allow_ambiguous_functions_ is false) */
+        uint32_t sid = f->hypo_sid;
+        int32_t fidx = -1;
+        if (b->function_index >= 0 && (uint32_t)b->function_index < f->n_functions) {
+            sid = f->func_sid[b->function_index];
+            fidx = b->function_index;
+        }
+        ckm_family_match_t m = {-1, -1, 0.0f, 0.0f, b->score, fidx};
+        /* 137-178, visiting families in ascending id instead of unordered_map order */
+        for (uint32_t fam = 0; fam < f->n_fams; fam++) {
+            if (!seen[fam]) continue;
+            if (hit_total[fam] >= 3 && f->fam_func_sid[fam] == sid) {
+                rollup[f->fam_pgf[fam]] += weighted[fam];
+                pseen[f->fam_pgf[fam]] = 1;
+                if (weighted[fam] > m.lfam_score) {
+                    m.lfam_score = weighted[fam];
+                    m.lfam = (int32_t)fam;
+                }
+            }
+        }
+        for (uint32_t g = 0; g < f->n_pgf; g++) { /* 187-197 */
+            if (!pseen[g]) continue;
+            if (rollup[g] > m.gfam_score) {
+                m.gfam_score = rollup[g];
+                m.gfam = (int32_t)g;
+            }
+            rollup[g] = 0;
+            pseen[g] = 0;
+        }
+        for (uint32_t fam = 0; fam < f->n_fams; fam++)
+            if (seen[fam]) { seen[fam] = 0; hit_total[fam] = 0; weighted[fam] = 0; }
+        out[i] = m;
+        orc_out_free(o);
+    }
+    free(hit_total); free(weighted); free(seen); free(rollup); free(pseen);
+}
+
+/* ---- D1: TranslationTable, trans_table.cc:8-63.  NCBI genetic code 11 listed in TCAG order; the table is
+ * re-indexed by encode_triple (A=0,C=1,G=2,T/U=3 -> 16*b1+4*b2+b3), slot 64 = 'X' for ambiguous codons ---- */
+static const char NCBI11_AAS[65] = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+static char AA11[65];
+static int aa11_ready = 0;
+static int encode_char(char c) { /* trans_table.h:47-68 */
+    switch (c) {
+        case 'a': case 'A': return 0;
+        case 'c': case 'C': return 1;
+        case 'g': case 'G': return 2;
+        case 't': case 'u': case 'T': case 'U': return 3;
+        default: return 4;
+    }
+}
+static void aa11_init(void) {
+    if (aa11_ready) return;
+    const char order[4] = {'T', 'C', 'A', 'G'};
+    for (int pos = 0; pos < 64; pos++) {
+        int e1 = encode_char(order[pos / 16]), e2 = encode_char(order[(pos / 4) % 4]), e3 = encode_char(order[pos % 4]);
+        AA11[e1 * 16 + e2 * 4 + e3] = NCBI11_AAS[pos];
+    }
+    AA11[64] = 'X';
+    aa11_ready = 1;
+}
+/* dna_seq.h:28-111 */
+static char complement(char c) {
+    switch (c) {
+        case 'a': return 't'; case 'A': return 'T';
+        case 'c': return 'g'; case 'C': return 'G';
+        case 'g': return 'c'; case 'G': return 'C';
+        case 't': case 'u': return 'a';
+        case 'T': case 'U': return 'A';
+        case 'm': return 'k'; case 'M': return 'K';
+        case 'r': return 'y'; case 'R': return 'Y';
+        case 'w': return 'w'; case 'W': return 'W';
+        case 's': return 'S'; case 'S': return 'S';
+        case 'y': return 'r'; case 'Y': return 'R';
+        case 'k': return 'm'; case 'K': return 'M';
+        case 'b': return 'v'; case 'B': return 'V';
+        case 'd': return 'h'; case 'D': return 'H';
+        case 'h': return 'd'; case 'H': return 'D';
+        case 'v': return 'b'; case 'V': return 'B';
+        case 'n': return 'n'; case 'N': return 'N';
+        default: return c;
+    }
+}
+/* D2: get_translated_frame (dna_seq.cc:25-37) over seq() or reverse_seq() (39-47), translate (trans_table.cc:65-84) */
+size_t orc_translate_frame(const char *dna, size_t len, int frame, char *out) {
+    aa11_init();
+    size_t off = (size_t)(frame < 0 ? -frame : frame) - 1, n = 0;
+    for (size_t i = off; i + 3 <= len; i += 3) {
+        char c[3];
+        for (int k = 0; k < 3; k++) c[k] = frame > 0 ? dna[i + k] : complement(dna[len - 1 - (i + k)]);
+        int e1 = encode_char(c[0]), e2 = encode_char(c[1]), e3 = encode_char(c[2]);
+        out[n++] = AA11[(e1 < 4 && e2 < 4 && e3 < 4) ? e1 * 16 + e2 * 4 + e3 : 64];
+    }
+    out[n] = 0;
+    return n;
+}
+
+typedef struct {
+    orc_fq_out_t pub;
+    int32_t *best_frame;
+    double *best_score;
+    uint64_t *match_off;
+    ckm_fq_match_t *matches;
+} fq_impl_t;
+
+/* D3: fq_process_request.cc:298-365.  boost::split(..., "*", token_compress_on) (dna_seq.cc:17) yields the
+ * maximal stop-free runs (plus empty tokens that the length filter drops). */
+orc_fq_out_t *orc_fq_batch(const orc_table *t, const orc_params_t *p, const orc_family *f, const char *bases,
+                           const uint64_t *offsets, uint32_t n) {
+    static const int FRAMES[6] = {1, 2, 3, -1, -2, -3};
+    fq_impl_t *o = calloc(1, sizeof *o);
+    o->best_frame = calloc(n ? n : 1, sizeof(int32_t));
+    o->best_score = calloc(n ? n : 1, sizeof(double));
+    o->match_off = calloc((size_t)n + 1, 8);
+    uint64_t cap = 64, nm = 0, nfrag = 0;
+    o->matches = malloc(cap * sizeof *o->matches);
+    ckm_fq_match_t *cur = NULL, *best = NULL;
+    size_t cur_cap = 0;
+    for (uint32_t r = 0; r < n; r++) {
+        const char *dna = bases + offsets[r];
+        size_t len = (size_t)(offsets[r + 1] - offsets[r]);
+        char *prot = malloc(len / 3 + 2);
+        if (len / 3 + 1 > cur_cap) {
+            cur_cap = len / 3 + 1;
+            cur = realloc(cur, cur_cap * sizeof *cur);
+            best = realloc(best, cur_cap * sizeof *best);
+        }
+        double best_score = 0.0;
+        int best_frame = 0;
+        size_t best_n = 0;
+        for (int fi = 0; fi < 6; fi++) {
+            size_t na = orc_translate_frame(dna, len, FRAMES[fi], prot);
+            double score = 0.0;
+            size_t ncur = 0;
+            for (size_t s = 0; s <= na;) {
+                size_t e = s;
+                while (e < na && prot[e] != '*') e++;
+                if (e - s > 10) { /* prot.length() > 10 */
+                    uint64_t off2[2] = {0, e - s};
+                    ckm_family_match_t m;
+                    orc_family_batch(t, p, f, prot + s, off2, 1, &m);
+                    cur[ncur].length = (uint32_t)(e - s);
+                    cur[ncur].m = m;
+                    ncur++;
+                    nfrag++;
+                    score += m.score;
+                }
+                if (score > best_score) { /* 340-346, inside the fragment loop */
+                    best_score = score;
+                    best_frame = FRAMES[fi];
+                    best_n = ncur;
+                    memcpy(best, cur, ncur * sizeof *cur);
+                }
+                s = e + 1;
+            }
+        }
+        o->best_frame[r] = best_score > 0.0 ? best_frame : 0;
+        o->best_score[r] = best_score;
+        if (best_score > 0.0) {
+            while (nm + best_n > cap) { cap *= 2; o->matches = realloc(o->matches, cap * sizeof *o->matches); }
+            memcpy(o->matches + nm, best, best_n * sizeof *best);
+            nm += best_n;
+        }
+        o->match_off[r + 1] = nm;
+        free(prot);
+    }
+    free(cur);
+    free(best);
+    o->pub.o.n = n;
+    o->pub.o.best_frame = o->best_frame;
+    o->pub.o.best_score = o->best_score;
+    o->pub.o.match_offsets = o->match_off;
+    o->pub.o.matches = o->matches;
+    o->pub.o.n_fragments = nfrag;
+    return &o->pub;
+}
+
+void orc_fq_out_free(orc_fq_out_t *pub) {
+    fq_impl_t *o = (fq_impl_t *)pub;
+    if (!o) return;
+    free(o->best_frame); free(o->best_score); free(o->match_off); free(o->matches); free(o);
+}
+
 /* ---- CPU-baseline timing loop (bench.py cpu_baseline "port" leg) ---- */
 typedef struct {
     const orc_table *t;

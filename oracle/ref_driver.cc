@@ -416,6 +416,22 @@ char *ref_family_text(void *hv, const char *residues, const uint64_t *offsets, u
     return dup_text(os.str());
 }
 
+// structured form: exact f32 scores + the three strings of best_match_t, one mapper for the whole block
+char *ref_family_batch(void *hv, const char *residues, const uint64_t *offsets, uint32_t n, float *gscore, float *lscore,
+                       float *score) {
+    RefHandle *h = (RefHandle *)hv;
+    FamilyMapper mapper(h->guts[0], h->mapping);
+    std::ostringstream os;
+    for (uint32_t i = 0; i < n; i++) {
+        auto b = mapper.find_best_family_match("seq", seq_at(residues, offsets, i));
+        gscore[i] = b.gfam_score;
+        lscore[i] = b.lfam_score;
+        score[i] = b.score;
+        os << b.gfam_id << "\t" << b.lfam_id << "\t" << b.function << "\n";
+    }
+    return dup_text(os.str());
+}
+
 // POST /fq_lookup inner loop: restates fq_process_request.cc:298-365 over reference DNASequence /
 // TranslationTable / FamilyMapper objects; one mapper per block (fq_process_request.cc:241-242).
 char *ref_fq_text(void *hv, const char *const *ids, const char *bases, const uint64_t *offsets, uint32_t n) {
@@ -461,6 +477,47 @@ char *ref_fq_text(void *hv, const char *const *ids, const char *bases, const uin
         }
     }
     return dup_text(os.str());
+}
+
+// same loop, structured and exact: one line per read
+//   frame \t best_score(%a) \t n_matches { \t len \t gfam \t gscore(%a) \t lfam \t lscore(%a) \t function \t score(%a) }*
+char *ref_fq_batch(void *hv, const char *bases, const uint64_t *offsets, uint32_t n) {
+    RefHandle *h = (RefHandle *)hv;
+    FamilyMapper mapper(h->guts[0], h->mapping);
+    TranslationTable trans_table = TranslationTable::make_table(11);
+    std::string out;
+    char buf[64];
+    auto hex = [&](double v) { snprintf(buf, sizeof buf, "%a", v); return std::string(buf); };
+    for (uint32_t r = 0; r < n; r++) {
+        std::string id = "read", seq = seq_at(bases, offsets, r);
+        DNASequence dna(id, seq);
+        auto prots = dna.get_possible_proteins(trans_table);
+        double best_score = 0.0;
+        int best_frame = 0;
+        std::vector<std::pair<size_t, FamilyMapper::best_match_t>> best_matches;
+        for (auto iter = prots.begin(); iter != prots.end(); iter++) {
+            double score = 0.0;
+            std::vector<std::pair<size_t, FamilyMapper::best_match_t>> matches;
+            for (auto prot : iter->second) {
+                if (prot.length() > 10) {
+                    matches.emplace_back(std::make_pair(prot.length(), mapper.find_best_family_match(id, prot)));
+                    score += matches.back().second.score;
+                }
+                if (score > best_score) {
+                    best_score = score;
+                    best_frame = iter->first;
+                    best_matches = matches;
+                }
+            }
+        }
+        if (!(best_score > 0.0)) { best_frame = 0; best_matches.clear(); }
+        out += std::to_string(best_frame) + "\t" + hex(best_score) + "\t" + std::to_string(best_matches.size());
+        for (auto &m : best_matches)
+            out += "\t" + std::to_string(m.first) + "\t" + m.second.gfam_id + "\t" + hex(m.second.gfam_score) + "\t" +
+                   m.second.lfam_id + "\t" + hex(m.second.lfam_score) + "\t" + m.second.function + "\t" + hex(m.second.score);
+        out += "\n";
+    }
+    return dup_text(out);
 }
 
 // 6-frame translation alone (D1, D2): frames joined as "frame\tfrag,frag,...\n" for inspection

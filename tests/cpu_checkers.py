@@ -30,6 +30,8 @@ BEST_DT = np.dtype([("function_index", "<i4"), ("ambig_a", "<i4"), ("ambig_b", "
                     ("score", "<f4"), ("weighted_score", "<f4"), ("score_offset", "<f4")])
 SLOT_DT = np.dtype([("which_kmer", "<u8"), ("otu_index", "<i4"), ("avg_from_end", "<u2"), ("pad_", "<u2"),
                     ("function_index", "<i4"), ("function_wt", "<f4")])
+FAMILY_DT = np.dtype([("gfam", "<i4"), ("lfam", "<i4"), ("gfam_score", "<f4"), ("lfam_score", "<f4"), ("score", "<f4"),
+                      ("function_index", "<i4")])
 assert CALL_DT.itemsize == 20 and HIT_DT.itemsize == 32 and BEST_DT.itemsize == 28 and SLOT_DT.itemsize == 24
 
 
@@ -37,6 +39,24 @@ class BatchOutC(C.Structure):
     _fields_ = [("n", C.c_uint32), ("call_offsets", C.c_void_p), ("calls", C.c_void_p), ("hit_offsets", C.c_void_p),
                 ("hits", C.c_void_p), ("otu_offsets", C.c_void_p), ("otus", C.c_void_p), ("best", C.c_void_p),
                 ("n_probes", C.c_uint64), ("n_hits", C.c_uint64)]
+
+
+class FqOutC(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("best_frame", C.c_void_p), ("best_score", C.c_void_p), ("match_offsets", C.c_void_p),
+                ("matches", C.c_void_p), ("n_fragments", C.c_uint64), ("n_probes", C.c_uint64)]
+
+
+FQ_MATCH_DT = np.dtype([("length", "<u4"), ("gfam", "<i4"), ("lfam", "<i4"), ("gfam_score", "<f4"), ("lfam_score", "<f4"),
+                        ("score", "<f4"), ("function_index", "<i4")])
+assert FQ_MATCH_DT.itemsize == 28
+
+
+def unpack_fq_out(o) -> dict:
+    n = o.n
+    off = _arr(o.match_offsets, n + 1, np.uint64)
+    return {"n": n, "best_frame": _arr(o.best_frame, n, np.int32), "best_score": _arr(o.best_score, n, np.float64),
+            "match_offsets": off, "matches": _arr(o.matches, int(off[-1]) if n + 1 else 0, FQ_MATCH_DT),
+            "n_fragments": o.n_fragments, "n_probes": o.n_probes}
 
 
 def _arr(ptr, count, dtype):
@@ -120,8 +140,12 @@ class Ref:
                                       C.c_void_p, C.c_void_p]
         L.ref_family_text.restype = C.c_void_p
         L.ref_family_text.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.ref_family_batch.restype = C.c_void_p
+        L.ref_family_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_fq_text.restype = C.c_void_p
         L.ref_fq_text.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.ref_fq_batch.restype = C.c_void_p
+        L.ref_fq_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         L.ref_six_frames.restype = C.c_void_p
         L.ref_six_frames.argtypes = [C.c_char_p]
         L.ref_free_text.argtypes = [C.c_void_p]
@@ -234,10 +258,37 @@ class Ref:
         off = np.ascontiguousarray(batch.offsets, np.uint64)
         return self._text(self.L.ref_family_text(self.h, res.ctypes.data, off.ctypes.data, batch.n))
 
+    def family_batch(self, batch):
+        """find_best_family_match per sequence: dict(gfam, lfam, function: lists of str; gscore, lscore, score: f32)."""
+        res = np.ascontiguousarray(batch.residues, np.uint8)
+        off = np.ascontiguousarray(batch.offsets, np.uint64)
+        g, l, s = (np.zeros(batch.n, np.float32) for _ in range(3))
+        txt = self._text(self.L.ref_family_batch(self.h, res.ctypes.data, off.ctypes.data, batch.n, g.ctypes.data,
+                                                 l.ctypes.data, s.ctypes.data))
+        rows = [ln.split("\t") for ln in txt.split("\n")[:batch.n]]
+        return dict(gfam=[r[0] for r in rows], lfam=[r[1] for r in rows], function=[r[2] for r in rows], gscore=g, lscore=l,
+                    score=s)
+
     def fq_text(self, ids, batch):
         res = np.ascontiguousarray(batch.residues, np.uint8)
         off = np.ascontiguousarray(batch.offsets, np.uint64)
         return self._text(self.L.ref_fq_text(self.h, _cstr_array(ids), res.ctypes.data, off.ctypes.data, batch.n))
+
+    def fq_batch(self, batch):
+        """Per read: (best_frame, best_score, [(len, gfam, gscore, lfam, lscore, function, score), ...]), exact floats."""
+        res = np.ascontiguousarray(batch.residues, np.uint8)
+        off = np.ascontiguousarray(batch.offsets, np.uint64)
+        txt = self._text(self.L.ref_fq_batch(self.h, res.ctypes.data, off.ctypes.data, batch.n))
+        out = []
+        for ln in txt.split("\n")[:batch.n]:
+            c = ln.split("\t")
+            ms = []
+            for k in range(int(c[2])):
+                b = 3 + 7 * k
+                ms.append((int(c[b]), c[b + 1], float.fromhex(c[b + 2]), c[b + 3], float.fromhex(c[b + 4]), c[b + 5],
+                           float.fromhex(c[b + 6])))
+            out.append((int(c[0]), float.fromhex(c[1]), ms))
+        return out
 
     def six_frames(self, bases: bytes) -> str:
         return self._text(self.L.ref_six_frames(bases))
@@ -266,6 +317,17 @@ class Oracle:
         L.orc_call_batch.argtypes = [C.c_void_p, C.POINTER(ParamsC), C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
         L.orc_out_free.argtypes = [C.c_void_p]
         L.orc_find_best_call.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        L.orc_family_new.restype = C.c_void_p
+        L.orc_family_new.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                     C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
+        L.orc_family_free.argtypes = [C.c_void_p]
+        L.orc_family_batch.argtypes = [C.c_void_p, C.POINTER(ParamsC), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                       C.c_void_p]
+        L.orc_translate_frame.restype = C.c_size_t
+        L.orc_translate_frame.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_char_p]
+        L.orc_fq_batch.restype = C.POINTER(FqOutC)
+        L.orc_fq_batch.argtypes = [C.c_void_p, C.POINTER(ParamsC), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.orc_fq_out_free.argtypes = [C.c_void_p]
         L.orc_bench_calls.restype = C.c_double
         L.orc_bench_calls.argtypes = [C.c_void_p, C.POINTER(ParamsC), C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int,
                                       C.POINTER(C.c_uint64)]
@@ -329,6 +391,57 @@ class Oracle:
         out = np.zeros(1, BEST_DT)
         self.L.orc_find_best_call(calls.ctypes.data, len(calls), out.ctypes.data)
         return out[0]
+
+    def family_load(self, fam):
+        """fam: close_kmers_b200.synth.FamilyTables (strings interned there)."""
+        self.fam = self.L.orc_family_new(len(fam.kmers), fam.kmers.ctypes.data, fam.fam_off.ctypes.data,
+                                         fam.fam_ids.ctypes.data, fam.n_fams, fam.fam_func_sid.ctypes.data,
+                                         fam.fam_pgf.ctypes.data, fam.n_pgf, len(fam.func_sid), fam.func_sid.ctypes.data,
+                                         fam.hypo_sid)
+        self._fam_keep = fam
+
+    def family_batch(self, batch):
+        res = np.ascontiguousarray(batch.residues, np.uint8)
+        off = np.ascontiguousarray(batch.offsets, np.uint64)
+        out = np.zeros(batch.n, FAMILY_DT)
+        self.L.orc_family_batch(self.t, C.byref(self.params), self.fam, res.ctypes.data, off.ctypes.data, batch.n,
+                                out.ctypes.data)
+        return out
+
+    def translate_frame(self, dna: bytes, frame: int) -> bytes:
+        out = C.create_string_buffer(len(dna) // 3 + 2)
+        n = self.L.orc_translate_frame(dna, len(dna), frame, out)
+        return out.raw[:n]
+
+    def six_frames(self, dna: bytes):
+        """[(frame, [fragments...])] with boost::split(token_compress_on) semantics (dna_seq.cc:9-23)."""
+        out = []
+        for f in (1, 2, 3, -1, -2, -3):
+            p = self.translate_frame(dna, f)
+            toks, i, n = [], 0, len(p)
+            while True:  # maximal stop-free runs; a leading / trailing stop run still yields one empty token
+                j = i
+                while j < n and p[j:j + 1] != b"*":
+                    j += 1
+                toks.append(p[i:j])
+                if j >= n:
+                    break
+                while j < n and p[j:j + 1] == b"*":
+                    j += 1
+                i = j
+                if i >= n:
+                    toks.append(b"")
+                    break
+            out.append((f, toks))
+        return out
+
+    def fq_batch(self, batch):
+        res = np.ascontiguousarray(batch.residues, np.uint8)
+        off = np.ascontiguousarray(batch.offsets, np.uint64)
+        o = self.L.orc_fq_batch(self.t, C.byref(self.params), self.fam, res.ctypes.data, off.ctypes.data, batch.n)
+        r = unpack_fq_out(o.contents)
+        self.L.orc_fq_out_free(o)
+        return r
 
     def bench_calls(self, batch, threads, want_best=True):
         res = np.ascontiguousarray(batch.residues, np.uint8)
