@@ -48,6 +48,20 @@ class DeviceOutC(C.Structure):
                 ("min_hits_for_call_base", C.c_int32), ("d_best", C.c_void_p), ("d_totals", C.c_void_p)]
 
 
+class FqOutC(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("best_frame", C.c_void_p), ("best_score", C.c_void_p), ("match_offsets", C.c_void_p),
+                ("matches", C.c_void_p), ("n_fragments", C.c_uint64), ("n_probes", C.c_uint64)]
+
+
+class FqFragmentsC(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("n_fragments", C.c_uint64), ("frag_frame_offsets", C.c_void_p),
+                ("frag_offsets", C.c_void_p), ("residues", C.c_void_p)]
+
+
+PAIR_DT = np.dtype([("eid_i", "<u4"), ("eid_j", "<u4"), ("count", "<u8")])
+FQ_MATCH_DT = np.dtype([("length", "<u4"), ("gfam", "<i4"), ("lfam", "<i4"), ("gfam_score", "<f4"), ("lfam_score", "<f4"),
+                        ("score", "<f4"), ("function_index", "<i4")])
+
 _lib = None
 
 
@@ -99,6 +113,28 @@ def lib() -> C.CDLL:
         getattr(L, f).argtypes = [C.c_void_p, C.c_int32]
     L.ckm_family_function_name.restype = C.c_char_p
     L.ckm_family_function_name.argtypes = [C.c_void_p, C.c_void_p]
+    L.ckm_fq_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(FqOutC)]
+    L.ckm_fq_translate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(FqFragmentsC)]
+    L.ckm_fq_text.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
+    L.ckm_family_text.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
+    L.ckm_postings_add.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    L.ckm_postings_append_last.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    L.ckm_postings_clear.argtypes = [C.c_void_p]
+    L.ckm_postings_count.restype = C.c_uint64
+    L.ckm_postings_count.argtypes = [C.c_void_p]
+    L.ckm_matrix_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                  C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.ckm_mapping_new.restype = C.c_void_p
+    L.ckm_mapping_free.argtypes = [C.c_void_p]
+    L.ckm_mapping_encode_id.restype = C.c_uint32
+    L.ckm_mapping_encode_id.argtypes = [C.c_void_p, C.c_char_p]
+    L.ckm_mapping_decode_id.restype = C.c_char_p
+    L.ckm_mapping_decode_id.argtypes = [C.c_void_p, C.c_uint32]
+    L.ckm_add_text.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int,
+                               C.POINTER(C.c_void_p)]
+    L.ckm_matrix_text.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
+    L.ckm_matrix_merge_pairs.restype = C.c_uint64
+    L.ckm_matrix_merge_pairs.argtypes = [C.c_void_p, C.c_uint64]
     L.ckm_query_text.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int,
                                  C.POINTER(C.c_void_p)]
     L.ckm_free_text.argtypes = [C.c_void_p]
@@ -149,6 +185,31 @@ def build_image(nbuckets: int, keys, fI, oI, avg, wt) -> np.ndarray:
 
 def save_kmer_hash_table(image: np.ndarray, kmer_dir: str) -> None:
     image.tofile(os.path.join(kmer_dir, "kmer.table.mem_map"))
+
+
+class KmerPegMapping:
+    """The peg-id table of KmerPegMapping (kmer.h:109-116, kmer.cc:272-295): ids in order of first encode_id."""
+
+    def __init__(self):
+        self._m = C.c_void_p(lib().ckm_mapping_new())
+
+    def encode_id(self, peg) -> int:
+        return lib().ckm_mapping_encode_id(self._m, peg.encode() if isinstance(peg, str) else peg)
+
+    def decode_id(self, i: int) -> str:
+        return lib().ckm_mapping_decode_id(self._m, i).decode()
+
+    def __del__(self):
+        if getattr(self, "_m", None):
+            lib().ckm_mapping_free(self._m)
+            self._m = None
+
+
+def merge_pairs(pairs: np.ndarray) -> np.ndarray:
+    """Order COO entries by (eid_i, eid_j) like the reference's std::map and sum equal keys."""
+    pairs = np.ascontiguousarray(pairs, PAIR_DT).copy()
+    n = lib().ckm_matrix_merge_pairs(pairs.ctypes.data, len(pairs))
+    return pairs[:n]
 
 
 class KmerGuts:
@@ -330,6 +391,100 @@ class KmerGuts:
         rec = np.array([m], dtype=FAMILY_DT)
         return (L.ckm_family_pgf_name(self._h, int(m["gfam"])).decode(), L.ckm_family_plf_name(self._h, int(m["lfam"])).decode(),
                 L.ckm_family_function_name(self._h, rec.ctypes.data).decode())
+
+    def family_text(self, residues, offsets) -> str:
+        residues = np.ascontiguousarray(residues, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        t = C.c_void_p()
+        _check(lib().ckm_family_text(self._h, residues.ctypes.data, offsets.ctypes.data, len(offsets) - 1, C.byref(t)))
+        return self._take_text(t)
+
+    # -- fastq reads (FqProcessRequest / DNASequence / TranslationTable) ---------------------------------
+    def get_possible_proteins_batch(self, bases, offsets, min_len=0):
+        """DNASequence::get_possible_proteins (dna_seq.cc:9-23) for every read, fragments longer than min_len:
+        list per read of [(frame, [fragment bytes, ...]) x 6]."""
+        bases = np.ascontiguousarray(bases, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        n = len(offsets) - 1
+        o = FqFragmentsC()
+        _check(lib().ckm_fq_translate(self._h, bases.ctypes.data, offsets.ctypes.data, n, min_len, C.byref(o)))
+        ffo = _arr(o.frag_frame_offsets, 6 * n + 1, np.uint64)
+        fo = _arr(o.frag_offsets, o.n_fragments + 1, np.uint64)
+        res = _arr(o.residues, int(fo[-1]) if len(fo) else 0, np.uint8).tobytes()
+        out = []
+        for r in range(n):
+            frames = []
+            for s, f in enumerate((1, 2, 3, -1, -2, -3)):
+                a, b = int(ffo[6 * r + s]), int(ffo[6 * r + s + 1])
+                frames.append((f, [res[int(fo[k]):int(fo[k + 1])] for k in range(a, b)]))
+            out.append(frames)
+        return out
+
+    def fq_batch(self, bases, offsets) -> dict:
+        """FqProcessRequest::on_parsed_seq (fq_process_request.cc:298-365) for every read."""
+        bases = np.ascontiguousarray(bases, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        n = len(offsets) - 1
+        o = FqOutC()
+        _check(lib().ckm_fq_batch(self._h, bases.ctypes.data, offsets.ctypes.data, n, C.byref(o)))
+        off = _arr(o.match_offsets, n + 1, np.uint64)
+        return {"n": n, "best_frame": _arr(o.best_frame, n, np.int32), "best_score": _arr(o.best_score, n, np.float64),
+                "match_offsets": off, "matches": _arr(o.matches, int(off[-1]), FQ_MATCH_DT), "n_fragments": o.n_fragments,
+                "n_probes": o.n_probes}
+
+    def fq_text(self, ids, bases, offsets) -> str:
+        bases = np.ascontiguousarray(bases, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        bs = [s.encode() if isinstance(s, str) else s for s in ids]
+        arr = (C.c_char_p * len(bs))(*bs)
+        t = C.c_void_p()
+        _check(lib().ckm_fq_text(self._h, arr, bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1, C.byref(t)))
+        return self._take_text(t)
+
+    # -- /add postings and /matrix ------------------------------------------------------------------------
+    def postings_add(self, eids, residues, offsets):
+        eids = np.ascontiguousarray(eids, np.uint32)
+        residues = np.ascontiguousarray(residues, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        _check(lib().ckm_postings_add(self._h, eids.ctypes.data, residues.ctypes.data, offsets.ctypes.data, len(offsets) - 1))
+
+    def postings_clear(self):
+        lib().ckm_postings_clear(self._h)
+
+    @property
+    def postings_count(self) -> int:
+        return lib().ckm_postings_count(self._h)
+
+    def matrix_rows(self, eids, residues, offsets, row_begin=0, row_end=None) -> np.ndarray:
+        """Rows [row_begin, row_end) of MatrixRequest's lower-triangular count matrix as unordered COO entries."""
+        eids = np.ascontiguousarray(eids, np.uint32)
+        residues = np.ascontiguousarray(residues, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        n = len(offsets) - 1
+        p, npairs = C.c_void_p(), C.c_uint64()
+        _check(lib().ckm_matrix_rows(self._h, eids.ctypes.data, residues.ctypes.data, offsets.ctypes.data, n, row_begin,
+                                     n if row_end is None else row_end, C.byref(p), C.byref(npairs)))
+        return _arr(p.value, npairs.value, PAIR_DT)
+
+    def add_text(self, mapping: KmerPegMapping, ids, residues, offsets, silent=0) -> str:
+        residues = np.ascontiguousarray(residues, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        bs = [s.encode() if isinstance(s, str) else s for s in ids]
+        arr = (C.c_char_p * len(bs))(*bs)
+        t = C.c_void_p()
+        _check(lib().ckm_add_text(self._h, mapping._m, arr, residues.ctypes.data, offsets.ctypes.data, len(offsets) - 1, silent,
+                                  C.byref(t)))
+        return self._take_text(t)
+
+    def matrix_text(self, mapping: KmerPegMapping, ids, residues, offsets) -> str:
+        residues = np.ascontiguousarray(residues, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        bs = [s.encode() if isinstance(s, str) else s for s in ids]
+        arr = (C.c_char_p * len(bs))(*bs)
+        t = C.c_void_p()
+        _check(lib().ckm_matrix_text(self._h, mapping._m, arr, residues.ctypes.data, offsets.ctypes.data, len(offsets) - 1,
+                                     C.byref(t)))
+        return self._take_text(t)
 
     def best_function(self, best_rec) -> str:
         """The `function` string find_best_call returns (kguts.cc:1160, 1176-1196)."""

@@ -64,6 +64,23 @@ struct ckm_ctx {
     } fam;
     PinBuf h_fam;
 
+    // /add postings + /matrix (ckm_matrix.cuh)
+    struct Post {
+        DevBuf keys, eids;  // the appended (k-mer, peg id) pairs
+        uint64_t n = 0, mask = 0;
+        bool dirty = true;
+        DevBuf tkeys, tcnt, tcur, toff, slots, ids;                          // index built lazily
+        DevBuf d_eids, d_first, rcap, rofs, nd, out_off, entries, out;      // per-request work buffers
+        PinBuf h_out;
+    } post;
+
+    // fastq path (ckm_fq.cuh)
+    struct Fq {
+        DevBuf nfrag, naa, frag_base, res_base, frag_off, frag_res;
+        DevBuf best_frame, best_score, best_n, best_first, match_off, matches;
+        PinBuf h_frag_base, h_frag_off, h_frag_res, h_best_frame, h_best_score, h_match_off, h_matches;
+    } fq;
+
     // pinned host buffers handed out through ckm_batch_out_t
     PinBuf h_off, h_totals, h_hit_off, h_hits, h_call_off, h_calls, h_otu_off, h_otus, h_best;
 
@@ -75,6 +92,16 @@ struct ckm_ctx {
         DevBuf *f[] = {&fam.table, &fam.ids, &fam.fam_func, &fam.fam_pgf, &fam.func_sid, &fam.hit_fam, &fam.E, &fam.gcap,
                        &fam.gofs, &fam.gscratch, &fam.matches};
         for (auto b : f) b->release();
+        DevBuf *pp[] = {&post.keys, &post.eids, &post.tkeys, &post.tcnt, &post.tcur, &post.toff, &post.slots, &post.ids,
+                        &post.d_eids, &post.d_first, &post.rcap, &post.rofs, &post.nd, &post.out_off, &post.entries, &post.out};
+        for (auto b : pp) b->release();
+        post.h_out.release();
+        DevBuf *q[] = {&fq.nfrag, &fq.naa, &fq.frag_base, &fq.res_base, &fq.frag_off, &fq.frag_res, &fq.best_frame,
+                       &fq.best_score, &fq.best_n, &fq.best_first, &fq.match_off, &fq.matches};
+        for (auto b : q) b->release();
+        PinBuf *qh[] = {&fq.h_frag_base, &fq.h_frag_off, &fq.h_frag_res, &fq.h_best_frame, &fq.h_best_score, &fq.h_match_off,
+                        &fq.h_matches};
+        for (auto b : qh) b->release();
         PinBuf *h[] = {&h_off, &h_totals, &h_hit_off, &h_hits, &h_call_off, &h_calls, &h_otu_off, &h_otus, &h_best, &h_fam};
         for (auto b : h) b->release();
     }

@@ -9,6 +9,8 @@
 #include <sstream>
 #include <string>
 #include <utility>
+#include <map>
+#include <unordered_map>
 #include <vector>
 
 namespace {
@@ -90,6 +92,144 @@ int ckm_query_text(ckm_ctx *ctx, const char *const *ids, const char *residues, c
                 for (uint64_t k = o.hit_offsets[i]; k < o.hit_offsets[i + 1]; k++) put_hit(os, ctx, o.hits[k]);
             put_otu_stats(os, id, len, o.otus + o.otu_offsets[i], o.otu_offsets[i + 1] - o.otu_offsets[i]);
         }
+    }
+    *text = dup_text(os.str());
+    return *text ? 0 : CKM_ENOMEM;
+}
+
+// operator<<(ostream&, best_match_t), family_mapper.h:70-75
+static void put_match(std::ostream &os, const ckm_ctx *ctx, const ckm_family_match_t &m) {
+    os << ckm_family_pgf_name(ctx, m.gfam) << "\t" << m.gfam_score << "\t" << ckm_family_plf_name(ctx, m.lfam) << "\t"
+       << m.lfam_score << "\t" << ckm_family_function_name(ctx, &m) << "\t" << m.score;
+}
+
+int ckm_family_text(ckm_ctx *ctx, const char *residues, const uint64_t *offsets, uint32_t n, char **text) {
+    if (!text) return CKM_EINVAL;
+    *text = nullptr;
+    const ckm_family_match_t *m = nullptr;
+    int rc = ckm_family_batch(ctx, residues, offsets, n, &m);
+    if (rc) return rc;
+    std::ostringstream os;
+    for (uint32_t i = 0; i < n; i++) {
+        put_match(os, ctx, m[i]);
+        os << "\n";
+    }
+    *text = dup_text(os.str());
+    return *text ? 0 : CKM_ENOMEM;
+}
+
+int ckm_fq_text(ckm_ctx *ctx, const char *const *ids, const char *bases, const uint64_t *offsets, uint32_t n, char **text) {
+    if (!text) return CKM_EINVAL;
+    *text = nullptr;
+    ckm_fq_out_t o;
+    int rc = ckm_fq_batch(ctx, bases, offsets, n, &o);
+    if (rc) return rc;
+    std::ostringstream os;
+    for (uint32_t r = 0; r < n; r++) {
+        const std::string id = ids[r];
+        if (id.empty()) continue;                // fq_process_request.cc:301-302
+        if (!(o.best_score[r] > 0.0)) continue;  // 349
+        os << id << "\t" << o.best_frame[r] << "\t" << o.best_score[r] << "\t";
+        for (uint64_t k = o.match_offsets[r]; k < o.match_offsets[r + 1]; k++) {
+            if (k != o.match_offsets[r]) os << "\t";
+            os << o.matches[k].length << "\t";
+            put_match(os, ctx, o.matches[k].m);
+        }
+        os << std::endl;
+    }
+    *text = dup_text(os.str());
+    return *text ? 0 : CKM_ENOMEM;
+}
+
+}  // extern "C"
+
+struct ckm_mapping {
+    std::unordered_map<std::string, uint32_t> peg_to_id;
+    std::vector<std::string> id_to_peg;
+};
+
+extern "C" {
+
+ckm_mapping *ckm_mapping_new(void) { return new ckm_mapping(); }
+void ckm_mapping_free(ckm_mapping *m) { delete m; }
+uint32_t ckm_mapping_encode_id(ckm_mapping *m, const char *peg) {  // kmer.cc:272-286
+    auto it = m->peg_to_id.find(peg);
+    if (it != m->peg_to_id.end()) return it->second;
+    const uint32_t id = (uint32_t)m->id_to_peg.size();
+    m->peg_to_id.emplace(peg, id);
+    m->id_to_peg.emplace_back(peg);
+    return id;
+}
+const char *ckm_mapping_decode_id(const ckm_mapping *m, uint32_t id) {  // kmer.cc:288-295
+    return id < m->id_to_peg.size() ? m->id_to_peg[id].c_str() : "";
+}
+
+int ckm_add_text(ckm_ctx *ctx, ckm_mapping *m, const char *const *ids, const char *residues, const uint64_t *offsets,
+                 uint32_t n, int silent, char **text) {
+    if (!text || !m) return CKM_EINVAL;
+    *text = nullptr;
+    // process_aa_seq_hits(id, seq, calls, hits, stats) + find_best_call (add_request.cc:133-146)
+    ckm_batch_out_t o;
+    int rc = ckm_call_batch(ctx, residues, offsets, n, CKM_WANT_CALLS | CKM_WANT_HITS | CKM_WANT_OTU | CKM_WANT_BEST, &o);
+    if (rc) return rc;
+    std::ostringstream os;
+    std::vector<uint32_t> eids(n);
+    for (uint32_t i = 0; i < n; i++) {
+        const std::string id = ids[i];
+        const uint64_t len = offsets[i + 1] - offsets[i];
+        if (!silent) {
+            os << "PROTEIN-ID\t" << id << "\t" << len << "\n";
+            for (uint64_t k = o.call_offsets[i]; k < o.call_offsets[i + 1]; k++) put_call(os, ctx, o.calls[k]);
+            put_otu_stats(os, id, len, o.otus + o.otu_offsets[i], o.otu_offsets[i + 1] - o.otu_offsets[i]);
+            std::string fn = best_function(ctx, o.best[i]);
+            if (fn.empty() || fn.find(" ?? ") != std::string::npos) fn = "hypothetical protein";  // 147-158
+            os << "BEST-CALL\t" << id << "\t" << fn << "\t" << o.best[i].score << "\t" << o.best[i].weighted_score << "\t"
+               << o.best[i].score_offset << "\n";
+        }
+        eids[i] = ckm_mapping_encode_id(m, ids[i]);  // add_request.cc:164
+    }
+    rc = ckm_postings_append_last(ctx, eids.data(), n);  // 165-170
+    if (rc) return rc;
+    *text = dup_text(os.str());
+    return *text ? 0 : CKM_ENOMEM;
+}
+
+uint64_t ckm_matrix_merge_pairs(ckm_pair_t *pairs, uint64_t n_pairs) {
+    std::sort(pairs, pairs + n_pairs, [](const ckm_pair_t &a, const ckm_pair_t &b) {
+        return a.eid_i != b.eid_i ? a.eid_i < b.eid_i : a.eid_j < b.eid_j;
+    });
+    uint64_t w = 0;
+    for (uint64_t r = 0; r < n_pairs; r++) {
+        if (w && pairs[w - 1].eid_i == pairs[r].eid_i && pairs[w - 1].eid_j == pairs[r].eid_j)
+            pairs[w - 1].count += pairs[r].count;  // a repeated id in the request shares one map entry
+        else
+            pairs[w++] = pairs[r];
+    }
+    return w;
+}
+
+int ckm_matrix_text(ckm_ctx *ctx, ckm_mapping *m, const char *const *ids, const char *residues, const uint64_t *offsets,
+                    uint32_t n, char **text) {
+    if (!text || !m) return CKM_EINVAL;
+    *text = nullptr;
+    std::vector<uint32_t> eids(n);
+    std::map<uint32_t, size_t> matrix_proteins;  // matrix_request.cc:88-90 (a later duplicate overwrites the size)
+    for (uint32_t i = 0; i < n; i++) {
+        eids[i] = ckm_mapping_encode_id(m, ids[i]);
+        matrix_proteins[eids[i]] = (size_t)(offsets[i + 1] - offsets[i]);
+    }
+    const ckm_pair_t *pairs = nullptr;
+    uint64_t np = 0;
+    int rc = ckm_matrix_rows(ctx, eids.data(), residues, offsets, n, 0, n, &pairs, &np);
+    if (rc) return rc;
+    std::vector<ckm_pair_t> v(pairs, pairs + np);
+    v.resize(ckm_matrix_merge_pairs(v.data(), v.size()));
+    std::ostringstream os;
+    for (const ckm_pair_t &p : v) {  // process_results, matrix_request.cc:171-184
+        const size_t l1 = matrix_proteins[p.eid_i], l2 = matrix_proteins[p.eid_j];
+        const float score = (float)p.count / ((float)(l1 + l2));
+        os << ckm_mapping_decode_id(m, p.eid_i) << "\t" << ckm_mapping_decode_id(m, p.eid_j) << "\t" << p.count << "\t" << score
+           << "\n";
     }
     *text = dup_text(os.str());
     return *text ? 0 : CKM_ENOMEM;

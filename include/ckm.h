@@ -253,6 +253,33 @@ typedef struct {
 int ckm_fq_translate(ckm_ctx *ctx, const char *bases, const uint64_t *offsets, uint32_t n, uint32_t min_len,
                      ckm_fq_fragments_t *out);
 
+/* ---- /add postings and the /matrix pairwise shared-k-mer counts ------------------------------------------
+ * AddRequest (add_request.cc:133, 164-170) pushes one kmer_to_id_ entry per hit occurrence (kmer.cc:174-214);
+ * MatrixRequest (matrix_request.cc:78-95, 130-161) counts, for the proteins of one request in order,
+ * distance[(eid_i, e)]++ for every hit of protein i and every posting e of the hit's k-mer with e != eid_i
+ * and e already seen in this request (matrix_proteins_ is set before protein i is processed). */
+
+/* append the postings of a batch: eids[i] is KmerPegMapping::encode_id(id_i), assigned by the caller */
+int ckm_postings_add(ckm_ctx *ctx, const uint32_t *eids, const char *residues, const uint64_t *offsets, uint32_t n);
+/* same, reusing the hits of the ckm_call_batch that just ran on these n sequences with CKM_WANT_HITS set
+ * (AddRequest computes calls, OTU stats and hits in one process_aa_seq_hits call: add_request.cc:133) */
+int ckm_postings_append_last(ckm_ctx *ctx, const uint32_t *eids, uint32_t n);
+void ckm_postings_clear(ckm_ctx *ctx);
+uint64_t ckm_postings_count(const ckm_ctx *ctx); /* (k-mer, peg) entries held */
+
+typedef struct {
+    uint32_t eid_i; /* the protein being processed */
+    uint32_t eid_j; /* a previously seen protein of the same request sharing signature k-mers */
+    uint64_t count; /* sum over hits of i of the multiplicity of eid_j in the k-mer's postings */
+} ckm_pair_t;       /* 16 bytes */
+
+/* Rows [row_begin, row_end) of the request's strictly-lower-triangular count matrix, as unordered COO
+ * entries (the handler layer orders them by (eid_i, eid_j) like the reference's std::map and merges rows of
+ * a repeated id).  The whole request (all n proteins) must be passed so that membership is known; only the
+ * selected rows are probed -- this is the unit of row-block sharding across GPUs. */
+int ckm_matrix_rows(ckm_ctx *ctx, const uint32_t *eids, const char *residues, const uint64_t *offsets, uint32_t n,
+                    uint32_t row_begin, uint32_t row_end, const ckm_pair_t **pairs, uint64_t *n_pairs);
+
 /* ---- image builder: KmerGuts(dir, nbuckets) + insert_kmer + save_kmer_hash_table (kguts.cc:77-115, 188-234).
  * Host-side; writes the reference's file bytes (header + nbuckets slots) into image_out, which must be
  * exactly 24 + 24*nbuckets bytes.  keys > MAX_ENCODED are skipped like kguts.cc:206-210. */

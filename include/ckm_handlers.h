@@ -22,6 +22,40 @@ extern "C" {
 int ckm_query_text(ckm_ctx *ctx, const char *const *ids, const char *residues, const uint64_t *offsets, uint32_t n,
                    int details, int find_best_call, char **text);
 
+/* KmerPegMapping's peg-id table (kmer.h:109-116, kmer.cc:272-295): ids are assigned in order of first
+ * encode_id.  Host-side state shared by /add and /matrix requests of one server. */
+typedef struct ckm_mapping ckm_mapping;
+ckm_mapping *ckm_mapping_new(void);
+void ckm_mapping_free(ckm_mapping *m);
+uint32_t ckm_mapping_encode_id(ckm_mapping *m, const char *peg);
+const char *ckm_mapping_decode_id(const ckm_mapping *m, uint32_t id); /* "" when unknown */
+
+/* POST /add (add_request.cc:102-170): unless `silent`, "PROTEIN-ID", "CALL" lines, "OTU-COUNTS" and a
+ * "BEST-CALL\t<id>\t<function>\t<score>\t<weighted>\t<offset>" line per sequence ("hypothetical protein" for an
+ * empty or ambiguous call; <offset> is printed as 0 where the reference prints an uninitialised float, i.e.
+ * when there are no calls); then every hit is appended to the ctx's k-mer -> peg postings. */
+int ckm_add_text(ckm_ctx *ctx, ckm_mapping *m, const char *const *ids, const char *residues, const uint64_t *offsets,
+                 uint32_t n, int silent, char **text);
+
+/* POST /matrix (matrix_request.cc:78-95, 163-189) for a request that fits one chunk: rows
+ * "<peg1>\t<peg2>\t<count>\t<count/(len1+len2)>\n" ordered by (encoded id 1, encoded id 2).  The HTTP status
+ * lines of process_results are the front end's business and are not included. */
+int ckm_matrix_text(ckm_ctx *ctx, ckm_mapping *m, const char *const *ids, const char *residues, const uint64_t *offsets,
+                    uint32_t n, char **text);
+
+/* the ordering / merging step of ckm_matrix_text on its own, for callers that computed row blocks on several
+ * GPUs: sorts by (eid_i, eid_j) and sums entries with equal keys, in place; returns the new count */
+uint64_t ckm_matrix_merge_pairs(ckm_pair_t *pairs, uint64_t n_pairs);
+
+/* POST /fq_lookup (fq_process_request.cc:298-365): one line per read with a positive best score,
+ * "<id>\t<frame>\t<best score>\t<len>\t<gfam>\t<gscore>\t<lfam>\t<lscore>\t<function>\t<score>[\t<len>...]*\n";
+ * reads with an empty id are skipped.  Needs ckm_family_load. */
+int ckm_fq_text(ckm_ctx *ctx, const char *const *ids, const char *bases, const uint64_t *offsets, uint32_t n, char **text);
+
+/* FamilyMapper::find_best_family_match as text, one "<gfam>\t<gscore>\t<lfam>\t<lscore>\t<function>\t<score>\n"
+ * line per sequence (operator<< of best_match_t, family_mapper.h:70-75) */
+int ckm_family_text(ckm_ctx *ctx, const char *residues, const uint64_t *offsets, uint32_t n, char **text);
+
 /* KmerGuts::format_call / format_hit / format_otu_stats (kguts.cc:939-973) for callers that assemble their own
  * responses.  `otus` are the ascending-otu_index pairs of one sequence; the function applies
  * KmerOtuStats::finalize's count-descending std::sort (kguts.h:214-218) and prints the top five. */

@@ -748,6 +748,82 @@ void orc_fq_out_free(orc_fq_out_t *pub) {
     free(o->best_frame); free(o->best_score); free(o->match_off); free(o->matches); free(o);
 }
 
+/* ---- M1: postings + pairwise counts ---- */
+typedef struct { uint64_t k; uint32_t e; } post_t;
+struct orc_postings {
+    post_t *p;
+    uint64_t n, cap;
+    int sorted;
+};
+orc_postings *orc_postings_new(void) { return calloc(1, sizeof(orc_postings)); }
+void orc_postings_free(orc_postings *p) { if (p) { free(p->p); free(p); } }
+uint64_t orc_postings_count(const orc_postings *p) { return p->n; }
+void orc_free(void *p) { free(p); }
+
+/* add_request.cc:133 (process_aa_seq_hits) + 164-170: one add_mapping(enc_id, hit.which_kmer) per hit */
+void orc_postings_add(const orc_table *t, const orc_params_t *prm, orc_postings *p, const uint32_t *eids,
+                      const char *residues, const uint64_t *offsets, uint32_t n) {
+    orc_out_t *o = orc_call_batch(t, prm, residues, offsets, n, CKM_WANT_HITS);
+    for (uint32_t i = 0; i < n; i++)
+        for (uint64_t h = o->o.hit_offsets[i]; h < o->o.hit_offsets[i + 1]; h++) {
+            post_t e = {o->o.hits[h].which_kmer, eids[i]};
+            VEC_PUSH(*p, e);
+        }
+    p->sorted = 0;
+    orc_out_free(o);
+}
+static int post_cmp(const void *a, const void *b) {
+    const post_t *x = a, *y = b;
+    return x->k < y->k ? -1 : x->k > y->k;
+}
+static int u64_cmp(const void *a, const void *b) {
+    uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+    return x < y ? -1 : x > y;
+}
+
+ckm_pair_t *orc_matrix_rows(const orc_table *t, const orc_params_t *prm, orc_postings *p, const uint32_t *eids,
+                            const char *residues, const uint64_t *offsets, uint32_t n, uint32_t row_begin,
+                            uint32_t row_end, uint64_t *n_pairs) {
+    if (!p->sorted) { qsort(p->p, p->n, sizeof *p->p, post_cmp); p->sorted = 1; }
+    /* matrix_proteins_: an id is a member from the first time it is set (matrix_request.cc:90) */
+    uint32_t max_e = 0;
+    for (uint32_t i = 0; i < n; i++) if (eids[i] > max_e) max_e = eids[i];
+    uint32_t *first = malloc(((size_t)max_e + 1) * 4);
+    for (uint32_t e = 0; e <= max_e; e++) first[e] = 0xffffffffu;
+    for (uint32_t i = 0; i < n; i++) if (first[eids[i]] == 0xffffffffu) first[eids[i]] = i;
+    struct { uint64_t *p; uint64_t n, cap; } contrib = {0};
+    if (row_end > n) row_end = n;
+    for (uint32_t i = row_begin; i < row_end; i++) {
+        uint64_t off2[2] = {0, offsets[i + 1] - offsets[i]};
+        orc_out_t *o = orc_call_batch(t, prm, residues + offsets[i], off2, 1, CKM_WANT_HITS); /* calls=0, otu=0: 92-94 */
+        for (uint64_t h = 0; h < o->o.hit_offsets[1]; h++) { /* on_hit, 130-161 */
+            uint64_t k = o->o.hits[h].which_kmer, lo = 0, hi = p->n;
+            while (lo < hi) { uint64_t mid = (lo + hi) / 2; if (p->p[mid].k < k) lo = mid + 1; else hi = mid; }
+            for (; lo < p->n && p->p[lo].k == k; lo++) {
+                uint32_t e = p->p[lo].e;
+                if (e != eids[i] && e <= max_e && first[e] <= i) {
+                    uint64_t key = ((uint64_t)eids[i] << 32) | e;
+                    VEC_PUSH(contrib, key);
+                }
+            }
+        }
+        orc_out_free(o);
+    }
+    qsort(contrib.p, contrib.n, 8, u64_cmp);
+    ckm_pair_t *out = malloc((contrib.n ? contrib.n : 1) * sizeof *out);
+    uint64_t np = 0;
+    for (uint64_t x = 0; x < contrib.n;) {
+        uint64_t y = x;
+        while (y < contrib.n && contrib.p[y] == contrib.p[x]) y++;
+        out[np++] = (ckm_pair_t){(uint32_t)(contrib.p[x] >> 32), (uint32_t)contrib.p[x], y - x};
+        x = y;
+    }
+    free(contrib.p);
+    free(first);
+    *n_pairs = np;
+    return out;
+}
+
 /* ---- CPU-baseline timing loop (bench.py cpu_baseline "port" leg) ---- */
 typedef struct {
     const orc_table *t;

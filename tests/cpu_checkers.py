@@ -46,6 +46,7 @@ class FqOutC(C.Structure):
                 ("matches", C.c_void_p), ("n_fragments", C.c_uint64), ("n_probes", C.c_uint64)]
 
 
+PAIR_DT = np.dtype([("eid_i", "<u4"), ("eid_j", "<u4"), ("count", "<u8")])
 FQ_MATCH_DT = np.dtype([("length", "<u4"), ("gfam", "<i4"), ("lfam", "<i4"), ("gfam_score", "<f4"), ("lfam_score", "<f4"),
                         ("score", "<f4"), ("function_index", "<i4")])
 assert FQ_MATCH_DT.itemsize == 28
@@ -328,6 +329,15 @@ class Oracle:
         L.orc_fq_batch.restype = C.POINTER(FqOutC)
         L.orc_fq_batch.argtypes = [C.c_void_p, C.POINTER(ParamsC), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         L.orc_fq_out_free.argtypes = [C.c_void_p]
+        L.orc_postings_new.restype = C.c_void_p
+        L.orc_postings_free.argtypes = [C.c_void_p]
+        L.orc_postings_add.argtypes = [C.c_void_p, C.POINTER(ParamsC), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.orc_postings_count.restype = C.c_uint64
+        L.orc_postings_count.argtypes = [C.c_void_p]
+        L.orc_matrix_rows.restype = C.c_void_p
+        L.orc_matrix_rows.argtypes = [C.c_void_p, C.POINTER(ParamsC), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                      C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
+        L.orc_free.argtypes = [C.c_void_p]
         L.orc_bench_calls.restype = C.c_double
         L.orc_bench_calls.argtypes = [C.c_void_p, C.POINTER(ParamsC), C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int,
                                       C.POINTER(C.c_uint64)]
@@ -406,6 +416,27 @@ class Oracle:
         out = np.zeros(batch.n, FAMILY_DT)
         self.L.orc_family_batch(self.t, C.byref(self.params), self.fam, res.ctypes.data, off.ctypes.data, batch.n,
                                 out.ctypes.data)
+        return out
+
+    def postings_new(self):
+        self.post = C.c_void_p(self.L.orc_postings_new())
+
+    def postings_add(self, eids, batch):
+        eids = np.ascontiguousarray(eids, np.uint32)
+        res = np.ascontiguousarray(batch.residues, np.uint8)
+        off = np.ascontiguousarray(batch.offsets, np.uint64)
+        self.L.orc_postings_add(self.t, C.byref(self.params), self.post, eids.ctypes.data, res.ctypes.data, off.ctypes.data,
+                                batch.n)
+
+    def matrix_rows(self, eids, batch, row_begin=0, row_end=None):
+        eids = np.ascontiguousarray(eids, np.uint32)
+        res = np.ascontiguousarray(batch.residues, np.uint8)
+        off = np.ascontiguousarray(batch.offsets, np.uint64)
+        npairs = C.c_uint64()
+        p = self.L.orc_matrix_rows(self.t, C.byref(self.params), self.post, eids.ctypes.data, res.ctypes.data, off.ctypes.data,
+                                   batch.n, row_begin, batch.n if row_end is None else row_end, C.byref(npairs))
+        out = _arr(p, npairs.value, PAIR_DT)
+        self.L.orc_free(p)
         return out
 
     def translate_frame(self, dna: bytes, frame: int) -> bytes:

@@ -1,0 +1,88 @@
+"""Pins the oracle's family voting (F1-F3), 6-frame translation / fq best frame (D1-D3) and matrix (M1)
+restatements to the reference's own object code (oracle/_ref)."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import workloads as wl
+from close_kmers_b200 import api, synth
+
+DNA_EDGE = [b"", b"A", b"AC", b"ACG", b"ACGT", b"acgtnACGTN" * 12, b"ATGAAATAGTAATGA" * 10, b"T" * 41, b"ACGURYKMSWBDHVN" * 8,
+            b"TAATAGTGA" * 6, b"ATGGCC" + b"TAA" + b"GCT" * 14 + b"TGA"]
+
+
+@pytest.fixture(scope="module")
+def world(checkers):
+    if not os.path.exists(checkers.REF_SO):
+        pytest.skip("oracle/_ref/libckm_ref.so not built (needs /root/reference)")
+    protos, sig, img = wl.small_world(otu_mode="minus1")
+    fam = synth.make_families(7, sig)
+    d = tempfile.mkdtemp(prefix="ckm_ref_")
+    api.save_kmer_hash_table(img, d)
+    synth.write_index_files(d, sig.n_functions, 0)
+    ref = checkers.Ref().open(d)
+    ref.set_params()
+    ref.family_load(fam.kmers, fam.fam_off, fam.fam_ids, fam.pgf, fam.plf, fam.function)
+    orc = checkers.Oracle().open_image(img)
+    orc.family_load(fam)
+    yield protos, sig, fam, ref, orc
+    ref.close()
+    orc.close()
+
+
+def test_translation_all_codons_and_frames(checkers, world):
+    _, _, _, ref, orc = world
+    rng = np.random.default_rng(5)
+    seqs = list(DNA_EDGE[3:]) + [bytes(rng.choice(np.frombuffer(b"ACGTacgtNRYU", np.uint8), int(rng.integers(3, 200)))) for _ in range(200)]
+    # every codon over ACGT
+    seqs.append(b"".join(bytes([a, b, c]) for a in b"ACGT" for b in b"ACGT" for c in b"ACGT"))
+    for s in seqs:
+        mine = "".join(f"{f}\t{','.join(t.decode() for t in toks)}\n" for f, toks in orc.six_frames(s))
+        assert mine == ref.six_frames(s), s
+
+
+def test_family_voting_matches_reference(checkers, world):
+    protos, sig, fam, ref, orc = world
+    batch = wl.concat_batches(wl.edge_batch(protos), synth.make_proteins(2, protos, 1500))
+    r, o = ref.family_batch(batch), orc.family_batch(batch)
+    wl.assert_family_equal(o, r, fam, synth.function_names(sig.n_functions), "oracle vs reference")
+    assert int((o["lfam"] >= 0).sum()) > 500
+
+
+def test_fq_best_frame_matches_reference(checkers, world):
+    protos, sig, fam, ref, orc = world
+    batch = wl.concat_batches(synth.batch_from_strings(DNA_EDGE), synth.make_reads(3, protos, 600))
+    r, o = ref.fq_batch(batch), orc.fq_batch(batch)
+    wl.assert_fq_equal(o, r, fam, synth.function_names(sig.n_functions), "oracle vs reference")
+    assert int((o["best_frame"] != 0).sum()) > 300
+
+
+def test_matrix_matches_reference(checkers, world):
+    protos, sig, fam, ref, orc = world
+    # 40 prototypes x 6 mutated copies, /add-ed in two chunks, then one matrix request over all of them
+    sub = synth.Prototypes(protos.codes[: int(protos.offsets[40])], protos.offsets[:41])
+    batch = synth.make_proteins(11, sub, 240, mix=(0.9, 0.1, 0.0, 0.0))
+    ids = [f"fig|{i % 230}.peg.{i % 230}" for i in range(batch.n)]  # ten ids appear twice
+    ref.mapping_new()
+    orc.postings_new()
+    eid_of = {}
+    half = batch.n // 2
+    for lo, hi in ((0, half), (half, batch.n)):
+        part = synth.Batch(batch.residues[int(batch.offsets[lo]):int(batch.offsets[hi])], batch.offsets[lo:hi + 1] - batch.offsets[lo])
+        ref.add_text(ids[lo:hi], part, silent=1)
+        eids = [eid_of.setdefault(x, len(eid_of)) for x in ids[lo:hi]]
+        orc.postings_add(eids, part)
+    order = np.random.default_rng(1).permutation(batch.n)[:200]
+    req = synth.batch_from_strings([batch.seq(i) for i in order])
+    req_ids = [ids[i] for i in order]
+    want = ref.matrix_text(req_ids, req)
+    eids = np.array([eid_of[x] for x in req_ids], np.uint32)
+    pairs = orc.matrix_rows(eids, req)
+    got = wl.matrix_text_from_pairs(pairs, eids, req, {v: k for k, v in eid_of.items()})
+    assert got == want
+    assert len(pairs) > 100
+    # row blocks partition the result
+    parts = np.concatenate([orc.matrix_rows(eids, req, a, b) for a, b in ((0, 70), (70, 71), (71, 200))])
+    assert wl.matrix_text_from_pairs(parts, eids, req, {v: k for k, v in eid_of.items()}) == want

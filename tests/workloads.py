@@ -83,3 +83,79 @@ def assert_results_equal(got: dict, want: dict, what: str, check_ambig_indices: 
     for key in ("n_probes", "n_hits"):
         if key in want and want[key] and key in got:
             assert got[key] == want[key], f"{what}: {key} {got[key]} != {want[key]}"
+
+
+def _close(a, b, rel=1e-6):
+    return abs(float(a) - float(b)) <= rel * max(1.0, abs(float(a)), abs(float(b)))
+
+
+def assert_family_equal(got, ref, fam, function_names, what):
+    """got: FAMILY_DT records (ids); ref: dict of strings + exact f32 scores from the reference.  Scores of the
+    best family and the best call must be bit-equal; the rolled-up PGF score within 1e-6 relative; names equal
+    except where the scores show an exact tie (the reference breaks ties by unordered_map iteration order)."""
+    n = len(got)
+    ties = 0
+    for i in range(n):
+        g = got[i]
+        fn = function_names[g["function_index"]] if g["function_index"] >= 0 else "hypothetical protein"
+        assert g["lfam_score"] == ref["lscore"][i], f"{what}[{i}] lfam_score {g['lfam_score']} != {ref['lscore'][i]}"
+        assert g["score"] == ref["score"][i], f"{what}[{i}] score"
+        assert fn == ref["function"][i], f"{what}[{i}] function {fn!r} != {ref['function'][i]!r}"
+        assert _close(g["gfam_score"], ref["gscore"][i]), f"{what}[{i}] gfam_score {g['gfam_score']} vs {ref['gscore'][i]}"
+        gname = fam.pgf_names[g["gfam"]] if g["gfam"] >= 0 else ""
+        lname = fam.plf[g["lfam"]] if g["lfam"] >= 0 else ""
+        assert (gname == "") == (ref["gfam"][i] == "") and (lname == "") == (ref["lfam"][i] == "")
+        if (gname, lname) != (ref["gfam"][i], ref["lfam"][i]):
+            ties += 1
+    assert ties <= max(3, n // 50), f"{what}: {ties} id differences is more than exact ties explain"
+    return ties
+
+
+def assert_family_records_equal(got, want, what):
+    """CUDA vs oracle: same tie rule on both sides, so ids match exactly; only the PGF roll-up order differs."""
+    assert len(got) == len(want)
+    for f in ("lfam", "lfam_score", "score", "function_index"):
+        bad = np.nonzero(got[f] != want[f])[0]
+        assert len(bad) == 0, f"{what}: {f} differs at {bad[:5]}: {got[f][bad[:5]]} vs {want[f][bad[:5]]}"
+    for i in range(len(got)):
+        assert _close(got["gfam_score"][i], want["gfam_score"][i]), f"{what}[{i}] gfam_score"
+        if got["gfam"][i] != want["gfam"][i]:  # a near-tie decided by summation order
+            assert _close(got["gfam_score"][i], want["gfam_score"][i])
+
+
+def assert_fq_equal(got, ref, fam, function_names, what):
+    """got: dict from fq_batch (ids); ref: list of (frame, score, [(len, gfam, gscore, lfam, lscore, function, score)])."""
+    assert got["n"] == len(ref)
+    for i, (fr, bs, ms) in enumerate(ref):
+        a, b = int(got["match_offsets"][i]), int(got["match_offsets"][i + 1])
+        assert got["best_frame"][i] == fr, f"{what}[{i}] frame {got['best_frame'][i]} != {fr}"
+        assert got["best_score"][i] == bs, f"{what}[{i}] best_score"
+        assert b - a == len(ms), f"{what}[{i}] n_matches {b - a} != {len(ms)}"
+        for k, m in enumerate(ms):
+            x = got["matches"][a + k]
+            fn = function_names[x["function_index"]] if x["function_index"] >= 0 else "hypothetical protein"
+            assert (x["length"], x["lfam_score"], x["score"], fn) == (m[0], np.float32(m[4]), np.float32(m[6]), m[5]), f"{what}[{i}][{k}]"
+            assert _close(x["gfam_score"], m[2]), f"{what}[{i}][{k}] gfam_score"
+
+
+def assert_fq_records_equal(got, want, what):
+    for f in ("best_frame", "best_score", "match_offsets"):
+        assert np.array_equal(got[f], want[f]), f"{what}: {f}"
+    for f in ("length", "lfam", "lfam_score", "score", "function_index"):
+        assert np.array_equal(got["matches"][f], want["matches"][f]), f"{what}: matches.{f}"
+    assert np.allclose(got["matches"]["gfam_score"], want["matches"]["gfam_score"], rtol=1e-6, atol=0)
+    assert got["n_fragments"] == want["n_fragments"]
+
+
+def matrix_text_from_pairs(pairs, eids, batch, id_to_peg):
+    """process_results (matrix_request.cc:163-189) over ordered, merged COO entries; floats like ostream << float."""
+    from close_kmers_b200 import api
+    pairs = api.merge_pairs(pairs)
+    lens = {}
+    for i, e in enumerate(eids):
+        lens[int(e)] = int(batch.offsets[i + 1] - batch.offsets[i])
+    out = []
+    for p in pairs:
+        score = np.float32(p["count"]) / np.float32(lens[int(p["eid_i"])] + lens[int(p["eid_j"])])
+        out.append(f"{id_to_peg[int(p['eid_i'])]}\t{id_to_peg[int(p['eid_j'])]}\t{int(p['count'])}\t{float(score):.6g}\n")
+    return "".join(out)
