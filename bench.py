@@ -365,6 +365,7 @@ def main():
             traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload)
         except (OSError, ValueError):
             pass
+        cal_rate, _ = guts.calibrate_gather(16, 4, 64, 8)  # independent random 16 B reads over the resident table
         value = prot_all * K / (ms_total * 1e-3)
         line = {
             "metric": "proteins/sec", "value": value, "unit": "proteins/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
@@ -376,7 +377,11 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "probe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                         "algorithmic_bytes_per_launch": alg_bytes},
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "gather_calibration": {"accesses_per_s": cal_rate, "as_32B_sectors_GBps": cal_rate * 32 / 1e9,
+                                                "probe_kernel_probes_per_s": n_probes / (probe_ms_avg * 1e-3),
+                                                "note": "ceiling of independent random reads over this table on this GPU "
+                                                        "(DESIGN.md section 6); probes/s / accesses_per_s = fraction of it"}},
             "e2e": {"value": prot_all * K / (ms_e2e * 1e-3), "unit": "proteins/s", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": total + (n + 1) * 8, "d2h_bytes_per_step": n * 28 + 24},
             "gpu_launches": int(launches),

@@ -1,0 +1,72 @@
+"""The C-ABI library builds, loads without a GPU, exports every symbol include/*.h declares, and its host-only
+entry points (statics, image builder, error paths) behave -- no compute calls here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from close_kmers_b200 import api, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = set()
+    for h in ("ckm.h", "ckm_handlers.h"):
+        text = open(os.path.join(ROOT, "include", h)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        for m in re.finditer(r"\b(ckm_[a-z0-9_]+)\s*\(", text):
+            names.add(m.group(1))
+    return sorted(names)
+
+
+def test_every_declared_symbol_is_exported():
+    L = api.lib()
+    syms = declared_symbols()
+    assert len(syms) >= 40
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+
+
+def test_record_layouts_match_header():
+    assert api.CALL_DT.itemsize == 20 and api.HIT_DT.itemsize == 32 and api.BEST_DT.itemsize == 28
+    assert api.SLOT_DT.itemsize == 24 and api.FAMILY_DT.itemsize == 24 and api.FQ_MATCH_DT.itemsize == 28 and api.PAIR_DT.itemsize == 16
+
+
+def test_encode_decode_known_answers():
+    assert api.encoded_aa_kmer(b"AAAAAAAA") == 0 and api.encoded_aa_kmer(b"AAAAAAAC") == 1
+    assert api.encoded_aa_kmer(b"YYYYYYYY") == 20**8 - 1 and api.encoded_aa_kmer(b"CAAAAAAA") == 20**7
+    for bad in (b"ACDEFGHX", b"acdefghi", b"ACDE*GHI", b"BJOUZXXX"):
+        assert api.encoded_aa_kmer(bad) == 20**8 + 1
+    for k in (0, 1, 20**7, 20**8 - 1, 1234567890):
+        assert api.encoded_aa_kmer(api.decoded_kmer(k)) == k
+
+
+def test_image_builder_format_and_limits():
+    keys = np.array([api.encoded_aa_kmer(b"ACDEFGHI"), api.encoded_aa_kmer(b"CDEFGHIK"), 20**8 + 1], np.uint64)
+    img = api.build_image(3769, keys, [1, 2, 3], [-1, 4, 5], [10, 20, 30], [1.5, 2.5, 3.5])
+    hdr = img[:24].view(np.uint64)
+    assert tuple(hdr) == (3769, 24, 1) and img.nbytes == 24 + 24 * 3769
+    slots = np.frombuffer(img, api.SLOT_DT, offset=24)
+    occ = slots[slots["which_kmer"] <= 20**8]
+    assert len(occ) == 2  # the invalid key is skipped (kguts.cc:206-210)
+    assert np.all(slots["which_kmer"][slots["which_kmer"] > 20**8] == 20**8 + 1)
+    s = slots[int(keys[0]) % 3769]
+    assert (s["which_kmer"], s["function_index"], s["otu_index"], s["avg_from_end"], s["function_wt"]) == (keys[0], 1, -1, 10, 1.5)
+    with pytest.raises(api.CkmError):  # half-full table is refused like kguts.cc:213-216
+        api.build_image(16, np.arange(9, dtype=np.uint64), [0] * 9, [0] * 9, [0] * 9, [0.0] * 9)
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    """Without a usable device every compute entry point must fail with CKM_ECUDA; on a GPU box this test is moot."""
+    protos = synth.make_prototypes(1, 8, 100)
+    sig = synth.make_signatures(protos, 500)
+    img = api.build_image(synth.bucket_count(len(sig.keys)), sig.keys, sig.fI, sig.oI, sig.avg, sig.wt)
+    try:
+        g = api.KmerGuts(image=img)
+    except api.CkmError as e:
+        assert e.code == -4 and "no CPU fallback" in str(e)
+    else:
+        g.close()
