@@ -386,7 +386,8 @@ def main():
                     "h2d_bytes_per_step": total + (n + 1) * 8, "d2h_bytes_per_step": n * 28 + 24},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "table": {"buckets": guts.num_sigs, "slot_bytes": guts.slot_bytes, "l2_fetch_granularity": guts.l2_fetch_granularity},
+            "table": {"buckets": guts.num_sigs, "slot_bytes": guts.slot_bytes, "l2_fetch_granularity": guts.l2_fetch_granularity,
+                      "occupancy_bitmap": guts.has_occupancy_bitmap},
         }
         if not args.no_cpu_baseline and world == 1:
             eng = CpuEngine(kdir, img, cpu_threads())

@@ -87,6 +87,7 @@ def lib() -> C.CDLL:
     L.ckm_num_sigs.argtypes = [C.c_void_p]
     L.ckm_table_slot_bytes.argtypes = [C.c_void_p]
     L.ckm_l2_fetch_granularity.argtypes = [C.c_void_p]
+    L.ckm_has_occupancy_bitmap.argtypes = [C.c_void_p]
     L.ckm_set_default_params.argtypes = [C.c_void_p]
     L.ckm_set_params.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     L.ckm_get_params.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
@@ -283,6 +284,10 @@ class KmerGuts:
     @property
     def l2_fetch_granularity(self) -> int:
         return lib().ckm_l2_fetch_granularity(self._h)
+
+    @property
+    def has_occupancy_bitmap(self) -> bool:
+        return bool(lib().ckm_has_occupancy_bitmap(self._h))
 
     @property
     def stream(self) -> int:

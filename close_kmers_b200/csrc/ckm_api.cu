@@ -111,6 +111,24 @@ pack_table_kernel(const uint64_t *__restrict__ raw /* 3 x u64 per slot */, uint6
     packed[i] = v;
 }
 
+// bit h of occupied[] = slot h holds a k-mer; one thread per 32 slots
+template <bool PACKED>
+__global__ void __launch_bounds__(256)
+occupancy_kernel(const void *__restrict__ slots, uint64_t num_sigs, uint32_t *__restrict__ occupied) {
+    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w * 32 >= num_sigs) return;
+    uint32_t bits = 0;
+    for (uint32_t b = 0; b < 32; b++) {
+        const uint64_t h = w * 32 + b;
+        if (h >= num_sigs) break;
+        bool occ;
+        if (PACKED) occ = !(reinterpret_cast<const uint4 *>(slots)[h].y & 0x8u);
+        else occ = reinterpret_cast<const uint64_t *>(slots)[3 * h] <= CKM_MAX_ENCODED;
+        bits |= occ ? (1u << b) : 0u;
+    }
+    occupied[w] = bits;
+}
+
 static int check_cuda(cudaError_t e, const char *what) {
     if (e == cudaSuccess) return 0;
     return ckm_fail(CKM_ECUDA, "%s: %s", what, cudaGetErrorString(e));
@@ -178,6 +196,43 @@ static int upload_table(ckm_ctx *c, const ckm_image_header_t *hdr) {
     }
     c->num_sigs = n;
     c->magic = n ? (uint64_t)((((unsigned __int128)1) << 64) / n) : 0;
+    // occupancy bitmap: only worth an extra L2 access per probe when the table itself cannot live in L2
+    const size_t table_bytes = (size_t)n * c->slot_bytes;
+    const char *ob = getenv("CKM_OCCUPANCY_BITMAP");  // "0" disables, "1" forces
+    const bool want_bitmap = ob ? ob[0] == '1' : table_bytes > (size_t)c->l2_bytes;
+    c->occupied.release();
+    if (want_bitmap) {
+        const uint64_t words = (n + 31) / 32;
+        RC(c->occupied.ensure(words * 4 + 64));
+        const unsigned blocks = (unsigned)((words + 255) / 256);
+        if (c->slot_bytes == kPackedSlotBytes)
+            occupancy_kernel<true><<<blocks, 256, 0, c->stream>>>(c->table.p, n, (uint32_t *)c->occupied.p);
+        else
+            occupancy_kernel<false><<<blocks, 256, 0, c->stream>>>(c->table.p, n, (uint32_t *)c->occupied.p);
+        c->launches++;
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaGetLastError());
+        // keep the bitmap resident: persisting L2 window on the ctx stream (best effort)
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, c->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+            const size_t bytes = words * 4;
+            const size_t carve = std::min<size_t>(bytes, (size_t)prop.persistingL2CacheMaxSize);
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+                cudaStreamAttrValue attr;
+                memset(&attr, 0, sizeof attr);
+                attr.accessPolicyWindow.base_ptr = c->occupied.p;
+                attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+                attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)bytes);
+                attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                if (!getenv("CKM_NO_L2_PERSIST") &&
+                    cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess)
+                    (void)cudaGetLastError();
+            } else {
+                (void)cudaGetLastError();
+            }
+        }
+    }
     return 0;
 }
 
@@ -201,6 +256,8 @@ static int ctx_create(int device, ckm_ctx **out) {
     RC(select_device(device));
     ckm_ctx *c = new ckm_ctx();
     c->device = device;
+    if (const char *pc = getenv("CKM_PIPELINE_CHUNK_KB")) c->pipeline_chunk_bytes = std::max<uint64_t>(1, (uint64_t)atol(pc)) << 10;
+    if (const char *pm = getenv("CKM_PIPELINE_MIN_KB")) c->pipeline_min_bytes = (uint64_t)atol(pm) << 10;
     const char *fr = getenv("CKM_FORCE_RAW_SLOTS");
     c->force_raw = fr && fr[0] == '1';
     if (check_cuda(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
@@ -210,6 +267,7 @@ static int ctx_create(int device, ckm_ctx **out) {
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     c->sm_count = prop.multiProcessorCount;
+    c->l2_bytes = prop.l2CacheSize;
     // The probe is a random 16-byte gather: with the default L2 fetch granularity every miss drags a whole
     // 128-byte line out of HBM (measured: 132 B of DRAM reads per probe, profiles/r1a).  Ask for single
     // 32-byte sectors instead.  It is a device-wide hint; CKM_L2_FETCH=64|128 restores coarser fetches.
@@ -302,7 +360,11 @@ extern "C" void ckm_close(ckm_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->stream2) cudaStreamSynchronize(c->stream2);
     c->free_all();
+    if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+    if (c->ev_done2) cudaEventDestroy(c->ev_done2);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -320,6 +382,7 @@ extern "C" int32_t ckm_otu_count(const ckm_ctx *c) { return (int32_t)c->otu_name
 extern "C" uint64_t ckm_num_sigs(const ckm_ctx *c) { return c->num_sigs; }
 extern "C" int ckm_table_slot_bytes(const ckm_ctx *c) { return c->slot_bytes; }
 extern "C" int ckm_l2_fetch_granularity(const ckm_ctx *c) { return c->l2_fetch; }
+extern "C" int ckm_has_occupancy_bitmap(const ckm_ctx *c) { return c->occupied.p != nullptr; }
 extern "C" void *ckm_stream(ckm_ctx *c) { return (void *)c->stream; }
 extern "C" uint64_t ckm_launch_count(const ckm_ctx *c) { return c->launches; }
 extern "C" int ckm_synchronize(ckm_ctx *c) {
@@ -432,28 +495,29 @@ static int prefix_sum(ckm_ctx *c, const uint32_t *d_in, uint64_t n, uint64_t *d_
     return 0;
 }
 
-// K1 + K2 over a batch that is already in HBM.  Leaves regions / per-protein counters on the device.
-static int run_device(ckm_ctx *c, const uint8_t *d_res, const uint64_t *d_off, uint32_t n, uint64_t total, uint32_t max_len,
-                      uint32_t flags) {
+struct RunPlan {
+    bool want_scan, general, want_keys, want_avg;
+};
+
+// size the per-batch regions (indexed by residue offset / sequence index, so chunked launches can share them)
+static int prepare_regions(ckm_ctx *c, uint32_t n, uint64_t total, uint32_t max_len, uint32_t flags, RunPlan *plan) {
     c->cur_n = n;
     c->cur_total = total;
     c->cur_flags = flags;
-    c->cur_off = d_off;
-    const bool want_scan = flags & (CKM_WANT_CALLS | CKM_WANT_OTU | CKM_WANT_BEST);
-    const bool general = want_scan && (c->prm.order_constraint != 0 || max_len == 0 || max_len > kHitCap + CKM_KMER_SIZE);
-    const bool want_keys = flags & CKM_WANT_HITS;
-    const bool want_avg = (flags & CKM_WANT_HITS) || (want_scan && c->prm.order_constraint != 0);
+    plan->want_scan = flags & (CKM_WANT_CALLS | CKM_WANT_OTU | CKM_WANT_BEST);
+    plan->general = plan->want_scan && (c->prm.order_constraint != 0 || max_len == 0 || max_len > kHitCap + CKM_KMER_SIZE);
+    plan->want_keys = flags & CKM_WANT_HITS;
+    plan->want_avg = (flags & CKM_WANT_HITS) || (plan->want_scan && c->prm.order_constraint != 0);
     const uint64_t ncall_slots = total / (uint64_t)std::max(1, c->prm.min_hits) + n + 1;
-
     RC(c->totals.ensure(64));
     RC(c->hits.ensure((total + 1) * sizeof(HitRec)));
     RC(c->n_hits.ensure(((size_t)n + 1) * 4));
-    if (want_keys) RC(c->hit_keys.ensure((total + 1) * 8));
-    if (want_avg) RC(c->hit_avg.ensure((total + 1) * 2));
-    if (want_scan) {
+    if (plan->want_keys) RC(c->hit_keys.ensure((total + 1) * 8));
+    if (plan->want_avg) RC(c->hit_avg.ensure((total + 1) * 2));
+    if (plan->want_scan) {
         RC(c->calls.ensure(ncall_slots * sizeof(ckm_call_t)));
         RC(c->n_calls.ensure(((size_t)n + 1) * 4));
-        if (general) RC(c->stored_idx.ensure((total + 1) * 4));
+        if (plan->general) RC(c->stored_idx.ensure((total + 1) * 4));
         if (flags & CKM_WANT_BEST) {
             RC(c->calls_work.ensure(ncall_slots * sizeof(ckm_call_t)));
             RC(c->best.ensure(((size_t)n + 1) * sizeof(ckm_best_t)));
@@ -463,9 +527,70 @@ static int run_device(ckm_ctx *c, const uint8_t *d_res, const uint64_t *d_off, u
             RC(c->n_otus.ensure(((size_t)n + 1) * 4));
         }
     }
+    return 0;
+}
+
+// K1 (+ K2) for sequences [i0, i0+cnt) of the batch on `stream`
+static int launch_range(ckm_ctx *c, cudaStream_t stream, const uint8_t *d_res, const uint64_t *d_off, uint32_t i0, uint32_t cnt,
+                        uint32_t flags, const RunPlan &plan, ckm_ctx::ProfEv *pe) {
+    if (cnt == 0) return 0;
+    TableView tv;
+    tv.slots = c->table.p;
+    tv.num_sigs = c->num_sigs;
+    tv.magic = c->magic;
+    tv.occupied = (const uint32_t *)c->occupied.p;
+    {
+        const uint32_t warps_per_block = kProbeThreads / 32;
+        uint64_t blocks = ((uint64_t)cnt + warps_per_block - 1) / warps_per_block;
+        blocks = std::min<uint64_t>(blocks, (uint64_t)c->sm_count * 8);
+        uint64_t *keys = plan.want_keys ? (uint64_t *)c->hit_keys.p : nullptr;
+        uint16_t *avg = plan.want_avg ? (uint16_t *)c->hit_avg.p : nullptr;
+        if (c->slot_bytes == kPackedSlotBytes)
+            probe_kernel<true><<<(unsigned)blocks, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, (HitRec *)c->hits.p, keys, avg,
+                                                                               (uint32_t *)c->n_hits.p + i0,
+                                                                               (unsigned long long *)c->totals.p);
+        else
+            probe_kernel<false><<<(unsigned)blocks, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, (HitRec *)c->hits.p, keys, avg,
+                                                                                (uint32_t *)c->n_hits.p + i0,
+                                                                                (unsigned long long *)c->totals.p);
+        c->launches++;
+    }
+    if (pe) CU(cudaEventRecord(pe->e1, stream));
+    if (plan.want_scan) {
+        ScanArgs a;
+        a.offsets = d_off + i0;
+        a.hits = (const HitRec *)c->hits.p;
+        a.hit_avg = (c->prm.order_constraint != 0) ? (const uint16_t *)c->hit_avg.p : nullptr;
+        a.n_hits = (const uint32_t *)c->n_hits.p + i0;
+        a.stored_idx = plan.general ? (uint32_t *)c->stored_idx.p : nullptr;
+        a.calls = (ckm_call_t *)c->calls.p;
+        a.calls_work = (flags & CKM_WANT_BEST) ? (ckm_call_t *)c->calls_work.p : nullptr;
+        a.n_calls = (uint32_t *)c->n_calls.p + i0;
+        a.otus = (flags & CKM_WANT_OTU) ? (ckm_otu_t *)c->otus.p : nullptr;
+        a.n_otus = (flags & CKM_WANT_OTU) ? (uint32_t *)c->n_otus.p + i0 : nullptr;
+        a.best = (flags & CKM_WANT_BEST) ? (ckm_best_t *)c->best.p + i0 : nullptr;
+        a.totals = (unsigned long long *)c->totals.p;
+        a.n = cnt;
+        a.index_base = i0;
+        a.prm = c->prm;
+        const unsigned blocks = (cnt + kScanThreads - 1) / kScanThreads;
+        if (plan.general)
+            scan_kernel<true><<<blocks, kScanThreads, 0, stream>>>(a);
+        else
+            scan_kernel<false><<<blocks, kScanThreads, 0, stream>>>(a);
+        c->launches++;
+    }
+    return 0;
+}
+
+// K1 + K2 over a batch that is already in HBM.  Leaves regions / per-protein counters on the device.
+static int run_device(ckm_ctx *c, const uint8_t *d_res, const uint64_t *d_off, uint32_t n, uint64_t total, uint32_t max_len,
+                      uint32_t flags) {
+    RunPlan plan;
+    RC(prepare_regions(c, n, total, max_len, flags, &plan));
+    c->cur_off = d_off;
     CU(cudaMemsetAsync(c->totals.p, 0, 64, c->stream));
     if (n == 0) return 0;
-
     ckm_ctx::ProfEv pe = {nullptr, nullptr, nullptr, false};
     if (c->profiling) {
         CU(cudaEventCreate(&pe.e0));
@@ -473,51 +598,10 @@ static int run_device(ckm_ctx *c, const uint8_t *d_res, const uint64_t *d_off, u
         CU(cudaEventCreate(&pe.e2));
         CU(cudaEventRecord(pe.e0, c->stream));
     }
-    TableView tv;
-    tv.slots = c->table.p;
-    tv.num_sigs = c->num_sigs;
-    tv.magic = c->magic;
-    {
-        const uint32_t warps_per_block = kProbeThreads / 32;
-        uint64_t blocks = ((uint64_t)n + warps_per_block - 1) / warps_per_block;
-        blocks = std::min<uint64_t>(blocks, (uint64_t)c->sm_count * 8);
-        if (c->slot_bytes == kPackedSlotBytes)
-            probe_kernel<true><<<(unsigned)blocks, kProbeThreads, 0, c->stream>>>(
-                tv, d_res, d_off, n, (HitRec *)c->hits.p, want_keys ? (uint64_t *)c->hit_keys.p : nullptr,
-                want_avg ? (uint16_t *)c->hit_avg.p : nullptr, (uint32_t *)c->n_hits.p, (unsigned long long *)c->totals.p);
-        else
-            probe_kernel<false><<<(unsigned)blocks, kProbeThreads, 0, c->stream>>>(
-                tv, d_res, d_off, n, (HitRec *)c->hits.p, want_keys ? (uint64_t *)c->hit_keys.p : nullptr,
-                want_avg ? (uint16_t *)c->hit_avg.p : nullptr, (uint32_t *)c->n_hits.p, (unsigned long long *)c->totals.p);
-        c->launches++;
-    }
-    if (c->profiling) CU(cudaEventRecord(pe.e1, c->stream));
-    if (want_scan) {
-        ScanArgs a;
-        a.offsets = d_off;
-        a.hits = (const HitRec *)c->hits.p;
-        a.hit_avg = (c->prm.order_constraint != 0) ? (const uint16_t *)c->hit_avg.p : nullptr;
-        a.n_hits = (const uint32_t *)c->n_hits.p;
-        a.stored_idx = general ? (uint32_t *)c->stored_idx.p : nullptr;
-        a.calls = (ckm_call_t *)c->calls.p;
-        a.calls_work = (flags & CKM_WANT_BEST) ? (ckm_call_t *)c->calls_work.p : nullptr;
-        a.n_calls = (uint32_t *)c->n_calls.p;
-        a.otus = (flags & CKM_WANT_OTU) ? (ckm_otu_t *)c->otus.p : nullptr;
-        a.n_otus = (flags & CKM_WANT_OTU) ? (uint32_t *)c->n_otus.p : nullptr;
-        a.best = (flags & CKM_WANT_BEST) ? (ckm_best_t *)c->best.p : nullptr;
-        a.totals = (unsigned long long *)c->totals.p;
-        a.n = n;
-        a.prm = c->prm;
-        const unsigned blocks = (n + kScanThreads - 1) / kScanThreads;
-        if (general)
-            scan_kernel<true><<<blocks, kScanThreads, 0, c->stream>>>(a);
-        else
-            scan_kernel<false><<<blocks, kScanThreads, 0, c->stream>>>(a);
-        c->launches++;
-    }
+    RC(launch_range(c, c->stream, d_res, d_off, 0, n, flags, plan, c->profiling ? &pe : nullptr));
     if (c->profiling) {
         CU(cudaEventRecord(pe.e2, c->stream));
-        pe.has_scan = want_scan;
+        pe.has_scan = plan.want_scan;
         c->prof.push_back(pe);
     }
     CU(cudaGetLastError());
@@ -604,6 +688,72 @@ static int upload_batch(ckm_ctx *c, const char *residues, const uint64_t *offset
     return 0;
 }
 
+// find_best_call-only batches (fixed-size results) are streamed: the batch is cut into chunks of about
+// pipeline_chunk_bytes residues that alternate between two CUDA streams, so that the H2D copy of chunk k+1 and the
+// D2H copy of chunk k-1 overlap the kernels of chunk k.  All chunks share the per-batch regions (indexed by residue
+// offset / sequence index, hence disjoint), so nothing is double-buffered.
+static int call_batch_pipelined(ckm_ctx *c, const char *residues, const uint64_t *offsets, uint32_t n, ckm_batch_out_t *out) {
+    CU(cudaSetDevice(c->device));
+    uint32_t max_len = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (offsets[i + 1] < offsets[i]) return ckm_fail(CKM_EINVAL, "offsets must be non-decreasing (at %u)", i);
+        const uint64_t l = offsets[i + 1] - offsets[i];
+        if (l > 500000000ull) return ckm_fail(CKM_EINVAL, "sequence %u longer than MAX_SEQ_LEN", i);
+        max_len = std::max<uint32_t>(max_len, (uint32_t)l);
+    }
+    const uint64_t base0 = offsets[0], total = offsets[n] - base0;
+    RunPlan plan;
+    RC(prepare_regions(c, n, total, std::max(max_len, 1u), CKM_WANT_BEST, &plan));
+    RC(c->in_res.ensure(total + 32));
+    RC(c->in_off.ensure(((size_t)n + 1) * 8));
+    RC(c->h_best.ensure(((size_t)n + 1) * sizeof(ckm_best_t)));
+    RC(c->h_totals.ensure(64));
+    if (!c->stream2) CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    if (!c->ev_ready) CU(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
+    if (!c->ev_done2) CU(cudaEventCreateWithFlags(&c->ev_done2, cudaEventDisableTiming));
+    c->cur_off = (const uint64_t *)c->in_off.p;
+    const uint64_t *h_off = offsets;
+    if (base0 != 0) {
+        RC(c->h_off.ensure(((size_t)n + 1) * 8));
+        uint64_t *t = (uint64_t *)c->h_off.p;
+        for (uint32_t i = 0; i <= n; i++) t[i] = offsets[i] - base0;
+        h_off = t;
+    }
+    // stream 0: offsets, counters, slack; stream 1 waits for them
+    CU(cudaMemcpyAsync(c->in_off.p, h_off, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(c->totals.p, 0, 64, c->stream));
+    CU(cudaMemsetAsync((uint8_t *)c->in_res.p + total, 0, 32, c->stream));
+    CU(cudaEventRecord(c->ev_ready, c->stream));
+    CU(cudaStreamWaitEvent(c->stream2, c->ev_ready, 0));
+    uint32_t i0 = 0;
+    int k = 0;
+    while (i0 < n) {
+        uint32_t i1 = i0;
+        const uint64_t start = h_off[i0];
+        while (i1 < n && h_off[i1 + 1] - start <= c->pipeline_chunk_bytes) i1++;
+        if (i1 == i0) i1 = i0 + 1;  // a single sequence longer than a chunk
+        const uint64_t bytes = h_off[i1] - start;
+        cudaStream_t st = (k & 1) ? c->stream2 : c->stream;
+        if (bytes) CU(cudaMemcpyAsync((uint8_t *)c->in_res.p + start, residues + base0 + start, bytes, cudaMemcpyHostToDevice, st));
+        RC(launch_range(c, st, (const uint8_t *)c->in_res.p, (const uint64_t *)c->in_off.p, i0, i1 - i0, CKM_WANT_BEST, plan, nullptr));
+        CU(cudaMemcpyAsync((ckm_best_t *)c->h_best.p + i0, (const ckm_best_t *)c->best.p + i0, (size_t)(i1 - i0) * sizeof(ckm_best_t),
+                           cudaMemcpyDeviceToHost, st));
+        i0 = i1;
+        k++;
+    }
+    // join stream 1 into stream 0, then read the batch counters
+    CU(cudaEventRecord(c->ev_done2, c->stream2));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_done2, 0));
+    uint64_t *ht = (uint64_t *)c->h_totals.p;
+    CU(cudaMemcpyAsync(ht, c->totals.p, 24, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    out->n_probes = ht[0];
+    out->n_hits = ht[1];
+    out->best = (const ckm_best_t *)c->h_best.p;
+    return 0;
+}
+
 extern "C" int ckm_call_batch(ckm_ctx *c, const char *residues, const uint64_t *offsets, uint32_t n, uint32_t flags,
                               ckm_batch_out_t *out) {
     if (!c || !out) return ckm_fail(CKM_EINVAL, "NULL argument");
@@ -611,6 +761,8 @@ extern "C" int ckm_call_batch(ckm_ctx *c, const char *residues, const uint64_t *
     out->n = n;
     uint64_t total = 0;
     uint32_t max_len = 0;
+    if (flags == CKM_WANT_BEST && offsets && n > 1 && offsets[n] - offsets[0] >= c->pipeline_min_bytes)
+        return call_batch_pipelined(c, residues, offsets, n, out);
     RC(upload_batch(c, residues, offsets, n, &total, &max_len));
     RC(run_device(c, (const uint8_t *)c->in_res.p, (const uint64_t *)c->in_off.p, n, total, std::max(max_len, 1u), flags));
 

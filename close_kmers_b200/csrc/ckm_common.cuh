@@ -33,6 +33,11 @@ struct TableView {
     const void *slots;   // packed: uint4[num_sigs]; raw: 24-byte ckm_sig_kmer_t[num_sigs] (8-byte aligned)
     uint64_t num_sigs;
     uint64_t magic;      // floor(2^64 / num_sigs), for key % num_sigs without a divide
+    // Occupancy bitmap (bit h = slot h holds a k-mer), 1/128 of the packed table: small enough to live in L2
+    // (63.5 MB for 508M buckets) while the table itself does not.  A probe whose slot is empty -- most misses at
+    // the reference's <= 1/3 load factor -- is answered from L2 and never becomes a DRAM transaction, which is
+    // what bounds this kernel.  NULL when the table itself fits L2.
+    const uint32_t *occupied;
 };
 
 // One table hit as the ordered scoring scan consumes it (KmerHit, kguts.h:154-163, minus the key).

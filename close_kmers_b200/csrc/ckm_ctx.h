@@ -26,12 +26,15 @@ struct PinBuf {  // page-locked host memory
 struct ckm_ctx {
     int device = 0;
     int sm_count = 148;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: second lane of the pipelined host path
+    cudaEvent_t ev_ready = nullptr, ev_done2 = nullptr;
+    uint64_t pipeline_chunk_bytes = 24ull << 20, pipeline_min_bytes = 48ull << 20;
     bool force_raw = false;
     int l2_fetch = 0;  // cudaLimitMaxL2FetchGranularity in effect
 
     // signature table in HBM
-    DevBuf table;
+    DevBuf table, occupied;  // occupied: 1 bit per slot, only for tables larger than L2
+    int l2_bytes = 0;
     uint64_t num_sigs = 0, magic = 0;
     int slot_bytes = 0;
 
@@ -85,7 +88,7 @@ struct ckm_ctx {
     PinBuf h_off, h_totals, h_hit_off, h_hits, h_call_off, h_calls, h_otu_off, h_otus, h_best;
 
     void free_all() {
-        DevBuf *d[] = {&table, &in_res, &in_off, &totals, &hits, &hit_keys, &hit_avg, &n_hits, &stored_idx, &calls, &calls_work,
+        DevBuf *d[] = {&table, &occupied, &in_res, &in_off, &totals, &hits, &hit_keys, &hit_avg, &n_hits, &stored_idx, &calls, &calls_work,
                        &n_calls, &otus, &n_otus, &best, &ps_blocks, &hit_off, &call_off, &otu_off, &hits_out, &calls_out,
                        &otus_out};
         for (auto b : d) b->release();

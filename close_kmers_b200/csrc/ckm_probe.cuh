@@ -166,22 +166,33 @@ probe_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64_t 
                     act |= ok ? (1u << j) : 0u;
                 }
 
-                // ---- probe: issue the four sector loads, then resolve ----
+                // ---- probe: occupancy bits from L2 first, then the sector loads that are still needed ----
+                uint32_t need = act;
+                if (tv.occupied) {
+                    uint32_t bw[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (act & (1u << j)) bw[j] = __ldg(tv.occupied + (h[j] >> 5));
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if ((act & (1u << j)) && !((bw[j] >> (h[j] & 31u)) & 1u)) need &= ~(1u << j);  // empty slot: miss
+                }
                 typename SlotIO<PACKED>::raw_t v[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++)
-                    if (act & (1u << j)) v[j] = SlotIO<PACKED>::load(tv.slots, h[j]);
+                    if (need & (1u << j)) v[j] = SlotIO<PACKED>::load(tv.slots, h[j]);
 
                 SlotFields f[4];
                 uint32_t hm = 0;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    if (act & (1u << j)) {
+                    if (need & (1u << j)) {
                         int r = SlotIO<PACKED>::test(v[j], key[j], f[j]);
                         uint64_t guard = 0;
                         while (r == 0) {  // linear probing: h = (h+1) % size_hash (kguts.cc:589)
                             h[j] = (h[j] + 1 == tv.num_sigs) ? 0 : h[j] + 1;
                             if (++guard >= tv.num_sigs) { r = -1; break; }  // table without an empty slot
+                            if (tv.occupied && !((__ldg(tv.occupied + (h[j] >> 5)) >> (h[j] & 31u)) & 1u)) { r = -1; break; }
                             v[j] = SlotIO<PACKED>::load(tv.slots, h[j]);
                             r = SlotIO<PACKED>::test(v[j], key[j], f[j]);
                         }

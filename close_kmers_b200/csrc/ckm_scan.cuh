@@ -189,6 +189,7 @@ struct ScanArgs {
     ckm_best_t *best;          // null unless wanted
     unsigned long long *totals;  // [2] += calls
     uint32_t n;
+    uint32_t index_base;       // batch index of sequence 0 of this launch (chunked launches share the call regions)
     Params prm;
 };
 
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(ScanArgs a) {
     const uint16_t *A = a.hit_avg ? a.hit_avg + base : nullptr;
     uint32_t *S = GENERAL ? a.stored_idx + base : nullptr;
     const uint32_t nh = a.n_hits[i];
-    ckm_call_t *calls = a.calls + call_region_base(base, i, a.prm.min_hits);
+    ckm_call_t *calls = a.calls + call_region_base(base, a.index_base + i, a.prm.min_hits);
     ckm_otu_t *otus = a.otus ? a.otus + base : nullptr;
     const int min_hits = a.prm.min_hits;
     const float min_weighted = (float)a.prm.min_weighted_hits;
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(ScanArgs a) {
     }
     if (a.best) {
         ckm_best_t b;
-        find_best_call_dev(calls, n_calls, a.calls_work + call_region_base(base, i, a.prm.min_hits), b);
+        find_best_call_dev(calls, n_calls, a.calls_work + call_region_base(base, a.index_base + i, a.prm.min_hits), b);
         a.best[i] = b;
     }
     {  // batch total: one atomic per (converged part of a) warp

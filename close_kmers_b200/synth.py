@@ -240,7 +240,7 @@ def make_families(seed: int, sig: Signatures, fams_per_function: int = 4, max_li
     pick = rng.random(len(sig.keys)) < coverage
     kmers = sig.keys[pick].astype(np.uint64)
     kf = sig.fI[pick].astype(np.int64)
-    cnt = np.minimum(rng.geometric(0.5, len(kmers)), max_list).astype(np.int64)
+    cnt = np.minimum(rng.geometric(0.5, len(kmers)), min(max_list, 2 * fams_per_function)).astype(np.int64)  # ids in a list are distinct
     fam_off = np.zeros(len(kmers) + 1, dtype=np.uint64)
     fam_off[1:] = np.cumsum(cnt)
     owner = np.repeat(np.arange(len(kmers)), cnt)

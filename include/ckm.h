@@ -147,6 +147,8 @@ uint64_t ckm_num_sigs(const ckm_ctx *ctx);
 int ckm_table_slot_bytes(const ckm_ctx *ctx);
 /* cudaLimitMaxL2FetchGranularity in effect on the ctx's device (the loader asks for 32-byte sectors) */
 int ckm_l2_fetch_granularity(const ckm_ctx *ctx);
+/* 1 when the L2-resident slot-occupancy bitmap is in use (tables larger than L2; CKM_OCCUPANCY_BITMAP=0/1 overrides) */
+int ckm_has_occupancy_bitmap(const ckm_ctx *ctx);
 
 /* ---- parameters (KmerGuts::set_default_parameters / set_parameters, kguts.cc:236-268) -------------- */
 void ckm_set_default_params(ckm_ctx *ctx); /* order_constraint 0, min_hits 5, min_weighted_hits 0, max_gap 200 */

@@ -51,6 +51,35 @@ def test_call_batch_bit_exact(checkers, world, prm):
     assert len(want["calls"]) > 100
 
 
+def test_occupancy_bitmap_and_pipelined_host_path(checkers, world):
+    """The two large-table mechanisms, forced on a small table: the L2-resident slot-occupancy bitmap (skips the
+    DRAM read of empty slots) and the chunked two-stream host path used for find_best_call-only batches."""
+    protos, sig, img, orc, _, _ = world
+    os.environ.update(CKM_OCCUPANCY_BITMAP="1", CKM_PIPELINE_MIN_KB="0", CKM_PIPELINE_CHUNK_KB="64")
+    try:
+        for raw in ("0", "1"):
+            os.environ["CKM_FORCE_RAW_SLOTS"] = raw
+            g = api.KmerGuts(image=img, function_names=synth.function_names(sig.n_functions))
+            assert g.has_occupancy_bitmap
+            batch = wl.concat_batches(wl.edge_batch(protos), synth.make_proteins(6, protos, 4000))
+            for prm in (dict(), dict(order_constraint=1, min_hits=3)):
+                orc.set_params(**prm)
+                g.set_parameters(prm)
+                want = orc.call_batch(batch, ALL)
+                wl.assert_results_equal(g.process_aa_seq_batch(batch.residues, batch.offsets, ALL), want, f"bitmap raw={raw} {prm}")
+                # best-only -> pipelined path (~20 chunks on two streams); also with a rebased offsets array
+                got = g.process_aa_seq_batch(batch.residues, batch.offsets, api.WANT_BEST)
+                assert got["best"].tobytes() == want["best"].tobytes() and got["n_probes"] == want["n_probes"]
+                k = 37
+                sub_off = batch.offsets[k:]
+                got2 = g.process_aa_seq_batch(batch.residues, sub_off, api.WANT_BEST)
+                assert got2["best"].tobytes() == want["best"][k:].tobytes()
+            g.close()
+    finally:
+        for k in ("CKM_OCCUPANCY_BITMAP", "CKM_PIPELINE_MIN_KB", "CKM_PIPELINE_CHUNK_KB", "CKM_FORCE_RAW_SLOTS"):
+            os.environ.pop(k, None)
+
+
 def test_each_flag_alone(checkers, world):
     """The handlers pass different subsets of (calls, hit_cb, otu_stats): every subset must agree."""
     protos, _, _, orc, guts, _ = world
