@@ -88,6 +88,7 @@ def lib() -> C.CDLL:
     L.ckm_table_slot_bytes.argtypes = [C.c_void_p]
     L.ckm_l2_fetch_granularity.argtypes = [C.c_void_p]
     L.ckm_has_occupancy_bitmap.argtypes = [C.c_void_p]
+    L.ckm_set_tuning.argtypes = [C.c_void_p, C.c_uint32]
     L.ckm_set_default_params.argtypes = [C.c_void_p]
     L.ckm_set_params.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     L.ckm_get_params.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
@@ -311,6 +312,9 @@ class KmerGuts:
         r, ms = C.c_double(), C.c_double()
         _check(lib().ckm_calibrate_gather(self._h, nbytes, unroll, rounds, blocks_per_sm, C.byref(r), C.byref(ms)))
         return r.value, ms.value
+
+    def set_tuning(self, bits: int):
+        lib().ckm_set_tuning(self._h, bits)
 
     def synchronize(self):
         _check(lib().ckm_synchronize(self._h))

@@ -382,6 +382,7 @@ extern "C" int32_t ckm_otu_count(const ckm_ctx *c) { return (int32_t)c->otu_name
 extern "C" uint64_t ckm_num_sigs(const ckm_ctx *c) { return c->num_sigs; }
 extern "C" int ckm_table_slot_bytes(const ckm_ctx *c) { return c->slot_bytes; }
 extern "C" int ckm_l2_fetch_granularity(const ckm_ctx *c) { return c->l2_fetch; }
+extern "C" void ckm_set_tuning(ckm_ctx *c, uint32_t bits) { c->tuning = bits; }
 extern "C" int ckm_has_occupancy_bitmap(const ckm_ctx *c) { return c->occupied.p != nullptr; }
 extern "C" void *ckm_stream(ckm_ctx *c) { return (void *)c->stream; }
 extern "C" uint64_t ckm_launch_count(const ckm_ctx *c) { return c->launches; }
@@ -539,10 +540,15 @@ static int launch_range(ckm_ctx *c, cudaStream_t stream, const uint8_t *d_res, c
     tv.num_sigs = c->num_sigs;
     tv.magic = c->magic;
     tv.occupied = (const uint32_t *)c->occupied.p;
+    tv.tuning = c->tuning;
     {
         const uint32_t warps_per_block = kProbeThreads / 32;
         uint64_t blocks = ((uint64_t)cnt + warps_per_block - 1) / warps_per_block;
-        blocks = std::min<uint64_t>(blocks, (uint64_t)c->sm_count * 8);
+        const uint32_t bps = (c->tuning >> 8) & 0xFu;  // blocks per SM override (0 = as many as fit)
+        // 64 blocks per SM in the grid (3 are resident at 80 registers): a finer grid than the residency evens out the
+        // tail between long and short proteins (measured: 7.5 -> 7.1 ms on C2, profiles/r1/tune3.jsonl)
+        const uint32_t gshift = (c->tuning >> 12) & 0xFu;
+        blocks = std::min<uint64_t>(blocks, ((uint64_t)c->sm_count * (bps ? bps : 8)) << (gshift ? gshift - 1 : 3));
         uint64_t *keys = plan.want_keys ? (uint64_t *)c->hit_keys.p : nullptr;
         uint16_t *avg = plan.want_avg ? (uint16_t *)c->hit_avg.p : nullptr;
         if (c->slot_bytes == kPackedSlotBytes)
@@ -694,16 +700,13 @@ static int upload_batch(ckm_ctx *c, const char *residues, const uint64_t *offset
 // offset / sequence index, hence disjoint), so nothing is double-buffered.
 static int call_batch_pipelined(ckm_ctx *c, const char *residues, const uint64_t *offsets, uint32_t n, ckm_batch_out_t *out) {
     CU(cudaSetDevice(c->device));
-    uint32_t max_len = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        if (offsets[i + 1] < offsets[i]) return ckm_fail(CKM_EINVAL, "offsets must be non-decreasing (at %u)", i);
-        const uint64_t l = offsets[i + 1] - offsets[i];
-        if (l > 500000000ull) return ckm_fail(CKM_EINVAL, "sequence %u longer than MAX_SEQ_LEN", i);
-        max_len = std::max<uint32_t>(max_len, (uint32_t)l);
-    }
-    const uint64_t base0 = offsets[0], total = offsets[n] - base0;
+    const uint64_t base0 = offsets[0];
+    if (offsets[n] < base0) return ckm_fail(CKM_EINVAL, "offsets must be non-decreasing");
+    const uint64_t total = offsets[n] - base0;
     RunPlan plan;
-    RC(prepare_regions(c, n, total, std::max(max_len, 1u), CKM_WANT_BEST, &plan));
+    // max_len is only known chunk by chunk (validation is overlapped with the copies): size for the general kernel
+    // lazily, below, if a chunk turns out to need it
+    RC(prepare_regions(c, n, total, 1u, CKM_WANT_BEST, &plan));
     RC(c->in_res.ensure(total + 32));
     RC(c->in_off.ensure(((size_t)n + 1) * 8));
     RC(c->h_best.ensure(((size_t)n + 1) * sizeof(ckm_best_t)));
@@ -712,33 +715,62 @@ static int call_batch_pipelined(ckm_ctx *c, const char *residues, const uint64_t
     if (!c->ev_ready) CU(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
     if (!c->ev_done2) CU(cudaEventCreateWithFlags(&c->ev_done2, cudaEventDisableTiming));
     c->cur_off = (const uint64_t *)c->in_off.p;
-    const uint64_t *h_off = offsets;
-    if (base0 != 0) {
-        RC(c->h_off.ensure(((size_t)n + 1) * 8));
-        uint64_t *t = (uint64_t *)c->h_off.p;
-        for (uint32_t i = 0; i <= n; i++) t[i] = offsets[i] - base0;
-        h_off = t;
-    }
-    // stream 0: offsets, counters, slack; stream 1 waits for them
-    CU(cudaMemcpyAsync(c->in_off.p, h_off, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    // stream 0: counters and slack; stream 1 waits for them.  Offsets travel with their chunk.
     CU(cudaMemsetAsync(c->totals.p, 0, 64, c->stream));
     CU(cudaMemsetAsync((uint8_t *)c->in_res.p + total, 0, 32, c->stream));
     CU(cudaEventRecord(c->ev_ready, c->stream));
     CU(cudaStreamWaitEvent(c->stream2, c->ev_ready, 0));
+    uint64_t *reb = nullptr;
+    if (base0 != 0) {
+        RC(c->h_off.ensure(((size_t)n + 1) * 8));
+        reb = (uint64_t *)c->h_off.p;
+        reb[0] = 0;
+    }
+    // chunk schedule: ramp up from 1/6 of the chunk size so the first kernels start early, and end on a short chunk
+    // so little compute is left once the last copy lands
+    const uint64_t cap = std::max<uint64_t>(c->pipeline_chunk_bytes, 1024), tail = cap / 4;
+    uint64_t want = std::max<uint64_t>(cap / 6, 1024);
     uint32_t i0 = 0;
     int k = 0;
     while (i0 < n) {
-        uint32_t i1 = i0;
-        const uint64_t start = h_off[i0];
-        while (i1 < n && h_off[i1 + 1] - start <= c->pipeline_chunk_bytes) i1++;
-        if (i1 == i0) i1 = i0 + 1;  // a single sequence longer than a chunk
-        const uint64_t bytes = h_off[i1] - start;
+        const uint64_t start = offsets[i0] - base0, left = total - start;
+        uint64_t goal = want;
+        if (left <= goal + tail) goal = left > 2 * tail ? left - tail : left;
+        uint32_t i1 = i0, max_len = 0;
+        while (i1 < n) {  // validate and size the chunk in one pass over its offsets
+            if (offsets[i1 + 1] < offsets[i1]) return ckm_fail(CKM_EINVAL, "offsets must be non-decreasing (at %u)", i1);
+            const uint64_t l = offsets[i1 + 1] - offsets[i1];
+            if (l > 500000000ull) return ckm_fail(CKM_EINVAL, "sequence %u longer than MAX_SEQ_LEN", i1);
+            if (i1 > i0 && offsets[i1 + 1] - base0 - start > goal) break;
+            max_len = std::max<uint32_t>(max_len, (uint32_t)l);
+            if (reb) reb[i1 + 1] = offsets[i1 + 1] - base0;
+            i1++;
+        }
+        const uint64_t bytes = offsets[i1] - base0 - start;
+        RunPlan cp = plan;
+        cp.general = max_len > kHitCap + CKM_KMER_SIZE || c->prm.order_constraint != 0;
+        if (cp.general) {
+            if (c->stored_idx.cap < (total + 1) * 4) {  // first general chunk: nothing in flight uses this buffer yet
+                CU(cudaStreamSynchronize(c->stream));
+                CU(cudaStreamSynchronize(c->stream2));
+                RC(c->stored_idx.ensure((total + 1) * 4));
+            }
+            cp.want_avg = c->prm.order_constraint != 0;
+            if (cp.want_avg && c->hit_avg.cap < (total + 1) * 2) {
+                CU(cudaStreamSynchronize(c->stream));
+                CU(cudaStreamSynchronize(c->stream2));
+                RC(c->hit_avg.ensure((total + 1) * 2));
+            }
+        }
         cudaStream_t st = (k & 1) ? c->stream2 : c->stream;
+        const uint64_t *src_off = reb ? reb : offsets;
+        CU(cudaMemcpyAsync((uint64_t *)c->in_off.p + i0, src_off + i0, ((size_t)(i1 - i0) + 1) * 8, cudaMemcpyHostToDevice, st));
         if (bytes) CU(cudaMemcpyAsync((uint8_t *)c->in_res.p + start, residues + base0 + start, bytes, cudaMemcpyHostToDevice, st));
-        RC(launch_range(c, st, (const uint8_t *)c->in_res.p, (const uint64_t *)c->in_off.p, i0, i1 - i0, CKM_WANT_BEST, plan, nullptr));
+        RC(launch_range(c, st, (const uint8_t *)c->in_res.p, (const uint64_t *)c->in_off.p, i0, i1 - i0, CKM_WANT_BEST, cp, nullptr));
         CU(cudaMemcpyAsync((ckm_best_t *)c->h_best.p + i0, (const ckm_best_t *)c->best.p + i0, (size_t)(i1 - i0) * sizeof(ckm_best_t),
                            cudaMemcpyDeviceToHost, st));
         i0 = i1;
+        want = std::min(cap, want * 2);
         k++;
     }
     // join stream 1 into stream 0, then read the batch counters

@@ -38,6 +38,9 @@ struct TableView {
     // the reference's <= 1/3 load factor -- is answered from L2 and never becomes a DRAM transaction, which is
     // what bounds this kernel.  NULL when the table itself fits L2.
     const uint32_t *occupied;
+    // cache-policy experiments (ckm_set_tuning): bit0 table loads evict_first, bit1 bitmap loads evict_last,
+    // bit2 hit-record stores evict_first
+    uint32_t tuning;
 };
 
 // One table hit as the ordered scoring scan consumes it (KmerHit, kguts.h:154-163, minus the key).
@@ -51,6 +54,32 @@ struct __align__(16) HitRec {
 struct Params {  // kguts.h:290-293
     int order_constraint, min_hits, min_weighted_hits, max_gap;
 };
+
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint4 ldg_v4_hint(const uint4 *p, uint64_t policy) {
+    uint4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldg_u32_hint(const uint32_t *p, uint64_t policy) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ void stg_v4_hint(uint4 *p, const uint4 &v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy)
+                 : "memory");
+}
 
 // key % d with d = num_sigs: q = mulhi(key, floor(2^64/d)) is floor(key/d) or one less.
 __device__ __forceinline__ uint64_t fast_mod(uint64_t key, uint64_t d, uint64_t magic) {

@@ -36,6 +36,9 @@ struct SlotIO<true> {
     static __device__ __forceinline__ raw_t load(const void *slots, uint64_t h) {
         return __ldg(reinterpret_cast<const uint4 *>(slots) + h);
     }
+    static __device__ __forceinline__ raw_t load_hint(const void *slots, uint64_t h, uint64_t policy) {
+        return ldg_v4_hint(reinterpret_cast<const uint4 *>(slots) + h, policy);
+    }
     static __device__ __forceinline__ int test(const raw_t &v, uint64_t key, SlotFields &f) {
         if (v.x == (uint32_t)key && (v.y & 0xFu) == (uint32_t)(key >> 32)) {
             f.fI = v.w & (kPackedFieldLimit - 1);
@@ -62,6 +65,7 @@ struct SlotIO<false> {
         r.b = __ldg(s + 2);
         return r;
     }
+    static __device__ __forceinline__ raw_t load_hint(const void *slots, uint64_t h, uint64_t) { return load(slots, h); }
     static __device__ __forceinline__ int test(const raw_t &v, uint64_t key, SlotFields &f) {
         if (v.k == key) {
             f.oI = (int32_t)(uint32_t)v.a;
@@ -90,6 +94,9 @@ probe_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64_t 
     const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     uint32_t my_probes = 0, my_hits = 0;
+    const bool t_tab = tv.tuning & 1u, t_bm = tv.tuning & 2u, t_st = tv.tuning & 4u;
+    const bool t_nostore = tv.tuning & 8u;  // TIMING EXPERIMENT ONLY: drop the hit records (results are then wrong)
+    const uint64_t pol_first = policy_evict_first(), pol_last = policy_evict_last();
 
     for (uint32_t i = warp0; i < n; i += n_warps) {
         const uint64_t base = __ldg(offsets + i);
@@ -172,7 +179,7 @@ probe_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64_t 
                     uint32_t bw[4];
 #pragma unroll
                     for (int j = 0; j < 4; j++)
-                        if (act & (1u << j)) bw[j] = __ldg(tv.occupied + (h[j] >> 5));
+                        if (act & (1u << j)) bw[j] = t_bm ? ldg_u32_hint(tv.occupied + (h[j] >> 5), pol_last) : __ldg(tv.occupied + (h[j] >> 5));
 #pragma unroll
                     for (int j = 0; j < 4; j++)
                         if ((act & (1u << j)) && !((bw[j] >> (h[j] & 31u)) & 1u)) need &= ~(1u << j);  // empty slot: miss
@@ -180,7 +187,7 @@ probe_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64_t 
                 typename SlotIO<PACKED>::raw_t v[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++)
-                    if (need & (1u << j)) v[j] = SlotIO<PACKED>::load(tv.slots, h[j]);
+                    if (need & (1u << j)) v[j] = t_tab ? SlotIO<PACKED>::load_hint(tv.slots, h[j], pol_first) : SlotIO<PACKED>::load(tv.slots, h[j]);
 
                 SlotFields f[4];
                 uint32_t hm = 0;
@@ -213,13 +220,14 @@ probe_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64_t 
                 uint32_t o = count + incl - cnt;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    if (hm & (1u << j)) {
+                    if ((hm & (1u << j)) && !t_nostore) {
                         HitRec rec;
                         rec.pos = q0 + j;
                         rec.fI = f[j].fI;
                         rec.wt = f[j].wt;
                         rec.oI = f[j].oI;
-                        out[o] = rec;
+                        if (t_st) stg_v4_hint(reinterpret_cast<uint4 *>(out + o), *reinterpret_cast<const uint4 *>(&rec), pol_first);
+                        else out[o] = rec;
                         if (hit_keys) hit_keys[base + o] = key[j];
                         if (hit_avg) hit_avg[base + o] = (uint16_t)f[j].avg;
                         o++;

@@ -149,6 +149,9 @@ int ckm_table_slot_bytes(const ckm_ctx *ctx);
 int ckm_l2_fetch_granularity(const ckm_ctx *ctx);
 /* 1 when the L2-resident slot-occupancy bitmap is in use (tables larger than L2; CKM_OCCUPANCY_BITMAP=0/1 overrides) */
 int ckm_has_occupancy_bitmap(const ckm_ctx *ctx);
+/* L2 cache-policy switches of the probe kernel (results unaffected): bit0 table loads evict_first, bit1 bitmap
+ * loads evict_last, bit2 hit-record stores evict_first */
+void ckm_set_tuning(ckm_ctx *ctx, uint32_t bits);
 
 /* ---- parameters (KmerGuts::set_default_parameters / set_parameters, kguts.cc:236-268) -------------- */
 void ckm_set_default_params(ckm_ctx *ctx); /* order_constraint 0, min_hits 5, min_weighted_hits 0, max_gap 200 */

@@ -165,5 +165,17 @@ def test_window_saturation_long_protein(checkers):
         got = guts.process_aa_seq_batch(batch.residues, batch.offsets, ALL)
         assert want["n_hits"] > 40_000
         wl.assert_results_equal(got, want, f"saturation {prm}")
+    # the chunked host path decides per chunk whether the general scan kernel is needed
+    os.environ.update(CKM_PIPELINE_MIN_KB="0", CKM_PIPELINE_CHUNK_KB="16")
+    try:
+        g2 = api.KmerGuts(image=img)
+        big = wl.concat_batches(synth.make_proteins(5, protos, 300), wl.concat_batches(batch, synth.make_proteins(6, protos, 300)))
+        orc.set_params()
+        want = orc.call_batch(big, api.WANT_BEST)
+        assert g2.process_aa_seq_batch(big.residues, big.offsets, api.WANT_BEST)["best"].tobytes() == want["best"].tobytes()
+        g2.close()
+    finally:
+        os.environ.pop("CKM_PIPELINE_MIN_KB")
+        os.environ.pop("CKM_PIPELINE_CHUNK_KB")
     guts.close()
     orc.close()

@@ -1,0 +1,39 @@
+"""End-to-end (host buffers in, best calls out) sweep over pipeline chunk sizes on the C2 workload (GPU box)."""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from close_kmers_b200 import api, synth
+
+n_prot = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+n_sigs = int(sys.argv[2]) if len(sys.argv) > 2 else 100_000_000
+protos = synth.make_prototypes(12345, max(64, -(-n_sigs // 293) + 8), 300, 60.0)
+batch = synth.make_proteins_parallel(12346, protos, n_prot)
+sig = synth.make_signatures(protos, n_sigs, dedupe=n_sigs <= 2_000_000)
+img = api.build_image(synth.bucket_count(len(sig.keys)), sig.keys, sig.fI, sig.oI, sig.avg, sig.wt)
+L = api.lib()
+total = int(batch.offsets[-1])
+hp_res, hp_off = C.c_void_p(), C.c_void_p()
+api._check(L.ckm_host_alloc(C.byref(hp_res), total + 64))
+api._check(L.ckm_host_alloc(C.byref(hp_off), (batch.n + 1) * 8))
+C.memmove(hp_res.value, batch.residues.ctypes.data, total)
+C.memmove(hp_off.value, batch.offsets.ctypes.data, (batch.n + 1) * 8)
+import torch
+props = torch.cuda.get_device_properties(0)
+print(json.dumps(dict(l2=props.L2_cache_size)), flush=True)
+for chunk_kb in (24576, 49152, 98304):
+    os.environ["CKM_PIPELINE_CHUNK_KB"] = str(chunk_kb)
+    g = api.KmerGuts(image=img)
+    for _ in range(2):
+        g.call_batch_raw(hp_res.value, hp_off.value, batch.n, api.WANT_BEST)
+    t0 = time.perf_counter()
+    K = 5
+    for _ in range(K):
+        g.call_batch_raw(hp_res.value, hp_off.value, batch.n, api.WANT_BEST)
+    dt = (time.perf_counter() - t0) / K
+    print(json.dumps(dict(chunk_kb=chunk_kb, e2e_ms=dt * 1e3, proteins_per_s=batch.n / dt)), flush=True)
+    g.close()
