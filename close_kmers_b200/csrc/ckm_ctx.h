@@ -28,7 +28,7 @@ struct ckm_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: second lane of the pipelined host path
     cudaEvent_t ev_ready = nullptr, ev_done2 = nullptr;
-    uint64_t pipeline_chunk_bytes = 48ull << 20, pipeline_min_bytes = 32ull << 20;
+    uint64_t pipeline_chunk_bytes = 96ull << 20, pipeline_min_bytes = 32ull << 20;
     bool force_raw = false;
     uint32_t tuning = 0;  // TableView::tuning
     int l2_fetch = 0;  // cudaLimitMaxL2FetchGranularity in effect
