@@ -19,7 +19,7 @@
 namespace ckm {
 
 constexpr uint32_t kFamSmemCap = 1024;  // slots of the per-warp shared-memory maps
-constexpr uint32_t kFamSmemE = 640;     // use them when the protein has at most this many list entries
+constexpr uint32_t kFamSmemE = 512;     // use them when the protein has at most this many list entries (cap = 2E)
 constexpr int kFamWarps = 4;            // warps per block of fam_vote_kernel
 constexpr int kFamStage = 8;            // list entries prefetched per hit
 constexpr uint32_t kFamWarpWords = 5 * kFamSmemCap + 32 * kFamStage;
@@ -128,7 +128,10 @@ fam_vote_kernel(FamTables ft, const uint64_t *__restrict__ offsets, const uint32
         uint32_t *keys, *cnt, *pkeys, cap;
         float *wsum, *pw;
         if (gcap[i] == 0) {
-            cap = kFamSmemCap;
+            // shared-memory maps sized to the protein: at most E distinct families, kept at most half full, so short
+            // fragments (the fastq path: a few dozen list entries) clear and scan 32-64 slots instead of 1024
+            cap = 32u;
+            while (cap < 2u * E[i]) cap <<= 1;
             keys = s_keys; cnt = s_cnt; wsum = s_w; pkeys = s_pkeys; pw = s_pw;
             for (uint32_t s = lane; s < cap; s += 32) { keys[s] = 0u; pkeys[s] = 0u; }
         } else {  // global scratch: 5 arrays of `cap` words, keys pre-zeroed by the host-side memset

@@ -97,7 +97,8 @@ matrix_row_kernel(const uint32_t *__restrict__ post_ids, const uint64_t *__restr
         const uint32_t nh = n_hits[r];
         uint32_t *keys, *cnt, cap;
         if (gcap[r] == 0) {
-            cap = kFamSmemCap;
+            cap = 32u;  // at most E distinct partners, map kept at most half full
+            while (cap < 2u * E[r]) cap <<= 1;
             keys = my;
             cnt = my + kFamSmemCap;
             for (uint32_t s = lane; s < cap; s += 32) { keys[s] = 0u; cnt[s] = 0u; }

@@ -13,7 +13,7 @@ from close_kmers_b200 import api, synth
 n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
 n_sigs = int(sys.argv[2]) if len(sys.argv) > 2 else 10_000_000
 protos = synth.make_prototypes(4242, -(-n_sigs // 293) + 8, 300, 60.0)
-sig = synth.make_signatures(protos, n_sigs, dedupe=n_sigs <= 2_000_000)
+sig = synth.make_signatures(protos, n_sigs, dedupe=True)  # family tables are keyed by k-mer: keys must be distinct
 img = api.build_image(synth.bucket_count(len(sig.keys)), sig.keys, sig.fI, sig.oI, sig.avg, sig.wt)
 fam = synth.make_families(7, sig)
 chunk = 250_000
