@@ -39,7 +39,7 @@ struct TableView {
     // what bounds this kernel.  NULL when the table itself fits L2.
     const uint32_t *occupied;
     // cache-policy experiments (ckm_set_tuning): bit0 table loads evict_first, bit1 bitmap loads evict_last,
-    // bit2 hit-record stores evict_first
+    // bit2 hit-record stores evict_first, bit4 table loads with a 64-byte L2 fetch (instead of bit0)
     uint32_t tuning;
 };
 
@@ -69,6 +69,11 @@ __device__ __forceinline__ uint4 ldg_v4_hint(const uint4 *p, uint64_t policy) {
     uint4 v;
     asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ uint4 ldg_v4_l2_64(const uint4 *p) {  // L2 fetches 64 B instead of the whole 128-byte line
+    uint4 v;
+    asm volatile("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
 __device__ __forceinline__ uint32_t ldg_u32_hint(const uint32_t *p, uint64_t policy) {

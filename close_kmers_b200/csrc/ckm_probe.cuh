@@ -37,7 +37,8 @@ struct SlotIO<true> {
         return __ldg(reinterpret_cast<const uint4 *>(slots) + h);
     }
     static __device__ __forceinline__ raw_t load_hint(const void *slots, uint64_t h, uint64_t policy) {
-        return ldg_v4_hint(reinterpret_cast<const uint4 *>(slots) + h, policy);
+        return policy ? ldg_v4_hint(reinterpret_cast<const uint4 *>(slots) + h, policy)
+                      : ldg_v4_l2_64(reinterpret_cast<const uint4 *>(slots) + h);
     }
     static __device__ __forceinline__ int test(const raw_t &v, uint64_t key, SlotFields &f) {
         if (v.x == (uint32_t)key && (v.y & 0xFu) == (uint32_t)(key >> 32)) {
@@ -94,9 +95,8 @@ probe_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64_t 
     const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     uint32_t my_probes = 0, my_hits = 0;
-    const bool t_tab = tv.tuning & 1u, t_bm = tv.tuning & 2u, t_st = tv.tuning & 4u;
-    const bool t_nostore = tv.tuning & 8u;  // TIMING EXPERIMENT ONLY: drop the hit records (results are then wrong)
-    const uint64_t pol_first = policy_evict_first(), pol_last = policy_evict_last();
+    const bool t_tab = tv.tuning & 17u, t_bm = tv.tuning & 2u, t_st = tv.tuning & 4u;
+    const uint64_t pol_first = (tv.tuning & 16u) ? 0ull : policy_evict_first(), pol_last = policy_evict_last();
 
     for (uint32_t i = warp0; i < n; i += n_warps) {
         const uint64_t base = __ldg(offsets + i);
@@ -220,7 +220,7 @@ probe_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64_t 
                 uint32_t o = count + incl - cnt;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    if ((hm & (1u << j)) && !t_nostore) {
+                    if (hm & (1u << j)) {
                         HitRec rec;
                         rec.pos = q0 + j;
                         rec.fI = f[j].fI;

@@ -23,10 +23,13 @@ g = api.KmerGuts(image=img, function_names=synth.function_names(sig.n_functions)
 g.family_load(fam.kmers, fam.fam_off, fam.fam_ids, fam.pgf, fam.plf, fam.function)
 g.fq_batch(reads.residues[: 150 * 100_000], reads.offsets[: 100_001])
 t0 = time.perf_counter()
-res = g.fq_batch(reads.residues, reads.offsets)
+res = g.fq_batch(reads.residues, reads.offsets)   # first full-size call: grows every work buffer
+dt_first = time.perf_counter() - t0
+t0 = time.perf_counter()
+res = g.fq_batch(reads.residues, reads.offsets)   # steady state
 dt = time.perf_counter() - t0
 out = dict(reads=n_reads, signature_kmers=len(sig.keys), fragments=int(res["n_fragments"]), probes=int(res["n_probes"]),
-           reads_with_output=int((res["best_frame"] != 0).sum()), gpu_e2e_s=dt, gpu_reads_per_s=n_reads / dt,
+           reads_with_output=int((res["best_frame"] != 0).sum()), gpu_first_call_s=dt_first, gpu_e2e_s=dt, gpu_reads_per_s=n_reads / dt,
            gpu_probes_per_s=int(res["n_probes"]) / dt)
 import cpu_checkers as cc
 cc.ensure_built()

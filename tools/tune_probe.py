@@ -25,7 +25,7 @@ for bitmap in ("1", "0"):
     os.environ["CKM_OCCUPANCY_BITMAP"] = bitmap
     for persist in ("0",):
         g = api.KmerGuts(image=img)
-        for tuning in (0, 0x1000, 0x5000):
+        for tuning in (0, 16):
             if bitmap == "0" and (tuning & 2):
                 continue
             g.set_tuning(tuning)
