@@ -79,8 +79,80 @@ struct SlotIO<false> {
     }
 };
 
-constexpr int kProbeThreads = 256;
 constexpr int kTile = 128;  // start positions per warp step (4 per lane)
+
+// The four 8-mer keys a lane owns in one 128-position warp step (positions t0 + 4*lane + j), with bit j of `act` set
+// when window j is probed: all eight residues valid (kguts.cc:273-339, 682-732) and j-th start < nwin.  `nwin` (= len-8:
+// the last window is never probed, kguts.cc:792) shrinks when an embedded NUL ends the protein (strlen, kguts.cc:791).
+struct TileKeys {
+    uint64_t key[4];
+    uint32_t act;
+};
+
+__device__ __forceinline__ TileKeys tile_keys(const uint8_t *lut, const uint32_t *__restrict__ wb, uint32_t nwords, uint32_t sh,
+                                              uint32_t t0, uint32_t lane, uint32_t len, uint32_t &nwin) {
+    // ---- residues: 32 words + 3 spill words, re-aligned to the protein start ----
+    const uint32_t wi = (t0 >> 2) + lane;
+    uint32_t w = wi < nwords ? __ldg(wb + wi) : 0u;
+    uint32_t x = (lane < 3u && wi + 32u < nwords) ? __ldg(wb + wi + 32u) : 0u;
+    uint32_t w_next = __shfl_down_sync(0xffffffffu, w, 1);
+    const uint32_t x0 = __shfl_sync(0xffffffffu, x, 0);
+    if (lane == 31u) w_next = x0;
+    const uint32_t x_next = __shfl_down_sync(0xffffffffu, x, 1);
+    const uint32_t a = __funnelshift_r(w, w_next, sh);   // residues t0+4*lane .. +3
+    const uint32_t e = __funnelshift_r(x, x_next, sh);   // lanes 0,1: residues t0+128.. / t0+132..
+
+    // the reference scans strlen(seq) residues (kguts.cc:791): an embedded NUL ends the protein
+    {
+        const uint32_t za = (a - 0x01010101u) & ~a & 0x80808080u;
+        const uint32_t ze = (e - 0x01010101u) & ~e & 0x80808080u;
+        uint32_t r = 0xffffffffu;
+        if (za) r = t0 + 4u * lane + ((__ffs(za) - 1) >> 3);
+        else if (lane < 2u && ze) r = t0 + kTile + 4u * lane + ((__ffs(ze) - 1) >> 3);
+        r = __reduce_min_sync(0xffffffffu, r);
+        if (r < len) nwin = min(nwin, r > CKM_KMER_SIZE ? r - CKM_KMER_SIZE : 0u);
+    }
+
+    const uint32_t c0 = codes_of_word(lut, a);
+    const uint32_t ce = codes_of_word(lut, e);
+    uint32_t c1 = __shfl_down_sync(0xffffffffu, c0, 1);
+    uint32_t c2 = __shfl_down_sync(0xffffffffu, c0, 2);
+    const uint32_t e0 = __shfl_sync(0xffffffffu, ce, 0);
+    const uint32_t e1 = __shfl_sync(0xffffffffu, ce, 1);
+    if (lane == 31u) { c1 = e0; c2 = e1; }
+    if (lane == 30u) c2 = e0;
+
+    // ---- four keys per lane ----
+    uint32_t b[11];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        b[k] = (c0 >> (8 * k)) & 0xFFu;
+        b[4 + k] = (c1 >> (8 * k)) & 0xFFu;
+        if (k < 3) b[8 + k] = (c2 >> (8 * k)) & 0xFFu;
+    }
+    // bit i of inv set <=> residue i of the lane's 11 is not one of the 20 amino acids
+    const uint32_t i0 = c0 & 0x80808080u, i1 = c1 & 0x80808080u, i2 = c2 & 0x00808080u;
+    const uint32_t inv = ((i0 >> 7) & 1u) | ((i0 >> 14) & 2u) | ((i0 >> 21) & 4u) | ((i0 >> 28) & 8u) |
+                         ((i1 >> 3) & 16u) | ((i1 >> 10) & 32u) | ((i1 >> 17) & 64u) | ((i1 >> 24) & 128u) |
+                         ((i2 << 1) & 256u) | ((i2 >> 6) & 512u) | ((i2 >> 13) & 1024u);
+    uint32_t g[8];
+    g[0] = ((b[0] * 20u + b[1]) * 20u + b[2]) * 20u + b[3];
+#pragma unroll
+    for (int q = 0; q < 7; q++) g[q + 1] = (g[q] - b[q] * 8000u) * 20u + b[q + 4];
+
+    const uint32_t q0 = t0 + 4u * lane;
+    TileKeys tk;
+    tk.act = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const bool ok = (((inv >> j) & 0xFFu) == 0u) && (q0 + j < nwin);
+        tk.key[j] = (uint64_t)g[j] * 160000ull + g[j + 4];
+        tk.act |= ok ? (1u << j) : 0u;
+    }
+    return tk;
+}
+
+constexpr int kProbeThreads = 256;
 
 template <bool PACKED>
 __global__ void __launch_bounds__(kProbeThreads)
@@ -113,64 +185,14 @@ probe_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64_t 
             HitRec *out = hits + base;
 
             for (uint32_t t0 = 0; t0 < nwin; t0 += kTile) {
-                // ---- residues: 32 words + 3 spill words, re-aligned to the protein start ----
-                const uint32_t wi = (t0 >> 2) + lane;
-                uint32_t w = wi < nwords ? __ldg(wb + wi) : 0u;
-                uint32_t x = (lane < 3u && wi + 32u < nwords) ? __ldg(wb + wi + 32u) : 0u;
-                uint32_t w_next = __shfl_down_sync(0xffffffffu, w, 1);
-                const uint32_t x0 = __shfl_sync(0xffffffffu, x, 0);
-                if (lane == 31u) w_next = x0;
-                const uint32_t x_next = __shfl_down_sync(0xffffffffu, x, 1);
-                const uint32_t a = __funnelshift_r(w, w_next, sh);   // residues t0+4*lane .. +3
-                const uint32_t e = __funnelshift_r(x, x_next, sh);   // lanes 0,1: residues t0+128.. / t0+132..
-
-                // the reference scans strlen(seq) residues (kguts.cc:791): an embedded NUL ends the protein
-                {
-                    const uint32_t za = (a - 0x01010101u) & ~a & 0x80808080u;
-                    const uint32_t ze = (e - 0x01010101u) & ~e & 0x80808080u;
-                    uint32_t r = 0xffffffffu;
-                    if (za) r = t0 + 4u * lane + ((__ffs(za) - 1) >> 3);
-                    else if (lane < 2u && ze) r = t0 + kTile + 4u * lane + ((__ffs(ze) - 1) >> 3);
-                    r = __reduce_min_sync(0xffffffffu, r);
-                    if (r < len) nwin = min(nwin, r > CKM_KMER_SIZE ? r - CKM_KMER_SIZE : 0u);
-                }
-
-                const uint32_t c0 = codes_of_word(lut, a);
-                const uint32_t ce = codes_of_word(lut, e);
-                uint32_t c1 = __shfl_down_sync(0xffffffffu, c0, 1);
-                uint32_t c2 = __shfl_down_sync(0xffffffffu, c0, 2);
-                const uint32_t e0 = __shfl_sync(0xffffffffu, ce, 0);
-                const uint32_t e1 = __shfl_sync(0xffffffffu, ce, 1);
-                if (lane == 31u) { c1 = e0; c2 = e1; }
-                if (lane == 30u) c2 = e0;
-
-                // ---- four keys per lane ----
-                uint32_t b[11];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    b[k] = (c0 >> (8 * k)) & 0xFFu;
-                    b[4 + k] = (c1 >> (8 * k)) & 0xFFu;
-                    if (k < 3) b[8 + k] = (c2 >> (8 * k)) & 0xFFu;
-                }
-                // bit i of inv set <=> residue i of the lane's 11 is not one of the 20 amino acids
-                const uint32_t i0 = c0 & 0x80808080u, i1 = c1 & 0x80808080u, i2 = c2 & 0x00808080u;
-                const uint32_t inv = ((i0 >> 7) & 1u) | ((i0 >> 14) & 2u) | ((i0 >> 21) & 4u) | ((i0 >> 28) & 8u) |
-                                     ((i1 >> 3) & 16u) | ((i1 >> 10) & 32u) | ((i1 >> 17) & 64u) | ((i1 >> 24) & 128u) |
-                                     ((i2 << 1) & 256u) | ((i2 >> 6) & 512u) | ((i2 >> 13) & 1024u);
-                uint32_t g[8];
-                g[0] = ((b[0] * 20u + b[1]) * 20u + b[2]) * 20u + b[3];
-#pragma unroll
-                for (int q = 0; q < 7; q++) g[q + 1] = (g[q] - b[q] * 8000u) * 20u + b[q + 4];
-
+                const TileKeys tk = tile_keys(lut, wb, nwords, sh, t0, lane, len, nwin);
                 const uint32_t q0 = t0 + 4u * lane;
+                const uint32_t act = tk.act;
                 uint64_t key[4], h[4];
-                uint32_t act = 0;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const bool ok = (((inv >> j) & 0xFFu) == 0u) && (q0 + j < nwin);
-                    key[j] = (uint64_t)g[j] * 160000ull + g[j + 4];
+                    key[j] = tk.key[j];
                     h[j] = fast_mod(key[j], tv.num_sigs, tv.magic);
-                    act |= ok ? (1u << j) : 0u;
                 }
 
                 // ---- probe: occupancy bits from L2 first, then the sector loads that are still needed ----

@@ -65,6 +65,52 @@ __global__ void k(const uint4 *base, uint64_t n_units, uint32_t rounds, unsigned
     if (acc == 0x12345678u) atomicAdd(sink, 1ull);
 }
 
+static const uint4 *g_buf;
+static unsigned long long *g_sink;
+static int g_sms;
+
+// Partitioned-probe emulation: record r (consumed in order by the grid) reads a random 16-byte unit inside table bin
+// r / recs_per_bin -- i.e. random within a sliding window of `bin_units` units -- to see what the L2 turns a
+// bin-sorted probe stream into.
+template <int UNROLL>
+__global__ void __launch_bounds__(256) k_window(const uint4 *base, uint64_t bin_units, uint64_t recs_per_bin, uint64_t n_recs,
+                                                unsigned long long *sink) {
+    uint32_t acc = 0;
+    const uint64_t per_block = (uint64_t)256 * UNROLL;
+    for (uint64_t r0 = (uint64_t)blockIdx.x * per_block; r0 < n_recs; r0 += (uint64_t)gridDim.x * per_block) {
+        uint4 v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const uint64_t r = r0 + (uint64_t)u * 256 + threadIdx.x;
+            const uint64_t bin = r / recs_per_bin;
+            const uint64_t idx = bin * bin_units + mix64(r + 0x9e3779b97f4a7c15ull) % bin_units;
+            v[u] = __ldg(base + idx);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) acc ^= v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
+    }
+    if (acc == 0x12345678u) atomicAdd(sink, 1ull);
+}
+
+static void run_window(double table_gb, double bin_mb, double recs_per_unit, int bps) {
+    const uint64_t bin_units = (uint64_t)(bin_mb * 1e6 / 16);
+    const uint64_t n_bins = (uint64_t)(table_gb * 1e9 / 16) / bin_units;
+    const uint64_t recs_per_bin = (uint64_t)(bin_units * recs_per_unit);
+    const uint64_t n_recs = recs_per_bin * n_bins;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    k_window<4><<<g_sms * bps, 256>>>(g_buf, bin_units, recs_per_bin, n_recs, g_sink);
+    CK(cudaEventRecord(e0));
+    k_window<4><<<g_sms * bps, 256>>>(g_buf, bin_units, recs_per_bin, n_recs, g_sink);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf("window: table %.1f GB, bins of %.0f MB, %.2f probes per 16-B slot (%.0fM probes), bps %d: %8.3f ms  %7.2f G probes/s\n",
+           table_gb, bin_mb, recs_per_unit, n_recs / 1e6, bps, ms, n_recs / ms / 1e6);
+}
+
 // TMA flavour: every lane issues UNROLL 1-D bulk copies of BYTES into shared memory, one mbarrier per warp
 template <int UNROLL, int BYTES>
 __global__ void k_tma(const uint8_t *base, uint64_t n_units, uint32_t rounds, unsigned long long *sink) {
@@ -100,9 +146,6 @@ __global__ void k_tma(const uint8_t *base, uint64_t n_units, uint32_t rounds, un
     if (acc == 0x12345678u) atomicAdd(sink, 1ull);
 }
 
-static const uint4 *g_buf;
-static unsigned long long *g_sink;
-static int g_sms;
 
 template <int V, int UNROLL>
 static double run(uint64_t n_units, int bps, int threads, uint32_t rounds, bool print = true) {
@@ -191,6 +234,10 @@ int main(int argc, char **argv) {
         run<V_LDG, 1>(u8, 1, 32, 256);
         run<V_LDG, 1>(u8, 1, 64, 256);
         run<V_LDG, 1>(u8, 1, 128, 256);
+    } else if (!strcmp(mode, "window")) {
+        for (double bin_mb : {8.0, 16.0, 32.0, 64.0})
+            for (int bps : {4, 8}) run_window(8.0, bin_mb, 0.57, bps);  // C2: 290M probes over 508M slots
+        run_window(4.0, 32.0, 4.7, 8);                                    // C3: 1.17G probes over 248M slots
     } else if (!strcmp(mode, "tma")) {
         run_tma<1, 16>(8000000000ull, 4, 256, 64);
         run_tma<4, 16>(8000000000ull, 4, 256, 32);
