@@ -326,10 +326,8 @@ def main():
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
     launches = guts.launch_count - launches0
-    phases, nb_prof, partitioned = guts.profile_read_phases()
+    probe_ms, scan_ms, nb_prof = guts.profile_read()
     guts.profile_enable(False)
-    phases = {k: v / max(nb_prof, 1) for k, v in phases.items()}
-    scan_ms = phases["scan"]
     n_probes, n_hits, n_calls = guts.read_totals()
 
     # ---- end to end through the C ABI with HOST buffers (H2D + kernels + D2H in the timed region)
@@ -359,20 +357,12 @@ def main():
         except OSError:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        # one 32 B sector per probe + 1 B per residue.  Direct path: one kernel (probe_kernel) does encode +
-        # probe + compaction.  Partitioned path: the probes are the part_probe_kernel launch (32 B x probes); the encode /
-        # partition / placement passes around it are reported as the path-level figure below.
-        path_ms = phases["count"] + phases["scatter"] + phases["probe"] + phases["place"]
-        probe_ms_avg = phases["probe"]
-        kernel_name = "part_probe_kernel" if partitioned else "probe_kernel"
-        alg_bytes = 32.0 * n_probes + (0.0 if partitioned else float(total))
+        alg_bytes = 32.0 * n_probes + float(total)  # one 32 B sector per probe + 1 B per residue
+        probe_ms_avg = probe_ms / max(nb_prof, 1)
         achieved = alg_bytes / (probe_ms_avg * 1e-3) / 1e9
-        path_bytes = 32.0 * n_probes + float(total)
-        path_achieved = path_bytes / (path_ms * 1e-3) / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(
-                args.workload + ("_partitioned" if partitioned else ""))
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload)
         except (OSError, ValueError):
             pass
         # independent random 16 B reads over the resident table: best of a few occupancies
@@ -384,21 +374,13 @@ def main():
             "dtype": "u64 keys / f32 scores", "data": "synthetic", "config": config,
             "probes_per_s": probes_all * K / (ms_total * 1e-3),
             "per_step": {"proteins": n, "residues": total, "probes": n_probes, "hits": n_hits, "calls": n_calls},
-            "kernels_ms": ({"part_encode_kernel<count>": phases["count"], "part_encode_kernel<scatter>": phases["scatter"],
-                            "part_probe_kernel": phases["probe"], "part_place_kernel": phases["place"],
-                            "scan_kernel<dense>": scan_ms} if partitioned else
-                           {"probe_kernel": probe_ms_avg, "scan_kernel": scan_ms}),
-            "probe_path": "partitioned (ckm_part.cuh)" if partitioned else "direct (ckm_probe.cuh)",
-            "roofline_path": {"what": "all kernels of the probe path before the ordered scan (encode + partition + probe + place, "
-                                      "or probe_kernel alone) against 32 B x probes + residues", "ms": path_ms,
-                              "achieved": path_achieved, "peak": peak, "unit": "GB/s", "frac": path_achieved / peak},
-            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "kernels_ms": {"probe_kernel": probe_ms_avg, "scan_kernel": scan_ms / max(nb_prof, 1)},
+            "roofline": {"bound": "hbm", "kernel": "probe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "gather_calibration": {"accesses_per_s": cal_rate, "as_32B_sectors_GBps": cal_rate * 32 / 1e9,
                                                 "probe_kernel_probes_per_s": n_probes / (probe_ms_avg * 1e-3),
-                                                "probe_path_probes_per_s": n_probes / (path_ms * 1e-3),
                                                 "note": "ceiling of independent random reads over this table on this GPU "
                                                         "(DESIGN.md section 6); probes/s / accesses_per_s = fraction of it"}},
             "e2e": {"value": prot_all * K / (ms_e2e * 1e-3), "unit": "proteins/s", "ms_per_step": ms_e2e / K,

@@ -140,7 +140,6 @@ def lib() -> C.CDLL:
     L.ckm_query_text.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int,
                                  C.POINTER(C.c_void_p)]
     L.ckm_free_text.argtypes = [C.c_void_p]
-    L.ckm_profile_read_phases.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
     L.ckm_image_build.argtypes = [C.c_uint64, C.c_uint64] + [C.c_void_p] * 6 + [C.c_size_t]
     L.ckm_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
     L.ckm_host_free.argtypes = [C.c_void_p]
@@ -313,13 +312,6 @@ class KmerGuts:
         r, ms = C.c_double(), C.c_double()
         _check(lib().ckm_calibrate_gather(self._h, nbytes, unroll, rounds, blocks_per_sm, C.byref(r), C.byref(ms)))
         return r.value, ms.value
-
-    def profile_read_phases(self):
-        """({count, scatter, probe, place, scan} ms summed, batches, partitioned?) since the last read."""
-        ph = (C.c_double * 5)()
-        n, part = C.c_uint64(), C.c_int()
-        _check(lib().ckm_profile_read_phases(self._h, ph, C.byref(n), C.byref(part)))
-        return dict(zip(("count", "scatter", "probe", "place", "scan"), list(ph))), n.value, bool(part.value)
 
     def set_tuning(self, bits: int):
         lib().ckm_set_tuning(self._h, bits)

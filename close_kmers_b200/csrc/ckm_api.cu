@@ -258,9 +258,6 @@ static int ctx_create(int device, ckm_ctx **out) {
     c->device = device;
     if (const char *pc = getenv("CKM_PIPELINE_CHUNK_KB")) c->pipeline_chunk_bytes = std::max<uint64_t>(1, (uint64_t)atol(pc)) << 10;
     if (const char *pm = getenv("CKM_PIPELINE_MIN_KB")) c->pipeline_min_bytes = (uint64_t)atol(pm) << 10;
-    if (const char *pmode = getenv("CKM_PARTITIONED")) c->part_mode = atoi(pmode);
-    if (const char *ts = getenv("CKM_PART_TSHIFT")) c->part_tshift = (uint32_t)atoi(ts);
-    if (const char *ds = getenv("CKM_PART_DSHIFT")) c->part_dshift = (uint32_t)atoi(ds);
     const char *fr = getenv("CKM_FORCE_RAW_SLOTS");
     c->force_raw = fr && fr[0] == '1';
     if (check_cuda(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
@@ -564,7 +561,7 @@ static int launch_range(ckm_ctx *c, cudaStream_t stream, const uint8_t *d_res, c
                                                                                 (unsigned long long *)c->totals.p);
         c->launches++;
     }
-    if (pe) CU(cudaEventRecord(pe->ev[1], stream));
+    if (pe) CU(cudaEventRecord(pe->e1, stream));
     if (plan.want_scan) {
         ScanArgs a;
         a.offsets = d_off + i0;
@@ -592,8 +589,6 @@ static int launch_range(ckm_ctx *c, cudaStream_t stream, const uint8_t *d_res, c
     return 0;
 }
 
-#include "ckm_part.cuh"
-
 // K1 + K2 over a batch that is already in HBM.  Leaves regions / per-protein counters on the device.
 static int run_device(ckm_ctx *c, const uint8_t *d_res, const uint64_t *d_off, uint32_t n, uint64_t total, uint32_t max_len,
                       uint32_t flags) {
@@ -602,17 +597,16 @@ static int run_device(ckm_ctx *c, const uint8_t *d_res, const uint64_t *d_off, u
     c->cur_off = d_off;
     CU(cudaMemsetAsync(c->totals.p, 0, 64, c->stream));
     if (n == 0) return 0;
-    if (use_partitioned(c, n, total, max_len, flags)) return run_partitioned(c, d_res, d_off, n, total, flags, plan);
-    ckm_ctx::ProfEv pe;
-    memset(&pe, 0, sizeof pe);
+    ckm_ctx::ProfEv pe = {nullptr, nullptr, nullptr, false};
     if (c->profiling) {
-        for (int k = 0; k < 3; k++) CU(cudaEventCreate(&pe.ev[k]));
-        CU(cudaEventRecord(pe.ev[0], c->stream));
+        CU(cudaEventCreate(&pe.e0));
+        CU(cudaEventCreate(&pe.e1));
+        CU(cudaEventCreate(&pe.e2));
+        CU(cudaEventRecord(pe.e0, c->stream));
     }
     RC(launch_range(c, c->stream, d_res, d_off, 0, n, flags, plan, c->profiling ? &pe : nullptr));
     if (c->profiling) {
-        CU(cudaEventRecord(pe.ev[2], c->stream));
-        pe.n_ev = 3;
+        CU(cudaEventRecord(pe.e2, c->stream));
         pe.has_scan = plan.want_scan;
         c->prof.push_back(pe);
     }
@@ -622,40 +616,23 @@ static int run_device(ckm_ctx *c, const uint8_t *d_res, const uint64_t *d_off, u
 
 extern "C" void ckm_profile_enable(ckm_ctx *c, int on) { c->profiling = on != 0; }
 
-// phases[]: direct path {0, 0, probe_kernel, 0, scan_kernel}; partitioned path {count, scatter, probe, place, scan}
-extern "C" int ckm_profile_read_phases(ckm_ctx *c, double phases[5], uint64_t *batches, int *partitioned) {
-    CU(cudaStreamSynchronize(c->stream));
-    double ph[5] = {0, 0, 0, 0, 0};
-    int part = 0;
-    for (auto &e : c->prof) {
-        float t = 0;
-        if (e.n_ev == 6) {
-            part = 1;
-            for (int k = 0; k < 5; k++) {
-                CU(cudaEventElapsedTime(&t, e.ev[k], e.ev[k + 1]));
-                ph[k] += t;
-            }
-        } else {
-            CU(cudaEventElapsedTime(&t, e.ev[0], e.ev[1]));
-            ph[2] += t;
-            CU(cudaEventElapsedTime(&t, e.ev[1], e.ev[2]));
-            if (e.has_scan) ph[4] += t;
-        }
-        for (int k = 0; k < e.n_ev; k++) cudaEventDestroy(e.ev[k]);
-    }
-    for (int k = 0; k < 5; k++) phases[k] = ph[k];
-    if (batches) *batches = c->prof.size();
-    if (partitioned) *partitioned = part;
-    c->prof.clear();
-    return 0;
-}
-
-// probe_ms = everything before the ordered scan (K1, or count + scatter + probe + place), scan_ms = the scan kernel
 extern "C" int ckm_profile_read(ckm_ctx *c, double *probe_ms, double *scan_ms, uint64_t *batches) {
-    double ph[5];
-    RC(ckm_profile_read_phases(c, ph, batches, nullptr));
-    if (probe_ms) *probe_ms = ph[0] + ph[1] + ph[2] + ph[3];
-    if (scan_ms) *scan_ms = ph[4];
+    CU(cudaStreamSynchronize(c->stream));
+    double p = 0, s = 0;
+    for (auto &e : c->prof) {
+        float a = 0, b = 0;
+        CU(cudaEventElapsedTime(&a, e.e0, e.e1));
+        CU(cudaEventElapsedTime(&b, e.e1, e.e2));
+        p += a;
+        if (e.has_scan) s += b;
+        cudaEventDestroy(e.e0);
+        cudaEventDestroy(e.e1);
+        cudaEventDestroy(e.e2);
+    }
+    if (probe_ms) *probe_ms = p;
+    if (scan_ms) *scan_ms = s;
+    if (batches) *batches = c->prof.size();
+    c->prof.clear();
     return 0;
 }
 

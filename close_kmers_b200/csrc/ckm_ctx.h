@@ -45,8 +45,7 @@ struct ckm_ctx {
 
     // optional per-kernel timing (ckm_profile_*): events bracketing K1 and K2 of every batch
     bool profiling = false;
-    // direct path: ev[0..2] = start, after K1, after K2; partitioned path: ev[0..5] = start, count, scatter, probe, place, scan
-    struct ProfEv { cudaEvent_t ev[6]; int n_ev; bool has_scan; };
+    struct ProfEv { cudaEvent_t e0, e1, e2; bool has_scan; };
     std::vector<ProfEv> prof;
 
     // current batch
@@ -68,13 +67,6 @@ struct ckm_ctx {
         DevBuf hit_fam, E, gcap, gofs, gscratch, matches;  // per-batch work buffers
     } fam;
     PinBuf h_fam;
-
-    // partitioned probe path (ckm_part.cuh)
-    int part_mode = 2;  // 0 off, 1 forced whenever applicable, 2 auto
-    uint32_t part_tshift = 0, part_dshift = 0;  // test overrides of the bin geometry
-    struct Part {
-        DevBuf hist, tbase, tcursor, recs, dbase, dcursor, counter, dense8, valid;
-    } part;
 
     // /add postings + /matrix (ckm_matrix.cuh)
     struct Post {
@@ -104,9 +96,6 @@ struct ckm_ctx {
         DevBuf *f[] = {&fam.table, &fam.ids, &fam.fam_func, &fam.fam_pgf, &fam.func_sid, &fam.hit_fam, &fam.E, &fam.gcap,
                        &fam.gofs, &fam.gscratch, &fam.matches};
         for (auto b : f) b->release();
-        DevBuf *pa[] = {&part.hist, &part.tbase, &part.tcursor, &part.recs, &part.dbase, &part.dcursor, &part.counter,
-                        &part.dense8, &part.valid};
-        for (auto b : pa) b->release();
         DevBuf *pp[] = {&post.keys, &post.eids, &post.tkeys, &post.tcnt, &post.tcur, &post.toff, &post.slots, &post.ids,
                         &post.d_eids, &post.d_first, &post.rcap, &post.rofs, &post.nd, &post.out_off, &post.entries, &post.out};
         for (auto b : pp) b->release();

@@ -189,8 +189,6 @@ struct ScanArgs {
     uint32_t *n_otus;
     ckm_best_t *best;          // null unless wanted
     unsigned long long *totals;  // [2] += calls
-    const uint32_t *valid;     // DENSE source (partitioned probe path): bit (global residue index) = a hit starts there
-    const uint2 *dense8;       // DENSE source: {function_index, function_wt bits} per global residue index
     uint32_t n;
     uint32_t index_base;       // batch index of sequence 0 of this launch (chunked launches share the call regions)
     Params prm;
@@ -198,9 +196,7 @@ struct ScanArgs {
 
 // GENERAL = order_constraint != 0 or a protein long enough to saturate the 39998-hit window: then the
 // stored hits are a strict subsequence of the hit list and their indices are kept in stored_idx.
-// DENSE = the hits come position-indexed (validity bitmap + 8-byte payload per residue index) from the partitioned
-// probe path instead of as a compacted list; only used with order_constraint off and no window saturation.
-template <bool GENERAL, bool DENSE = false>
+template <bool GENERAL>
 __global__ void __launch_bounds__(kScanThreads) scan_kernel(ScanArgs a) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
@@ -208,7 +204,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(ScanArgs a) {
     const HitRec *H = a.hits + base;
     const uint16_t *A = a.hit_avg ? a.hit_avg + base : nullptr;
     uint32_t *S = GENERAL ? a.stored_idx + base : nullptr;
-    const uint32_t nh = DENSE ? 0u : a.n_hits[i];
+    const uint32_t nh = a.n_hits[i];
     ckm_call_t *calls = a.calls + call_region_base(base, a.index_base + i, a.prm.min_hits);
     ckm_otu_t *otus = a.otus ? a.otus + base : nullptr;
     const int min_hits = a.prm.min_hits;
@@ -311,7 +307,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(ScanArgs a) {
             if (num > 1 && cur_fI != h.fI && p2_fI == p1_fI) flush();
         }
     };
-    for (uint32_t k0 = 0; !DENSE && k0 < nh; k0 += kScanBatch) {
+    for (uint32_t k0 = 0; k0 < nh; k0 += kScanBatch) {
         HitRec hb[kScanBatch];
         uint32_t ab[kScanBatch];
 #pragma unroll
@@ -324,46 +320,6 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(ScanArgs a) {
 #pragma unroll
         for (int u = 0; u < kScanBatch; u++)
             if (k0 + u < nh) step(hb[u], k0 + u, ab[u]);
-    }
-    if (DENSE) {
-        const uint64_t end = a.offsets[i + 1];
-        uint32_t k = 0;
-        const uint64_t w0 = base >> 5, w1 = (end + 31) >> 5;
-        uint32_t next_word = w0 < w1 ? a.valid[w0] : 0u;
-        for (uint64_t w = w0; w < w1; w++) {
-            uint32_t word = next_word;
-            if (w + 1 < w1) next_word = a.valid[w + 1];
-            if (w == w0) word &= 0xffffffffu << (base & 31u);
-            if (((w + 1) << 5) > end) word &= (1u << (end & 31u)) - 1u;  // end & 31 != 0 here
-            const uint32_t rel = (uint32_t)((w << 5) - base);  // mod 2^32; rel + bit index is the position in the protein
-            while (word) {
-                uint32_t p[kScanBatch];
-                uint2 d[kScanBatch];
-                int c = 0;
-#pragma unroll
-                for (int u = 0; u < kScanBatch; u++) {
-                    if (word) {
-                        p[u] = (uint32_t)(__ffs(word) - 1);
-                        word &= word - 1;
-                        c = u + 1;
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < kScanBatch; u++)
-                    if (u < c) d[u] = a.dense8[(w << 5) + p[u]];
-#pragma unroll
-                for (int u = 0; u < kScanBatch; u++) {
-                    if (u < c) {
-                        HitRec h;
-                        h.pos = rel + p[u];
-                        h.fI = d[u].x;
-                        h.wt = __uint_as_float(d[u].y);
-                        h.oI = 0;
-                        step(h, k++, 0u);
-                    }
-                }
-            }
-        }
     }
     if ((int)num >= min_hits) flush();  // 873-876
 

@@ -313,9 +313,6 @@ int ckm_synchronize(ckm_ctx *ctx);
  * returns the summed durations (ms) and the number of batches since the last read, and resets. */
 void ckm_profile_enable(ckm_ctx *ctx, int on);
 int ckm_profile_read(ckm_ctx *ctx, double *probe_ms, double *scan_ms, uint64_t *batches);
-/* per-phase form: phases = {count, scatter, probe, place, scan} ms for the partitioned probe path (batches dense enough
- * in a table larger than L2; CKM_PARTITIONED=0/1 overrides), {0, 0, probe_kernel, 0, scan_kernel} for the direct path */
-int ckm_profile_read_phases(ckm_ctx *ctx, double phases[5], uint64_t *batches, int *partitioned);
 
 #ifdef __cplusplus
 }

@@ -80,38 +80,6 @@ def test_occupancy_bitmap_and_pipelined_host_path(checkers, world):
             os.environ.pop(k, None)
 
 
-@pytest.mark.parametrize("shifts", [(10, 12), (13, 9), (0, 0)])
-def test_partitioned_probe_path(checkers, world, shifts):
-    """The radix-partitioned probe path (ckm_part.cuh), forced on a small table with tiny bins so that probe records
-    and hits cross many table / position bins and every write-combining line is flushed many times."""
-    protos, sig, img, orc, _, _ = world
-    os.environ.update(CKM_PARTITIONED="1", CKM_PART_TSHIFT=str(shifts[0]), CKM_PART_DSHIFT=str(shifts[1]))
-    try:
-        g = api.KmerGuts(image=img, function_names=synth.function_names(sig.n_functions))
-    finally:
-        for k in ("CKM_PARTITIONED", "CKM_PART_TSHIFT", "CKM_PART_DSHIFT"):
-            os.environ.pop(k, None)
-    # many copies of one protein: thousands of records for the same few table bins (contended staging lines)
-    hot = synth.batch_from_strings([synth.AA[protos.codes[:300]].tobytes()] * 600 + [b"A" * 500] * 50)
-    batch = wl.concat_batches(wl.concat_batches(wl.edge_batch(protos), synth.make_proteins(8, protos, 5000)), hot)
-    for prm in (dict(), dict(min_hits=2, max_gap=30), dict(min_hits=3, min_weighted_hits=15)):
-        orc.set_params(**prm)
-        g.set_parameters(prm)
-        want = orc.call_batch(batch, api.WANT_CALLS | api.WANT_BEST)
-        g.profile_enable(True)
-        for flags in (api.WANT_BEST, api.WANT_CALLS, api.WANT_CALLS | api.WANT_BEST):
-            got = g.process_aa_seq_batch(batch.residues, batch.offsets, flags)
-            wl.assert_results_equal(got, {k: v for k, v in want.items() if k in got}, f"partitioned {shifts} {prm} flags={flags}")
-            assert got["n_probes"] == want["n_probes"] and got["n_hits"] == orc.call_batch(batch, api.WANT_HITS)["n_hits"]
-        _, nb, part = g.profile_read_phases()
-        g.profile_enable(False)
-        assert part and nb == 3, "the partitioned path did not run"
-    # paths that need hit lists or OTU stats fall back to the direct kernels on the same ctx
-    want = orc.call_batch(batch, ALL)
-    wl.assert_results_equal(g.process_aa_seq_batch(batch.residues, batch.offsets, ALL), want, "direct path on a partitioned ctx")
-    g.close()
-
-
 def test_each_flag_alone(checkers, world):
     """The handlers pass different subsets of (calls, hit_cb, otu_stats): every subset must agree."""
     protos, _, _, orc, guts, _ = world

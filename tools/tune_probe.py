@@ -21,22 +21,22 @@ max_len = int(np.diff(batch.offsets.astype(np.int64)).max())
 d_res = torch.zeros(total + 64, dtype=torch.uint8, device="cuda")
 d_res[:total] = torch.from_numpy(batch.residues).cuda()
 d_off = torch.from_numpy(batch.offsets.astype(np.int64)).cuda()
-for mode, ts in (("2", "0"), ("2", "20"), ("2", "22"), ("0", "0")):
-    os.environ["CKM_PARTITIONED"] = mode
-    os.environ["CKM_PART_TSHIFT"] = ts
-    g = api.KmerGuts(image=img)
-    g.profile_enable(True)
-    for _ in range(3):
-        g.call_batch_device(d_res.data_ptr(), d_off.data_ptr(), batch.n, total, max_len, api.WANT_BEST)
-    g.profile_read_phases()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(5):
-        g.call_batch_device(d_res.data_ptr(), d_off.data_ptr(), batch.n, total, max_len, api.WANT_BEST)
-    g.synchronize()
-    wall = (time.perf_counter() - t0) / 5
-    ph, nb, part = g.profile_read_phases()
-    probes = g.read_totals()[0]
-    print(json.dumps(dict(partitioned=part, tshift=ts, wall_ms=wall * 1e3, phases_ms={k: v / nb for k, v in ph.items()},
-                          total_ms=sum(ph.values()) / nb, probes=probes)), flush=True)
-    g.close()
+for bitmap in ("1", "0"):
+    os.environ["CKM_OCCUPANCY_BITMAP"] = bitmap
+    for persist in ("0",):
+        g = api.KmerGuts(image=img)
+        for tuning in (0, 16):
+            if bitmap == "0" and (tuning & 2):
+                continue
+            g.set_tuning(tuning)
+            g.profile_enable(True)
+            for _ in range(3):
+                g.call_batch_device(d_res.data_ptr(), d_off.data_ptr(), batch.n, total, max_len, api.WANT_BEST)
+            g.profile_read()
+            for _ in range(5):
+                g.call_batch_device(d_res.data_ptr(), d_off.data_ptr(), batch.n, total, max_len, api.WANT_BEST)
+            p, s, nb = g.profile_read()
+            probes = g.read_totals()[0]
+            print(json.dumps(dict(bitmap=bitmap, no_persist=persist, tuning=tuning, probe_ms=p / nb, scan_ms=s / nb,
+                                  gprobes_per_s=probes / (p / nb) / 1e6)), flush=True)
+        g.close()
