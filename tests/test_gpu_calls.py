@@ -179,3 +179,42 @@ def test_window_saturation_long_protein(checkers):
         os.environ.pop("CKM_PIPELINE_CHUNK_KB")
     guts.close()
     orc.close()
+
+
+def test_randomised_parameters_and_shapes(checkers, world):
+    """Seeded random sweeps over engine parameters, flag subsets and batch shapes (many tiny sequences, a few very
+    long ones, high-bit bytes, runs of one residue), each against the oracle."""
+    protos, sig, img, orc, guts, guts_raw = world
+    rng = np.random.default_rng(2024)
+    aa = synth.AA
+    for trial in range(12):
+        seqs = []
+        for _ in range(int(rng.integers(1, 400))):
+            kind = int(rng.integers(0, 7))
+            p = int(rng.integers(0, protos.n))
+            s = aa[protos.codes[int(protos.offsets[p]):int(protos.offsets[p + 1])]].copy()
+            if kind == 0:
+                s = s[: int(rng.integers(0, 30))]
+            elif kind == 1:  # several prototypes glued: long, many runs
+                parts = [aa[protos.codes[int(protos.offsets[q]):int(protos.offsets[q + 1])]] for q in rng.integers(0, protos.n, int(rng.integers(2, 30)))]
+                s = np.concatenate(parts)
+            elif kind == 2:
+                s[rng.integers(0, len(s), int(rng.integers(1, 40)))] = rng.integers(0, 256, 1, dtype=np.uint8)[0] or 1
+            elif kind == 3:
+                s = np.full(int(rng.integers(1, 300)), aa[int(rng.integers(0, 20))], np.uint8)
+            elif kind == 4:
+                s = s[int(rng.integers(0, 200)):]
+            elif kind == 5:
+                s = np.concatenate([s[:100], s[:100], s[50:150]])
+            seqs.append(s.tobytes())
+        batch = synth.batch_from_strings(seqs)
+        prm = dict(order_constraint=int(rng.integers(0, 2)), min_hits=int(rng.integers(1, 9)),
+                   min_weighted_hits=int(rng.integers(0, 30)), max_gap=int(rng.choice([0, 1, 7, 50, 200, 100000])))
+        flags = int(rng.integers(1, 16))
+        orc.set_params(**prm)
+        want = orc.call_batch(batch, flags)
+        for g in (guts, guts_raw):
+            g.set_parameters(prm)
+            wl.assert_results_equal(g.process_aa_seq_batch(batch.residues, batch.offsets, flags), want, f"trial {trial} {prm} flags={flags}")
+    guts.set_default_parameters()
+    guts_raw.set_default_parameters()
