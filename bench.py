@@ -136,6 +136,21 @@ def cpu_threads():
         return os.cpu_count() or 1
 
 
+class stdout_to_stderr:
+    """The reference's own code prints to stdout (kmer_image.cc:44, kmer.cc:46); bench.py's stdout carries exactly one
+    JSON line, so the CPU arm runs with file descriptor 1 pointed at stderr."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 class CpuEngine:
     """The reference's CPU path for this workload: oracle/_ref (the reference's own object code, one KmerGuts
     per thread sharing one mmapped image, like threadpool.cc:18-45) when present, else the plain-C port."""
@@ -212,13 +227,14 @@ def main():
             synth.write_index_files(kdir, sig.n_functions, 0)
         T = cpu_threads()
         try:
-            eng = CpuEngine(kdir, img, T)
-            vals = []
-            for s in range(W + K):
-                r = eng.sample(batch, target_s=max(1.0, 40.0 / (W + K)))
-                if s >= W:
-                    vals.append(r)
-            eng.close()
+            with stdout_to_stderr():
+                eng = CpuEngine(kdir, img, T)
+                vals = []
+                for s in range(W + K):
+                    r = eng.sample(batch, target_s=max(1.0, 40.0 / (W + K)))
+                    if s >= W:
+                        vals.append(r)
+                eng.close()
         finally:
             if kdir:
                 shutil.rmtree(kdir, ignore_errors=True)
@@ -391,9 +407,10 @@ def main():
                       "occupancy_bitmap": guts.has_occupancy_bitmap},
         }
         if not args.no_cpu_baseline and world == 1:
-            eng = CpuEngine(kdir, img, cpu_threads())
-            cb = eng.sample(batch, target_s=8.0)
-            eng.close()
+            with stdout_to_stderr():
+                eng = CpuEngine(kdir, img, cpu_threads())
+                cb = eng.sample(batch, target_s=8.0)
+                eng.close()
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "probes_per_s")}
         print(json.dumps(line), flush=True)
     barrier()
