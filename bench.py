@@ -192,7 +192,26 @@ class CpuEngine:
         self.eng.close()
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """bench.py's stdout carries exactly ONE JSON line.  Libraries print there too (NCCL's version banner, the
+    reference's own std::cout lines), so file descriptor 1 is pointed at stderr for the whole run and the JSON line is
+    written to a private duplicate of the original stdout."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -246,7 +265,7 @@ def main():
                 "cpu_baseline": {k: vals[-1][k] for k in ("value", "unit", "cores", "kind", "sample")} | {"value": v},
                 "e2e": {"value": v, "unit": "proteins/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ our arm
@@ -412,7 +431,7 @@ def main():
                 cb = eng.sample(batch, target_s=8.0)
                 eng.close()
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "probes_per_s")}
-        print(json.dumps(line), flush=True)
+        emit(line)
     barrier()
     guts.close()
     L.ckm_host_free(hp_res)

@@ -20,10 +20,17 @@ namespace ckm {
 
 constexpr uint32_t kFamSmemCap = 1024;  // slots of the per-warp shared-memory maps
 constexpr uint32_t kFamSmemE = 512;     // use them when the protein has at most this many list entries (cap = 2E)
-constexpr int kFamWarps = 4;            // warps per block of fam_vote_kernel
 constexpr int kFamStage = 8;            // list entries prefetched per hit
-constexpr uint32_t kFamWarpWords = 5 * kFamSmemCap + 32 * kFamStage;
-constexpr size_t kFamVoteSmem = (size_t)kFamWarps * kFamWarpWords * 4;
+// Two instantiations of fam_vote_kernel share one batch: SMALL (maps of <= kFamSmallCap slots, 8 warps per block, 8
+// blocks per SM) takes the proteins whose map fits -- every fastq fragment does -- and LARGE (1024-slot maps, 4 warps per
+// block, 2 blocks per SM) takes the rest, including those whose maps live in global scratch.
+constexpr uint32_t kFamSmallCap = 128;
+template <uint32_t CAP>
+struct FamVoteCfg {
+    static constexpr int kWarps = CAP <= kFamSmallCap ? 8 : 4;
+    static constexpr uint32_t kWarpWords = 5 * CAP + 32 * kFamStage;
+    static constexpr size_t kSmem = (size_t)kWarps * kWarpWords * 4;
+};
 
 struct FamSlot {
     uint64_t key1;  // k-mer + 1, 0 = empty
@@ -108,30 +115,32 @@ __device__ __forceinline__ uint32_t map_slot(uint32_t *keys, uint32_t mask, uint
     }
 }
 
-__global__ void __launch_bounds__(kFamWarps * 32)
+template <uint32_t CAP>
+__global__ void __launch_bounds__(FamVoteCfg<CAP>::kWarps * 32)
 fam_vote_kernel(FamTables ft, const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ n_hits,
                 const uint2 *__restrict__ hit_fam, const uint32_t *__restrict__ E, const uint32_t *__restrict__ gcap,
                 const uint64_t *__restrict__ gofs, uint32_t *__restrict__ gscratch, const ckm_best_t *__restrict__ best,
                 uint32_t n, ckm_family_match_t *__restrict__ out) {
-    extern __shared__ __align__(16) uint32_t fam_smem[];  // kFamVoteSmem bytes, carved per warp below
+    extern __shared__ __align__(16) uint32_t fam_smem[];  // FamVoteCfg<CAP>::kSmem bytes, carved per warp below
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
-    uint32_t *const my_smem = fam_smem + (size_t)wib * kFamWarpWords;
-    uint32_t *const s_keys = my_smem, *const s_cnt = my_smem + kFamSmemCap;
-    float *const s_w = reinterpret_cast<float *>(my_smem + 2 * kFamSmemCap);
-    uint32_t *const s_pkeys = my_smem + 3 * kFamSmemCap;
-    float *const s_pw = reinterpret_cast<float *>(my_smem + 4 * kFamSmemCap);
-    uint32_t(*const s_stage)[kFamStage] = reinterpret_cast<uint32_t(*)[kFamStage]>(my_smem + 5 * kFamSmemCap);
+    uint32_t *const my_smem = fam_smem + (size_t)wib * FamVoteCfg<CAP>::kWarpWords;
+    uint32_t *const s_keys = my_smem, *const s_cnt = my_smem + CAP;
+    float *const s_w = reinterpret_cast<float *>(my_smem + 2 * CAP);
+    uint32_t *const s_pkeys = my_smem + 3 * CAP;
+    float *const s_pw = reinterpret_cast<float *>(my_smem + 4 * CAP);
+    uint32_t(*const s_stage)[kFamStage] = reinterpret_cast<uint32_t(*)[kFamStage]>(my_smem + 5 * CAP);
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t i = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < n; i += n_warps) {
-        const uint64_t base = offsets[i];
-        const uint32_t nh = n_hits[i];
         uint32_t *keys, *cnt, *pkeys, cap;
         float *wsum, *pw;
+        // shared-memory maps sized to the protein: at most E distinct families, kept at most half full
+        cap = 32u;
+        while (cap < 2u * E[i]) cap <<= 1;
+        const bool small = gcap[i] == 0 && cap <= kFamSmallCap;
+        if (small != (CAP <= kFamSmallCap)) continue;  // the other instantiation's protein
+        const uint64_t base = offsets[i];
+        const uint32_t nh = n_hits[i];
         if (gcap[i] == 0) {
-            // shared-memory maps sized to the protein: at most E distinct families, kept at most half full, so short
-            // fragments (the fastq path: a few dozen list entries) clear and scan 32-64 slots instead of 1024
-            cap = 32u;
-            while (cap < 2u * E[i]) cap <<= 1;
             keys = s_keys; cnt = s_cnt; wsum = s_w; pkeys = s_pkeys; pw = s_pw;
             for (uint32_t s = lane; s < cap; s += 32) { keys[s] = 0u; pkeys[s] = 0u; }
         } else {  // global scratch: 5 arrays of `cap` words, keys pre-zeroed by the host-side memset
@@ -389,13 +398,20 @@ static int family_device(ckm_ctx *c, const uint64_t *d_off, uint32_t n, uint64_t
         RC(F.gscratch.ensure(gtotal * 5 * 4));
         CU(cudaMemsetAsync(F.gscratch.p, 0, gtotal * 5 * 4, c->stream));
     }
-    const unsigned vb = std::min<uint64_t>(((uint64_t)n + kFamWarps - 1) / kFamWarps, (uint64_t)c->sm_count * 8);
-    CU(cudaFuncSetAttribute(fam_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFamVoteSmem));
-    fam_vote_kernel<<<vb, kFamWarps * 32, kFamVoteSmem, c->stream>>>(ft, d_off, (const uint32_t *)c->n_hits.p, (const uint2 *)F.hit_fam.p,
-                                                         (const uint32_t *)F.E.p, (const uint32_t *)F.gcap.p,
-                                                         (const uint64_t *)F.gofs.p, (uint32_t *)F.gscratch.p,
-                                                         (const ckm_best_t *)c->best.p, n, (ckm_family_match_t *)F.matches.p);
-    c->launches++;
+    {
+        typedef FamVoteCfg<kFamSmallCap> S;
+        typedef FamVoteCfg<kFamSmemCap> L;
+        CU(cudaFuncSetAttribute(fam_vote_kernel<kFamSmemCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kSmem));
+        const unsigned sb = (unsigned)std::min<uint64_t>(((uint64_t)n + S::kWarps - 1) / S::kWarps, (uint64_t)c->sm_count * 32);
+        const unsigned lb2 = (unsigned)std::min<uint64_t>(((uint64_t)n + L::kWarps - 1) / L::kWarps, (uint64_t)c->sm_count * 8);
+        fam_vote_kernel<kFamSmallCap><<<sb, S::kWarps * 32, S::kSmem, c->stream>>>(
+            ft, d_off, (const uint32_t *)c->n_hits.p, (const uint2 *)F.hit_fam.p, (const uint32_t *)F.E.p, (const uint32_t *)F.gcap.p,
+            (const uint64_t *)F.gofs.p, (uint32_t *)F.gscratch.p, (const ckm_best_t *)c->best.p, n, (ckm_family_match_t *)F.matches.p);
+        fam_vote_kernel<kFamSmemCap><<<lb2, L::kWarps * 32, L::kSmem, c->stream>>>(
+            ft, d_off, (const uint32_t *)c->n_hits.p, (const uint2 *)F.hit_fam.p, (const uint32_t *)F.E.p, (const uint32_t *)F.gcap.p,
+            (const uint64_t *)F.gofs.p, (uint32_t *)F.gscratch.p, (const ckm_best_t *)c->best.p, n, (ckm_family_match_t *)F.matches.p);
+        c->launches += 2;
+    }
     CU(cudaGetLastError());
     return 0;
 }

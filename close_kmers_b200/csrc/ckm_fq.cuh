@@ -48,6 +48,9 @@ __device__ __forceinline__ char frame_aa(const uint8_t *read, uint32_t len, uint
     return tbl[(c0 < 4u && c1 < 4u && c2 < 4u) ? c0 * 16u + c1 * 4u + c2 : 64u];
 }
 
+constexpr uint32_t kFqReadsPerBlock = 42;   // 252 of the block's 256 threads
+constexpr uint32_t kFqStageBytes = 12 * 1024;
+
 template <bool FILL>
 __global__ void __launch_bounds__(256)
 fq_frames_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ offsets, uint32_t n, uint32_t min_len,
@@ -55,14 +58,28 @@ fq_frames_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__
                  const uint64_t *__restrict__ frag_base, const uint64_t *__restrict__ res_base,  // fill pass inputs
                  uint64_t *__restrict__ frag_off, uint8_t *__restrict__ frag_res) {
     __shared__ char tbl[65];
+    __shared__ __align__(16) uint8_t s_bases[kFqStageBytes + 16];
     fill_aa11(tbl);
+    // the block's reads (kFqReadsPerBlock consecutive ones, six threads each) are staged in shared memory with
+    // coalesced word loads when they fit; every base is then read six times (once per frame) from there
+    const uint32_t r0 = blockIdx.x * kFqReadsPerBlock;
+    const uint32_t r1 = min(n, r0 + kFqReadsPerBlock);
+    const uint64_t blk0 = r0 < n ? offsets[r0] : 0, blk1 = r0 < n ? offsets[r1] : 0;
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(bases + blk0) & 3u);
+    const bool staged = (blk1 - blk0) + mis <= kFqStageBytes;
+    if (staged) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(bases + blk0 - mis);
+        const uint32_t words = (uint32_t)((blk1 - blk0) + mis + 3u) >> 2;
+        for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) reinterpret_cast<uint32_t *>(s_bases)[w] = __ldg(src + w);
+    }
     __syncthreads();
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 6ull * n) return;
-    const uint32_t r = (uint32_t)(t / 6u), slot = (uint32_t)(t % 6u);
+    if (threadIdx.x >= 6u * kFqReadsPerBlock) return;
+    const uint32_t r = r0 + threadIdx.x / 6u, slot = threadIdx.x % 6u;
+    if (r >= n) return;
+    const uint64_t t = 6ull * r + slot;
     const uint64_t b0 = offsets[r];
     const uint32_t len = (uint32_t)(offsets[r + 1] - b0);
-    const uint8_t *read = bases + b0;
+    const uint8_t *read = staged ? s_bases + mis + (b0 - blk0) : bases + b0;
     const uint32_t skip = slot % 3u;
     const uint32_t ncod = len >= skip + 3u ? (len - skip) / 3u : 0u;  // complete codons only (trans_table.cc:70-81)
     uint32_t cnt = 0, aa_total = 0, run = 0;
@@ -148,7 +165,7 @@ static int fq_translate_device(ckm_ctx *c, const char *bases, const uint64_t *of
     RC(Q.res_base.ensure((nt + 2) * 8));
     uint64_t n_frags = 0, n_aa = 0;
     if (n) {
-        const unsigned blocks = (unsigned)((nt + 255) / 256);
+        const unsigned blocks = (n + ckm::kFqReadsPerBlock - 1) / ckm::kFqReadsPerBlock;
         fq_frames_kernel<false><<<blocks, 256, 0, c->stream>>>((const uint8_t *)c->in_res.p, (const uint64_t *)c->in_off.p, n,
                                                               min_len, (uint32_t *)Q.nfrag.p, (uint32_t *)Q.naa.p, nullptr,
                                                               nullptr, nullptr, nullptr);
@@ -164,7 +181,7 @@ static int fq_translate_device(ckm_ctx *c, const char *bases, const uint64_t *of
     RC(Q.frag_off.ensure((n_frags + 2) * 8));
     RC(Q.frag_res.ensure(n_aa + 64));
     if (n) {
-        const unsigned blocks = (unsigned)((nt + 255) / 256);
+        const unsigned blocks = (n + ckm::kFqReadsPerBlock - 1) / ckm::kFqReadsPerBlock;
         fq_frames_kernel<true><<<blocks, 256, 0, c->stream>>>((const uint8_t *)c->in_res.p, (const uint64_t *)c->in_off.p, n,
                                                              min_len, nullptr, nullptr, (const uint64_t *)Q.frag_base.p,
                                                              (const uint64_t *)Q.res_base.p, (uint64_t *)Q.frag_off.p,
