@@ -21,10 +21,10 @@ namespace ckm {
 constexpr uint32_t kFamSmemCap = 1024;  // slots of the per-warp shared-memory maps
 constexpr uint32_t kFamSmemE = 512;     // use them when the protein has at most this many list entries (cap = 2E)
 constexpr int kFamStage = 8;            // list entries prefetched per hit
-// Two instantiations of fam_vote_kernel share one batch: SMALL (maps of <= kFamSmallCap slots, 8 warps per block, 8
+// Two instantiations of fam_vote_kernel share one batch: SMALL (maps of <= kFamSmallCap slots, 8 warps per block, 4
 // blocks per SM) takes the proteins whose map fits -- every fastq fragment does -- and LARGE (1024-slot maps, 4 warps per
 // block, 2 blocks per SM) takes the rest, including those whose maps live in global scratch.
-constexpr uint32_t kFamSmallCap = 128;
+constexpr uint32_t kFamSmallCap = 256;
 template <uint32_t CAP>
 struct FamVoteCfg {
     static constexpr int kWarps = CAP <= kFamSmallCap ? 8 : 4;
@@ -402,6 +402,7 @@ static int family_device(ckm_ctx *c, const uint64_t *d_off, uint32_t n, uint64_t
         typedef FamVoteCfg<kFamSmallCap> S;
         typedef FamVoteCfg<kFamSmemCap> L;
         CU(cudaFuncSetAttribute(fam_vote_kernel<kFamSmemCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kSmem));
+        CU(cudaFuncSetAttribute(fam_vote_kernel<kFamSmallCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kSmem));
         const unsigned sb = (unsigned)std::min<uint64_t>(((uint64_t)n + S::kWarps - 1) / S::kWarps, (uint64_t)c->sm_count * 32);
         const unsigned lb2 = (unsigned)std::min<uint64_t>(((uint64_t)n + L::kWarps - 1) / L::kWarps, (uint64_t)c->sm_count * 8);
         fam_vote_kernel<kFamSmallCap><<<sb, S::kWarps * 32, S::kSmem, c->stream>>>(
