@@ -257,6 +257,8 @@ static int ctx_create(int device, ckm_ctx **out) {
     ckm_ctx *c = new ckm_ctx();
     c->device = device;
     if (const char *pc = getenv("CKM_PIPELINE_CHUNK_KB")) c->pipeline_chunk_bytes = std::max<uint64_t>(1, (uint64_t)atol(pc)) << 10;
+    if (const char *pr = getenv("CKM_PIPELINE_RAMP_DIV")) c->pipeline_ramp_div = std::max(1, atoi(pr));
+    if (const char *pt = getenv("CKM_PIPELINE_TAIL_DIV")) c->pipeline_tail_div = std::max(1, atoi(pt));
     if (const char *pm = getenv("CKM_PIPELINE_MIN_KB")) c->pipeline_min_bytes = (uint64_t)atol(pm) << 10;
     const char *fr = getenv("CKM_FORCE_RAW_SLOTS");
     c->force_raw = fr && fr[0] == '1';
@@ -728,8 +730,8 @@ static int call_batch_pipelined(ckm_ctx *c, const char *residues, const uint64_t
     }
     // chunk schedule: ramp up from 1/6 of the chunk size so the first kernels start early, and end on a short chunk
     // so little compute is left once the last copy lands
-    const uint64_t cap = std::max<uint64_t>(c->pipeline_chunk_bytes, 1024), tail = cap / 4;
-    uint64_t want = std::max<uint64_t>(cap / 6, 1024);
+    const uint64_t cap = std::max<uint64_t>(c->pipeline_chunk_bytes, 1024), tail = cap / c->pipeline_tail_div;
+    uint64_t want = std::max<uint64_t>(cap / c->pipeline_ramp_div, 1024);
     uint32_t i0 = 0;
     int k = 0;
     while (i0 < n) {

@@ -25,15 +25,17 @@ C.memmove(hp_off.value, batch.offsets.ctypes.data, (batch.n + 1) * 8)
 import torch
 props = torch.cuda.get_device_properties(0)
 print(json.dumps(dict(l2=props.L2_cache_size)), flush=True)
-for chunk_kb in (24576, 49152, 98304):
+for chunk_kb, ramp, tail in ((98304, 6, 4), (98304, 24, 8), (98304, 12, 8), (65536, 16, 8), (131072, 32, 8), (98304, 24, 16)):
     os.environ["CKM_PIPELINE_CHUNK_KB"] = str(chunk_kb)
+    os.environ["CKM_PIPELINE_RAMP_DIV"] = str(ramp)
+    os.environ["CKM_PIPELINE_TAIL_DIV"] = str(tail)
     g = api.KmerGuts(image=img)
     for _ in range(2):
         g.call_batch_raw(hp_res.value, hp_off.value, batch.n, api.WANT_BEST)
     t0 = time.perf_counter()
-    K = 5
+    K = 8
     for _ in range(K):
         g.call_batch_raw(hp_res.value, hp_off.value, batch.n, api.WANT_BEST)
     dt = (time.perf_counter() - t0) / K
-    print(json.dumps(dict(chunk_kb=chunk_kb, e2e_ms=dt * 1e3, proteins_per_s=batch.n / dt)), flush=True)
+    print(json.dumps(dict(chunk_kb=chunk_kb, ramp_div=ramp, tail_div=tail, e2e_ms=dt * 1e3, proteins_per_s=batch.n / dt)), flush=True)
     g.close()
