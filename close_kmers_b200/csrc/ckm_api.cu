@@ -225,9 +225,12 @@ static int upload_table(ckm_ctx *c, const ckm_image_header_t *hdr) {
                 attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)bytes);
                 attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
                 attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-                if (!getenv("CKM_NO_L2_PERSIST") &&
-                    cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess)
-                    (void)cudaGetLastError();
+                if (!getenv("CKM_NO_L2_PERSIST")) {
+                    if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess)
+                        (void)cudaGetLastError();
+                    c->l2_window = attr.accessPolicyWindow;  // also applied to the second pipeline stream when it is created
+                    c->has_l2_window = true;
+                }
             } else {
                 (void)cudaGetLastError();
             }
@@ -713,7 +716,15 @@ static int call_batch_pipelined(ckm_ctx *c, const char *residues, const uint64_t
     RC(c->in_off.ensure(((size_t)n + 1) * 8));
     RC(c->h_best.ensure(((size_t)n + 1) * sizeof(ckm_best_t)));
     RC(c->h_totals.ensure(64));
-    if (!c->stream2) CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    if (!c->stream2) {
+        CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+        if (c->has_l2_window) {
+            cudaStreamAttrValue attr;
+            memset(&attr, 0, sizeof attr);
+            attr.accessPolicyWindow = c->l2_window;
+            if (cudaStreamSetAttribute(c->stream2, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) (void)cudaGetLastError();
+        }
+    }
     if (!c->ev_ready) CU(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
     if (!c->ev_done2) CU(cudaEventCreateWithFlags(&c->ev_done2, cudaEventDisableTiming));
     c->cur_off = (const uint64_t *)c->in_off.p;

@@ -37,6 +37,8 @@ struct ckm_ctx {
     // signature table in HBM
     DevBuf table, occupied;  // occupied: 1 bit per slot, only for tables larger than L2
     int l2_bytes = 0;
+    bool has_l2_window = false;
+    cudaAccessPolicyWindow l2_window;  // persisting window over `occupied`
     uint64_t num_sigs = 0, magic = 0;
     int slot_bytes = 0;
 
