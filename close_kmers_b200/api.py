@@ -110,6 +110,11 @@ def lib() -> C.CDLL:
     L.ckm_family_load.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
                                   C.c_void_p]
     L.ckm_family_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
+    L.ckm_family_nr_begin.argtypes = [C.c_void_p]
+    L.ckm_family_nr_add.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    L.ckm_family_nr_finish.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64),
+                                       C.POINTER(C.c_uint64)]
+    L.ckm_family_export.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
     for f in ("ckm_family_pgf_name", "ckm_family_plf_name"):
         getattr(L, f).restype = C.c_char_p
         getattr(L, f).argtypes = [C.c_void_p, C.c_int32]
@@ -212,6 +217,20 @@ def merge_pairs(pairs: np.ndarray) -> np.ndarray:
     pairs = np.ascontiguousarray(pairs, PAIR_DT).copy()
     n = lib().ckm_matrix_merge_pairs(pairs.ctypes.data, len(pairs))
     return pairs[:n]
+
+
+def canonical_family_csr(kmers, fam_off, fam_ids) -> tuple:
+    """Sort a k-mer -> family-list CSR by k-mer and each list by family id (the lists are sets: kmer.cc:216-230)."""
+    kmers = np.asarray(kmers, np.uint64)
+    fam_off = np.asarray(fam_off, np.uint64)
+    fam_ids = np.asarray(fam_ids, np.uint32)
+    cnt = np.diff(fam_off).astype(np.int64)
+    owner = np.repeat(kmers, cnt)
+    order = np.lexsort((fam_ids, owner))
+    ks = np.argsort(kmers, kind="stable")
+    off = np.zeros(len(kmers) + 1, np.uint64)
+    off[1:] = np.cumsum(cnt[ks])
+    return kmers[ks], off, fam_ids[order]
 
 
 class KmerGuts:
@@ -384,6 +403,33 @@ class KmerGuts:
         mk = lambda xs: (C.c_char_p * len(xs))(*[x.encode() for x in xs])
         _check(lib().ckm_family_load(self._h, len(kmers), kmers.ctypes.data, fam_off.ctypes.data, fam_ids.ctypes.data, len(pgf),
                                      mk(pgf), mk(plf), mk(function)))
+
+    # family-mode start-up load (NRLoader::thread_load + KmerInserter + add_fam_mapping), on the GPU
+    def family_nr_begin(self):
+        _check(lib().ckm_family_nr_begin(self._h))
+
+    def family_nr_add(self, fam_ids, residues, offsets):
+        """One chunk of families.nr: fam_ids[i] = family of sequence i, 0xFFFFFFFF = none (ends the chunk, nr_loader.cc:159)."""
+        fam_ids = np.ascontiguousarray(fam_ids, np.uint32)
+        residues = np.ascontiguousarray(residues, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        _check(lib().ckm_family_nr_add(self._h, fam_ids.ctypes.data, residues.ctypes.data, offsets.ctypes.data, len(offsets) - 1))
+
+    def family_nr_finish(self, pgf, plf, function) -> tuple:
+        """Install the collected table; returns (n_kmers, n_entries)."""
+        mk = lambda xs: (C.c_char_p * len(xs))(*[x.encode() for x in xs])
+        nk, ne = C.c_uint64(), C.c_uint64()
+        _check(lib().ckm_family_nr_finish(self._h, len(pgf), mk(pgf), mk(plf), mk(function), C.byref(nk), C.byref(ne)))
+        self._fam_size = (nk.value, ne.value)
+        return self._fam_size
+
+    def family_export(self, n_kmers, n_entries) -> tuple:
+        """(kmers, fam_off, fam_ids) of the installed table, k-mers ascending and every list ascending."""
+        k = np.zeros(n_kmers, np.uint64)
+        o = np.zeros(n_kmers + 1, np.uint64)
+        ids = np.zeros(max(n_entries, 1), np.uint32)
+        _check(lib().ckm_family_export(self._h, n_kmers, n_entries, k.ctypes.data, o.ctypes.data, ids.ctypes.data))
+        return canonical_family_csr(k, o, ids[:n_entries])
 
     def find_best_family_match_batch(self, residues, offsets) -> np.ndarray:
         """FamilyMapper::find_best_family_match (family_mapper.cc:65-205) for every sequence."""

@@ -79,7 +79,7 @@ struct ckm_ctx {
         DevBuf tkeys, tcnt, tcur, toff, slots, ids;                          // index built lazily
         DevBuf d_eids, d_first, rcap, rofs, nd, out_off, entries, out;      // per-request work buffers
         PinBuf h_out;
-    } post;
+    } post, famnr;  // famnr: (k-mer, family id) pairs being collected by ckm_family_nr_add
 
     // fastq path (ckm_fq.cuh)
     struct Fq {
@@ -103,6 +103,9 @@ struct ckm_ctx {
                         &post.d_eids, &post.d_first, &post.rcap, &post.rofs, &post.nd, &post.out_off, &post.entries, &post.out};
         for (auto b : pp) b->release();
         post.h_out.release();
+        DevBuf *pn[] = {&famnr.keys, &famnr.eids, &famnr.tkeys, &famnr.tcnt, &famnr.tcur, &famnr.toff, &famnr.slots, &famnr.ids,
+                        &famnr.d_eids, &famnr.d_first, &famnr.rcap, &famnr.rofs, &famnr.nd, &famnr.out_off, &famnr.entries, &famnr.out};
+        for (auto b : pn) b->release();
         DevBuf *q[] = {&fq.nfrag, &fq.naa, &fq.frag_base, &fq.res_base, &fq.frag_off, &fq.frag_res, &fq.best_frame,
                        &fq.best_score, &fq.best_n, &fq.best_first, &fq.match_off, &fq.matches};
         for (auto b : q) b->release();

@@ -271,14 +271,9 @@ __global__ void __launch_bounds__(256) fam_validate_kernel(const uint64_t *__res
 // ---------------------------------------------------------------------------------------------------
 #include <unordered_map>
 
-extern "C" int ckm_family_load(ckm_ctx *c, uint64_t n_kmers, const uint64_t *kmers, const uint64_t *fam_offsets,
-                               const uint32_t *fam_ids, uint32_t n_families, const char *const *pgf, const char *const *plf,
-                               const char *const *function) {
-    if (!c) return ckm_fail(CKM_EINVAL, "ctx is NULL");
-    if (n_kmers && (!kmers || !fam_offsets || !fam_ids)) return ckm_fail(CKM_EINVAL, "NULL family table");
-    CU(cudaSetDevice(c->device));
-    const uint64_t n_entries = n_kmers ? fam_offsets[n_kmers] : 0;
-    if (n_entries >= (1ull << 32)) return ckm_fail(CKM_EINVAL, "more than 2^32 k-mer->family entries");
+// family_data_ -> interned ids on the device + host strings (shared by ckm_family_load and ckm_family_nr_finish)
+static int family_install_metadata(ckm_ctx *c, uint32_t n_families, const char *const *pgf, const char *const *plf,
+                                   const char *const *function) {
     ckm_ctx::Family &F = c->fam;
     // intern function and PGF strings (family_mapper.cc:150-169 compares strings)
     std::unordered_map<std::string, uint32_t> sids, pgfs;
@@ -308,14 +303,34 @@ extern "C" int ckm_family_load(ckm_ctx *c, uint64_t n_kmers, const uint64_t *kme
     F.n_fams = n_families;
     F.n_functions = (uint32_t)c->functions.size();
     F.hypo_sid = hypo;
+    RC(F.fam_func.ensure(((size_t)n_families + 1) * 4));
+    RC(F.fam_pgf.ensure(((size_t)n_families + 1) * 4));
+    RC(F.func_sid.ensure((func_sid.size() + 1) * 4));
+    if (n_families) {
+        CU(cudaMemcpyAsync(F.fam_func.p, fam_func.data(), (size_t)n_families * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(F.fam_pgf.p, fam_pgf.data(), (size_t)n_families * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (!func_sid.empty())
+        CU(cudaMemcpyAsync(F.func_sid.p, func_sid.data(), func_sid.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));  // the host vectors go out of scope
+    return 0;
+}
+
+extern "C" int ckm_family_load(ckm_ctx *c, uint64_t n_kmers, const uint64_t *kmers, const uint64_t *fam_offsets,
+                               const uint32_t *fam_ids, uint32_t n_families, const char *const *pgf, const char *const *plf,
+                               const char *const *function) {
+    if (!c) return ckm_fail(CKM_EINVAL, "ctx is NULL");
+    if (n_kmers && (!kmers || !fam_offsets || !fam_ids)) return ckm_fail(CKM_EINVAL, "NULL family table");
+    CU(cudaSetDevice(c->device));
+    const uint64_t n_entries = n_kmers ? fam_offsets[n_kmers] : 0;
+    if (n_entries >= (1ull << 32)) return ckm_fail(CKM_EINVAL, "more than 2^32 k-mer->family entries");
+    ckm_ctx::Family &F = c->fam;
+    RC(family_install_metadata(c, n_families, pgf, plf, function));
     uint64_t cap = 16;
     while (cap < 2 * n_kmers) cap <<= 1;
     F.mask = cap - 1;
     RC(F.table.ensure(cap * sizeof(FamSlot)));
     RC(F.ids.ensure((n_entries + 1) * 4));
-    RC(F.fam_func.ensure(((size_t)n_families + 1) * 4));
-    RC(F.fam_pgf.ensure(((size_t)n_families + 1) * 4));
-    RC(F.func_sid.ensure((func_sid.size() + 1) * 4));
     DevBuf d_k, d_o, d_flag;
     RC(d_k.ensure((n_kmers + 1) * 8));
     RC(d_o.ensure((n_kmers + 2) * 8));
@@ -327,12 +342,6 @@ extern "C" int ckm_family_load(ckm_ctx *c, uint64_t n_kmers, const uint64_t *kme
         CU(cudaMemcpyAsync(d_o.p, fam_offsets, (n_kmers + 1) * 8, cudaMemcpyHostToDevice, c->stream));
         if (n_entries) CU(cudaMemcpyAsync(F.ids.p, fam_ids, n_entries * 4, cudaMemcpyHostToDevice, c->stream));
     }
-    if (n_families) {
-        CU(cudaMemcpyAsync(F.fam_func.p, fam_func.data(), (size_t)n_families * 4, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(F.fam_pgf.p, fam_pgf.data(), (size_t)n_families * 4, cudaMemcpyHostToDevice, c->stream));
-    }
-    if (!func_sid.empty())
-        CU(cudaMemcpyAsync(F.func_sid.p, func_sid.data(), func_sid.size() * 4, cudaMemcpyHostToDevice, c->stream));
     unsigned int dup = 0;
     if (n_kmers) {
         const unsigned blocks = (unsigned)((n_kmers + 255) / 256);

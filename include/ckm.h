@@ -199,6 +199,20 @@ int ckm_family_load(ckm_ctx *ctx, uint64_t n_kmers, const uint64_t *kmers, const
                     const uint32_t *fam_ids, uint32_t n_families, const char *const *pgf, const char *const *plf,
                     const char *const *function);
 
+/* The same tables built on the GPU from the proteins of families.nr, replacing NRLoader::thread_load (nr_loader.cc:131-202),
+ * KmerInserter (kmer_inserter.cc:36-58) and add_fam_mapping / fam_map_insert (kmer.cc:216-268): every signature k-mer hit
+ * of a protein is mapped to the protein's family, each family once per k-mer.  fam_ids[i] = encoded family id of sequence
+ * i (< 2^29), or 0xFFFFFFFF for a protein without a family.  One add() call is one chunk (seq_list_t) of the loader:
+ * like thread_load, whose "NO FAM FOR id" branch returns (nr_loader.cc:154-160), the first protein without a family ends
+ * the chunk and the sequences after it in that call are not loaded.  finish() installs the result exactly as
+ * ckm_family_load would, and reports the table's size. */
+int ckm_family_nr_begin(ckm_ctx *ctx);
+int ckm_family_nr_add(ckm_ctx *ctx, const uint32_t *fam_ids, const char *residues, const uint64_t *offsets, uint32_t n);
+int ckm_family_nr_finish(ckm_ctx *ctx, uint32_t n_families, const char *const *pgf, const char *const *plf,
+                         const char *const *function, uint64_t *n_kmers, uint64_t *n_entries);
+/* the installed k-mer -> family lists as CSR on the host (lists unordered): kmers[n_kmers], offsets[n_kmers+1], ids[n_entries] */
+int ckm_family_export(ckm_ctx *ctx, uint64_t n_kmers, uint64_t n_entries, uint64_t *kmers, uint64_t *offsets, uint32_t *ids);
+
 /* best_match_t (family_mapper.h:20-28) with names left as ids */
 typedef struct {
     int32_t gfam;           /* id of the best PGF (ckm_family_pgf_name), -1 if none */

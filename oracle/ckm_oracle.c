@@ -781,6 +781,46 @@ static int u64_cmp(const void *a, const void *b) {
     return x < y ? -1 : x > y;
 }
 
+/* ---- N2: family tables from families.nr proteins.  nr_loader.cc:131-202 (thread_load, family mode) queues
+ * (hit.which_kmer, fam_id) for every hit of process_aa_seq(id, seq, 0, hit_cb, 0); kmer_inserter.cc:36-58 applies
+ * add_fam_mapping (kmer.cc:244-268), whose fam_map_insert (216-230) keeps a family once per k-mer.  A sequence with
+ * no family (fam id 0xFFFFFFFF) ends its chunk (the return at nr_loader.cc:159).  The pairs accumulate in an
+ * orc_postings; orc_family_nr_table returns them as CSR sorted by (k-mer, family id), each pair once. ---- */
+void orc_family_nr_add(const orc_table *t, const orc_params_t *prm, orc_postings *p, const uint32_t *fam_ids,
+                       const char *residues, const uint64_t *offsets, uint32_t n) {
+    uint32_t m = 0;
+    while (m < n && fam_ids[m] != 0xffffffffu) m++;
+    orc_postings_add(t, prm, p, fam_ids, residues, offsets, m);
+}
+static int post_cmp2(const void *a, const void *b) {
+    const post_t *x = a, *y = b;
+    if (x->k != y->k) return x->k < y->k ? -1 : 1;
+    return x->e < y->e ? -1 : x->e > y->e;
+}
+/* malloc'ed outputs: kmers[*n_kmers], fam_off[*n_kmers + 1], ids[*n_entries] */
+void orc_family_nr_table(orc_postings *p, uint64_t *n_kmers, uint64_t *n_entries, uint64_t **kmers, uint64_t **fam_off,
+                         uint32_t **ids) {
+    qsort(p->p, p->n, sizeof(post_t), post_cmp2);
+    p->sorted = 0;
+    uint64_t *K = malloc((p->n + 1) * 8), *O = malloc((p->n + 2) * 8);
+    uint32_t *I = malloc((p->n + 1) * 4);
+    uint64_t nk = 0, ne = 0;
+    for (uint64_t i = 0; i < p->n; i++) {
+        if (i && p->p[i].k == p->p[i - 1].k && p->p[i].e == p->p[i - 1].e) continue;
+        if (!i || p->p[i].k != p->p[i - 1].k) {
+            K[nk] = p->p[i].k;
+            O[nk++] = ne;
+        }
+        I[ne++] = p->p[i].e;
+    }
+    O[nk] = ne;
+    *n_kmers = nk;
+    *n_entries = ne;
+    *kmers = K;
+    *fam_off = O;
+    *ids = I;
+}
+
 ckm_pair_t *orc_matrix_rows(const orc_table *t, const orc_params_t *prm, orc_postings *p, const uint32_t *eids,
                             const char *residues, const uint64_t *offsets, uint32_t n, uint32_t row_begin,
                             uint32_t row_end, uint64_t *n_pairs) {

@@ -55,6 +55,12 @@ KmerPegMapping::encoded_id_t KmerPegMapping::encode_id(const std::string &peg) {
     return id;
 }
 void KmerPegMapping::add_mapping(encoded_id_t enc, unsigned long kmer) { kmer_to_id_[kmer].push_back(enc); }
+// add_fam_mapping + fam_map_insert (vector flavour), kmer.cc:216-230 and 244-268, without the progress print
+void KmerPegMapping::add_fam_mapping(encoded_family_id_t fam_id, encoded_kmer_t kmer) {
+    auto n = kmer_to_family_id_.emplace(std::make_pair(kmer, family_counts_t()));
+    family_counts_t &data = n.first->second;
+    if (std::find(data.begin(), data.end(), fam_id) == data.end()) data.push_back(fam_id);
+}
 
 namespace {
 
@@ -399,6 +405,57 @@ void ref_family_load(void *hv, uint64_t n_kmers, const uint64_t *kmers, const ui
         d.count = 0;
         m.family_data_[f] = d;
     }
+}
+
+// Family-mode start-up load of one families.nr chunk: NRLoader::thread_load (nr_loader.cc:131-202) with the
+// KmerInserter queues (kmer_inserter.cc:36-58) drained inline.  fam_ids[i] = peg_to_family_ entry of sequence i or
+// 0xFFFFFFFF when it has none; like the reference, the first sequence without a family ENDS the chunk (the `return`
+// at nr_loader.cc:159).
+void ref_family_nr_add(void *hv, const uint32_t *fam_ids, const char *residues, const uint64_t *offsets, uint32_t n) {
+    RefHandle *h = (RefHandle *)hv;
+    if (!h->mapping) h->mapping = std::make_shared<KmerPegMapping>();
+    KmerPegMapping &m = *h->mapping;
+    KmerGuts *g = h->guts[0];
+    for (uint32_t i = 0; i < n; i++) {
+        if (fam_ids[i] == 0xffffffffu) return;
+        const KmerPegMapping::encoded_family_id_t fam_id = fam_ids[i];
+        std::vector<std::pair<unsigned long long, KmerPegMapping::encoded_family_id_t>> work;
+        std::function<void(KmerGuts::hit_in_sequence_t)> hit_cb = [&work, fam_id](KmerGuts::hit_in_sequence_t hit) {
+            work.emplace_back(std::make_pair(hit.hit.which_kmer, fam_id));
+        };
+        g->process_aa_seq("seq", seq_at(residues, offsets, i), 0, hit_cb, 0);
+        for (auto &item : work) m.add_fam_mapping(item.second, item.first);
+    }
+}
+
+void ref_family_set_data(void *hv, uint32_t n_fams, const char *const *pgf, const char *const *plf, const char *const *function) {
+    ref_family_load(hv, 0, nullptr, nullptr, nullptr, n_fams, pgf, plf, function);
+}
+
+// size, then contents, of kmer_to_family_id_ as CSR (k-mers in map order, lists in insertion order)
+void ref_family_table_size(void *hv, uint64_t *n_kmers, uint64_t *n_entries) {
+    RefHandle *h = (RefHandle *)hv;
+    *n_kmers = *n_entries = 0;
+    if (!h->mapping) return;
+    for (auto &e : h->mapping->kmer_to_family_id_) {
+        (*n_kmers)++;
+        *n_entries += e.second.size();
+    }
+}
+void ref_family_table(void *hv, uint64_t *kmers, uint64_t *fam_off, uint32_t *ids) {
+    RefHandle *h = (RefHandle *)hv;
+    uint64_t k = 0, e = 0;
+    fam_off[0] = 0;
+    if (!h->mapping) return;
+    for (auto &ent : h->mapping->kmer_to_family_id_) {
+        kmers[k] = ent.first;
+        for (auto f : ent.second) ids[e++] = f;
+        fam_off[++k] = e;
+    }
+}
+void ref_family_clear(void *hv) {
+    RefHandle *h = (RefHandle *)hv;
+    if (h->mapping) h->mapping->kmer_to_family_id_.clear();
 }
 
 static void put_match(std::ostringstream &os, const FamilyMapper::best_match_t &b) { os << b; }

@@ -139,6 +139,11 @@ class Ref:
         L.ref_mapping_new.argtypes = [C.c_void_p]
         L.ref_family_load.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                       C.c_void_p, C.c_void_p]
+        L.ref_family_nr_add.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.ref_family_set_data.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_family_table_size.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.ref_family_table.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_family_clear.argtypes = [C.c_void_p]
         L.ref_family_text.restype = C.c_void_p
         L.ref_family_text.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         L.ref_family_batch.restype = C.c_void_p
@@ -253,6 +258,30 @@ class Ref:
         fam_ids = np.ascontiguousarray(fam_ids, np.uint32)
         self.L.ref_family_load(self.h, len(kmers), kmers.ctypes.data, fam_off.ctypes.data, fam_ids.ctypes.data, len(pgf),
                                _cstr_array(pgf), _cstr_array(plf), _cstr_array(function))
+
+    # NRLoader::thread_load in family mode (+ KmerInserter + add_fam_mapping) for one chunk
+    def family_nr_add(self, fam_ids, batch):
+        fam_ids = np.ascontiguousarray(fam_ids, np.uint32)
+        res = np.ascontiguousarray(batch.residues, np.uint8)
+        off = np.ascontiguousarray(batch.offsets, np.uint64)
+        self.L.ref_family_nr_add(self.h, fam_ids.ctypes.data, res.ctypes.data, off.ctypes.data, batch.n)
+
+    def family_set_data(self, pgf, plf, function):
+        self.L.ref_family_set_data(self.h, len(pgf), _cstr_array(pgf), _cstr_array(plf), _cstr_array(function))
+
+    def family_table(self):
+        """kmer_to_family_id_ as (kmers, fam_off, fam_ids), canonical order."""
+        from close_kmers_b200.api import canonical_family_csr
+        nk, ne = C.c_uint64(), C.c_uint64()
+        self.L.ref_family_table_size(self.h, C.byref(nk), C.byref(ne))
+        k = np.zeros(nk.value, np.uint64)
+        o = np.zeros(nk.value + 1, np.uint64)
+        ids = np.zeros(max(ne.value, 1), np.uint32)
+        self.L.ref_family_table(self.h, k.ctypes.data, o.ctypes.data, ids.ctypes.data)
+        return canonical_family_csr(k, o, ids[:ne.value])
+
+    def family_clear(self):
+        self.L.ref_family_clear(self.h)
 
     def family_text(self, batch):
         res = np.ascontiguousarray(batch.residues, np.uint8)
@@ -417,6 +446,31 @@ class Oracle:
         self.L.orc_family_batch(self.t, C.byref(self.params), self.fam, res.ctypes.data, off.ctypes.data, batch.n,
                                 out.ctypes.data)
         return out
+
+    def family_nr_build(self, chunks):
+        """chunks: iterable of (fam_ids, batch).  Returns (kmers, fam_off, fam_ids) sorted by (k-mer, family)."""
+        L = self.L
+        L.orc_postings_new.restype = C.c_void_p
+        L.orc_family_nr_add.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.orc_family_nr_table.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        L.orc_postings_free.argtypes = [C.c_void_p]
+        L.orc_free.argtypes = [C.c_void_p]
+        p = C.c_void_p(L.orc_postings_new())
+        for fam_ids, batch in chunks:
+            fam_ids = np.ascontiguousarray(fam_ids, np.uint32)
+            res = np.ascontiguousarray(batch.residues, np.uint8)
+            off = np.ascontiguousarray(batch.offsets, np.uint64)
+            L.orc_family_nr_add(self.t, C.byref(self.params), p, fam_ids.ctypes.data, res.ctypes.data, off.ctypes.data, batch.n)
+        nk, ne = C.c_uint64(), C.c_uint64()
+        pk, po, pi = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        L.orc_family_nr_table(p, C.byref(nk), C.byref(ne), C.byref(pk), C.byref(po), C.byref(pi))
+        k = np.ctypeslib.as_array(C.cast(pk, C.POINTER(C.c_uint64)), (max(nk.value, 1),))[:nk.value].copy()
+        o = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_uint64)), (nk.value + 1,)).copy()
+        ids = np.ctypeslib.as_array(C.cast(pi, C.POINTER(C.c_uint32)), (max(ne.value, 1),))[:ne.value].copy()
+        for q in (pk, po, pi):
+            L.orc_free(q)
+        L.orc_postings_free(p)
+        return k, o, ids
 
     def postings_new(self):
         self.post = C.c_void_p(self.L.orc_postings_new())

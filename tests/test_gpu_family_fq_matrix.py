@@ -7,7 +7,7 @@ import pytest
 
 import workloads as wl
 from close_kmers_b200 import api, synth
-from test_oracle_family_fq_matrix import DNA_EDGE
+from test_oracle_family_fq_matrix import DNA_EDGE, nr_chunks
 
 pytestmark = pytest.mark.gpu
 
@@ -48,6 +48,49 @@ def test_family_voting(checkers, world):
         wl.assert_family_equal(got if not prm else guts.find_best_family_match_batch(batch.residues, batch.offsets),
                                ref.family_batch(batch), fam, synth.function_names(sig.n_functions), "cuda vs reference")
     assert int((want["lfam"] >= 0).sum()) > 1000
+
+
+def test_family_nr_load_on_gpu(checkers, world):
+    """N2: the k-mer -> family table built on the device from families.nr proteins equals the one the reference's
+    NRLoader / KmerInserter / add_fam_mapping build, and votes identically afterwards."""
+    import dataclasses
+    protos, sig, fam, _, _, _, d = world
+    _, _, img = wl.small_world(otu_mode="mixed")
+    chunks = nr_chunks(protos, fam.n_fams)
+    orc = checkers.Oracle().open_image(img)
+    want = orc.family_nr_build(chunks)
+    guts = api.KmerGuts(kmer_dir=d)
+    try:
+        for rep in range(2):  # a second begin() starts from an empty table
+            guts.family_nr_begin()
+            for fam_ids, batch in chunks:
+                guts.family_nr_add(fam_ids, batch.residues, batch.offsets)
+            nk, ne = guts.family_nr_finish(fam.pgf, fam.plf, fam.function)
+            assert (nk, ne) == (len(want[0]), len(want[2]))
+            got = guts.family_export(nk, ne)
+            for a, b, name in zip(got, want, ("kmers", "fam_off", "fam_ids")):
+                np.testing.assert_array_equal(a, b, err_msg=name)
+        batch = wl.concat_batches(wl.edge_batch(protos), synth.make_proteins(78, protos, 2500))
+        orc.family_load(dataclasses.replace(fam, kmers=want[0], fam_off=want[1], fam_ids=want[2]))
+        got_m = guts.find_best_family_match_batch(batch.residues, batch.offsets)
+        wl.assert_family_records_equal(got_m, orc.family_batch(batch), "cuda vs oracle on the nr-loaded table")
+        if os.path.exists(checkers.REF_SO):
+            ref = checkers.Ref().open(d)
+            ref.set_params()
+            for fam_ids, b in chunks:
+                ref.family_nr_add(fam_ids, b)
+            for a, b, name in zip(got, ref.family_table(), ("kmers", "fam_off", "fam_ids")):
+                np.testing.assert_array_equal(a, b, err_msg="reference " + name)
+            ref.family_set_data(fam.pgf, fam.plf, fam.function)
+            wl.assert_family_equal(got_m, ref.family_batch(batch), fam, synth.function_names(sig.n_functions), "cuda vs reference")
+            ref.close()
+        # an empty load installs an empty table: nobody matches
+        guts.family_nr_begin()
+        assert guts.family_nr_finish(fam.pgf, fam.plf, fam.function) == (0, 0)
+        assert int((guts.find_best_family_match_batch(batch.residues, batch.offsets)["lfam"] >= 0).sum()) == 0
+    finally:
+        guts.close()
+        orc.close()
 
 
 def test_family_large_fanout_uses_global_maps(checkers):

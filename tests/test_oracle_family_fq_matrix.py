@@ -86,3 +86,55 @@ def test_matrix_matches_reference(checkers, world):
     # row blocks partition the result
     parts = np.concatenate([orc.matrix_rows(eids, req, a, b) for a, b in ((0, 70), (70, 71), (71, 200))])
     assert wl.matrix_text_from_pairs(parts, eids, req, {v: k for k, v in eid_of.items()}) == want
+
+
+def nr_chunks(protos, n_fams, seed=21, n=900):
+    """families.nr stand-in: three chunks of proteins with their family ids; the middle chunk holds one protein without a
+    family, which ends that chunk (nr_loader.cc:154-160)."""
+    rng = np.random.default_rng(seed)
+    chunks = []
+    for c in range(3):
+        batch = wl.concat_batches(wl.edge_batch(protos), synth.make_proteins(seed + c, protos, n // 3)) if c == 0 else \
+            synth.make_proteins(seed + c, protos, n // 3)
+        fam_ids = rng.integers(0, n_fams, batch.n).astype(np.uint32)
+        fam_ids[: batch.n // 2] = fam_ids[: batch.n // 2] % 5  # many proteins of few families: duplicate (k-mer, family) pairs
+        if c == 1:
+            fam_ids[batch.n * 2 // 3] = 0xFFFFFFFF
+        chunks.append((fam_ids, batch))
+    return chunks
+
+
+def test_family_nr_load_matches_reference(checkers, world):
+    """N2: NRLoader family-mode load (thread_load -> KmerInserter -> add_fam_mapping) restated by the oracle."""
+    import dataclasses
+    protos, sig, fam, _, _ = world
+    _, _, img = wl.small_world(otu_mode="minus1")
+    d = tempfile.mkdtemp(prefix="ckm_ref_nr_")
+    api.save_kmer_hash_table(img, d)
+    synth.write_index_files(d, sig.n_functions, 0)
+    ref = checkers.Ref().open(d)
+    ref.set_params()
+    orc = checkers.Oracle().open_image(img)
+    chunks = nr_chunks(protos, fam.n_fams)
+    for fam_ids, batch in chunks:
+        ref.family_nr_add(fam_ids, batch)
+    want = ref.family_table()
+    got = orc.family_nr_build(chunks)
+    for a, b, name in zip(got, want, ("kmers", "fam_off", "fam_ids")):
+        np.testing.assert_array_equal(a, b, err_msg=name)
+    assert len(got[0]) > 1000 and len(got[2]) > len(got[0])
+    # a protein after the family-less one contributes nothing: rebuilding without the tail of chunk 1 gives the same table
+    f1, b1 = chunks[1]
+    cut = int(np.flatnonzero(f1 == 0xFFFFFFFF)[0])
+    head = synth.Batch(b1.residues[: int(b1.offsets[cut])], b1.offsets[: cut + 1])
+    again = orc.family_nr_build([chunks[0], (f1[:cut], head), chunks[2]])
+    for a, b in zip(again, got):
+        np.testing.assert_array_equal(a, b)
+    # and the voting that runs on the loaded table agrees
+    ref.family_set_data(fam.pgf, fam.plf, fam.function)
+    orc.family_load(dataclasses.replace(fam, kmers=got[0], fam_off=got[1], fam_ids=got[2]))
+    batch = synth.make_proteins(77, protos, 800)
+    wl.assert_family_equal(orc.family_batch(batch), ref.family_batch(batch), fam, synth.function_names(sig.n_functions),
+                           "oracle vs reference on the nr-loaded table")
+    ref.close()
+    orc.close()
