@@ -74,12 +74,13 @@ struct ckm_ctx {
     // /add postings + /matrix (ckm_matrix.cuh)
     struct Post {
         DevBuf keys, eids;  // the appended (k-mer, peg id) pairs
-        uint64_t n = 0, mask = 0;
+        uint64_t n = 0, mask = 0, n_keys = 0;  // n_keys: distinct k-mers, known after indexing
         bool dirty = true;
-        DevBuf tkeys, tcnt, tcur, toff, slots, ids;                          // index built lazily
+        DevBuf tkeys, tcnt, tcur, toff, slots, ids, occ;                     // index built lazily
         DevBuf d_eids, d_first, rcap, rofs, nd, out_off, entries, out;      // per-request work buffers
         PinBuf h_out;
     } post, famnr;  // famnr: (k-mer, family id) pairs being collected by ckm_family_nr_add
+    uint64_t famnr_compact_at = 1ull << 28, famnr_last_unique = 0;  // dedupe the collected pairs once this many are held
 
     // fastq path (ckm_fq.cuh)
     struct Fq {
@@ -103,7 +104,7 @@ struct ckm_ctx {
                         &post.d_eids, &post.d_first, &post.rcap, &post.rofs, &post.nd, &post.out_off, &post.entries, &post.out};
         for (auto b : pp) b->release();
         post.h_out.release();
-        DevBuf *pn[] = {&famnr.keys, &famnr.eids, &famnr.tkeys, &famnr.tcnt, &famnr.tcur, &famnr.toff, &famnr.slots, &famnr.ids,
+        DevBuf *pn[] = {&famnr.keys, &famnr.eids, &famnr.tkeys, &famnr.tcnt, &famnr.tcur, &famnr.toff, &famnr.slots, &famnr.ids, &famnr.occ, &post.occ,
                         &famnr.d_eids, &famnr.d_first, &famnr.rcap, &famnr.rofs, &famnr.nd, &famnr.out_off, &famnr.entries, &famnr.out};
         for (auto b : pn) b->release();
         DevBuf *q[] = {&fq.nfrag, &fq.naa, &fq.frag_base, &fq.res_base, &fq.frag_off, &fq.frag_res, &fq.best_frame,

@@ -57,14 +57,17 @@ post_fill_kernel(const uint64_t *__restrict__ pkeys, const uint32_t *__restrict_
 
 __global__ void __launch_bounds__(256)
 post_pack_kernel(const unsigned long long *__restrict__ tkeys, const uint32_t *__restrict__ tcnt,
-                 const uint64_t *__restrict__ toff, uint64_t cap, FamSlot *__restrict__ slots) {
-    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= cap) return;
+                 const uint64_t *__restrict__ toff, uint64_t cap, FamSlot *__restrict__ slots, unsigned long long *n_occupied) {
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // cap is a multiple of 16 >= 16, blocks are whole warps
     FamSlot f;
-    f.key1 = tkeys[s];
-    f.off = (uint32_t)toff[s];
-    f.cnt = tcnt[s];
-    slots[s] = f;
+    f.key1 = s < cap ? tkeys[s] : 0ull;
+    if (s < cap) {
+        f.off = (uint32_t)toff[s];
+        f.cnt = tcnt[s];
+        slots[s] = f;
+    }
+    const unsigned occ = __popc(__ballot_sync(0xffffffffu, f.key1 != 0ull));
+    if ((threadIdx.x & 31u) == 0 && occ) atomicAdd(n_occupied, (unsigned long long)occ);
 }
 
 // capacity of row i's output region: it has at most min(E_i, i) distinct partners
@@ -227,9 +230,12 @@ extern "C" uint64_t ckm_postings_count(const ckm_ctx *c) { return c->post.n; }
 static int postings_index(ckm_ctx *c, ckm_ctx::Post &P) {
     if (!P.dirty) return 0;
     if (P.n >= (1ull << 32)) return ckm_fail(CKM_EINVAL, "more than 2^32 postings");
+    // every key is a signature k-mer that was hit: there are at most num_sigs distinct ones
     uint64_t cap = 16;
-    while (cap < 2 * P.n) cap <<= 1;
+    while (cap < 2 * std::min<uint64_t>(P.n, c->num_sigs)) cap <<= 1;
     P.mask = cap - 1;
+    RC(P.occ.ensure(64));
+    CU(cudaMemsetAsync(P.occ.p, 0, 8, c->stream));
     RC(P.tkeys.ensure(cap * 8));
     RC(P.tcnt.ensure((cap + 1) * 4));
     RC(P.tcur.ensure((cap + 1) * 4));
@@ -255,8 +261,9 @@ static int postings_index(ckm_ctx *c, ckm_ctx::Post &P) {
     }
     post_pack_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, c->stream>>>((const unsigned long long *)P.tkeys.p,
                                                                           (const uint32_t *)P.tcnt.p, (const uint64_t *)P.toff.p,
-                                                                          cap, (FamSlot *)P.slots.p);
+                                                                          cap, (FamSlot *)P.slots.p, (unsigned long long *)P.occ.p);
     c->launches++;
+    CU(cudaMemcpyAsync(&P.n_keys, P.occ.p, 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
     P.dirty = false;
@@ -374,39 +381,9 @@ pair_dedupe_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict
 }
 }  // namespace ckm
 
-extern "C" int ckm_family_nr_begin(ckm_ctx *c) {
-    if (!c) return ckm_fail(CKM_EINVAL, "ctx is NULL");
-    c->famnr.n = 0;
-    c->famnr.dirty = true;
-    return 0;
-}
-
-extern "C" int ckm_family_nr_add(ckm_ctx *c, const uint32_t *fam_ids, const char *residues, const uint64_t *offsets, uint32_t n) {
-    if (!c || (n && !fam_ids)) return ckm_fail(CKM_EINVAL, "NULL argument");
-    for (uint32_t i = 0; i < n; i++)
-        if (fam_ids[i] != 0xffffffffu && fam_ids[i] >= (1u << 29)) return ckm_fail(CKM_EINVAL, "family id %u does not fit 29 bits", fam_ids[i]);
-    // "NO FAM FOR id" (nr_loader.cc:154-160): thread_load RETURNS there, so the first protein without a family ends the
-    // chunk -- the sequences after it in the same call are not loaded either.  Kept as is.
-    for (uint32_t i = 0; i < n; i++)
-        if (fam_ids[i] == 0xffffffffu) {
-            n = i;
-            break;
-        }
-    if (n == 0) return 0;
-    uint64_t total = 0;
-    uint32_t max_len = 0;
-    RC(upload_batch(c, residues, offsets, n, &total, &max_len));
-    // process_aa_seq(id, seq, 0, hit_cb, 0): hits only (nr_loader.cc:172)
-    RC(run_device(c, (const uint8_t *)c->in_res.p, (const uint64_t *)c->in_off.p, n, total, std::max(max_len, 1u), CKM_WANT_HITS));
-    return postings_append_device(c, c->famnr, fam_ids, (const uint64_t *)c->in_off.p, n);
-}
-
-extern "C" int ckm_family_nr_finish(ckm_ctx *c, uint32_t n_families, const char *const *pgf, const char *const *plf,
-                                    const char *const *function, uint64_t *n_kmers_out, uint64_t *n_entries_out) {
-    if (!c) return ckm_fail(CKM_EINVAL, "ctx is NULL");
-    CU(cudaSetDevice(c->device));
+// drop repeated (k-mer, family) pairs from the collected list; idempotent, so it can run whenever the list has grown
+static int famnr_compact(ckm_ctx *c) {
     ckm_ctx::Post &P = c->famnr;
-    // 1. (k-mer, family) pairs, each once
     uint64_t cap = 16;
     while (cap < 2 * P.n) cap <<= 1;
     DevBuf set, ukeys, ufams, cnt;
@@ -427,13 +404,58 @@ extern "C" int ckm_family_nr_finish(ckm_ctx *c, uint32_t n_families, const char 
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
     set.release();
-    // 2. group by k-mer with the postings indexer (count -> prefix sum -> fill)
+    cnt.release();
     P.keys.release();
     P.eids.release();
     P.keys = ukeys;
     P.eids = ufams;
     P.n = n_unique;
     P.dirty = true;
+    c->famnr_last_unique = n_unique;
+    return 0;
+}
+
+extern "C" int ckm_family_nr_begin(ckm_ctx *c) {
+    if (!c) return ckm_fail(CKM_EINVAL, "ctx is NULL");
+    c->famnr.n = 0;
+    c->famnr.dirty = true;
+    c->famnr_last_unique = 0;
+    if (const char *e = getenv("CKM_FAMNR_COMPACT_AT")) c->famnr_compact_at = strtoull(e, nullptr, 10);
+    return 0;
+}
+
+extern "C" int ckm_family_nr_add(ckm_ctx *c, const uint32_t *fam_ids, const char *residues, const uint64_t *offsets, uint32_t n) {
+    if (!c || (n && !fam_ids)) return ckm_fail(CKM_EINVAL, "NULL argument");
+    for (uint32_t i = 0; i < n; i++)
+        if (fam_ids[i] != 0xffffffffu && fam_ids[i] >= (1u << 29)) return ckm_fail(CKM_EINVAL, "family id %u does not fit 29 bits", fam_ids[i]);
+    // "NO FAM FOR id" (nr_loader.cc:154-160): thread_load RETURNS there, so the first protein without a family ends the
+    // chunk -- the sequences after it in the same call are not loaded either.  Kept as is.
+    for (uint32_t i = 0; i < n; i++)
+        if (fam_ids[i] == 0xffffffffu) {
+            n = i;
+            break;
+        }
+    if (n == 0) return 0;
+    uint64_t total = 0;
+    uint32_t max_len = 0;
+    RC(upload_batch(c, residues, offsets, n, &total, &max_len));
+    // process_aa_seq(id, seq, 0, hit_cb, 0): hits only (nr_loader.cc:172)
+    RC(run_device(c, (const uint8_t *)c->in_res.p, (const uint64_t *)c->in_off.p, n, total, std::max(max_len, 1u), CKM_WANT_HITS));
+    RC(postings_append_device(c, c->famnr, fam_ids, (const uint64_t *)c->in_off.p, n));
+    // members of one family share most of their k-mers: keep the list near its distinct size instead of its raw size
+    if (c->famnr.n >= std::max<uint64_t>(c->famnr_compact_at, 2 * c->famnr_last_unique)) RC(famnr_compact(c));
+    return 0;
+}
+
+extern "C" int ckm_family_nr_finish(ckm_ctx *c, uint32_t n_families, const char *const *pgf, const char *const *plf,
+                                    const char *const *function, uint64_t *n_kmers_out, uint64_t *n_entries_out) {
+    if (!c) return ckm_fail(CKM_EINVAL, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    ckm_ctx::Post &P = c->famnr;
+    // 1. (k-mer, family) pairs, each once
+    RC(famnr_compact(c));
+    const uint64_t n_unique = P.n;
+    // 2. group by k-mer with the postings indexer (count -> prefix sum -> fill)
     RC(postings_index(c, P));
     // 3. install as the family table (same slot format), with the family metadata interned like ckm_family_load
     ckm_ctx::Family &F = c->fam;
@@ -446,16 +468,8 @@ extern "C" int ckm_family_nr_finish(ckm_ctx *c, uint32_t n_families, const char 
     P.slots = DevBuf();
     P.ids = DevBuf();
     F.loaded = true;
-    // distinct k-mers = occupied slots; count on the host from the offsets' tail is not available: report via a scan of tcnt
     if (n_entries_out) *n_entries_out = n_unique;
-    if (n_kmers_out) {
-        // occupied slots of the index = distinct k-mers
-        std::vector<unsigned long long> hk((size_t)(P.mask + 1));
-        CU(cudaMemcpy(hk.data(), P.tkeys.p, hk.size() * 8, cudaMemcpyDeviceToHost));
-        uint64_t nk = 0;
-        for (auto k : hk) nk += k != 0;
-        *n_kmers_out = nk;
-    }
+    if (n_kmers_out) *n_kmers_out = P.n_keys;
     P.n = 0;
     DevBuf *work[] = {&P.keys, &P.eids, &P.tkeys, &P.tcnt, &P.tcur, &P.toff};
     for (auto b : work) b->release();

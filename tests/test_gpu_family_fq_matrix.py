@@ -61,7 +61,8 @@ def test_family_nr_load_on_gpu(checkers, world):
     want = orc.family_nr_build(chunks)
     guts = api.KmerGuts(kmer_dir=d)
     try:
-        for rep in range(2):  # a second begin() starts from an empty table
+        for rep in range(2):  # a second begin() starts from an empty table; it also dedupes after every chunk
+            os.environ["CKM_FAMNR_COMPACT_AT"] = "1000" if rep else str(1 << 28)
             guts.family_nr_begin()
             for fam_ids, batch in chunks:
                 guts.family_nr_add(fam_ids, batch.residues, batch.offsets)
@@ -89,6 +90,7 @@ def test_family_nr_load_on_gpu(checkers, world):
         assert guts.family_nr_finish(fam.pgf, fam.plf, fam.function) == (0, 0)
         assert int((guts.find_best_family_match_batch(batch.residues, batch.offsets)["lfam"] >= 0).sum()) == 0
     finally:
+        os.environ.pop("CKM_FAMNR_COMPACT_AT", None)
         guts.close()
         orc.close()
 
