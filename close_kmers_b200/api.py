@@ -219,6 +219,68 @@ def merge_pairs(pairs: np.ndarray) -> np.ndarray:
     return pairs[:n]
 
 
+class SeqBatchC(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("ids", C.POINTER(C.c_char_p)), ("residues", C.c_void_p), ("offsets", C.POINTER(C.c_uint64)),
+                ("n_errors", C.c_uint64)]
+
+
+class SeqParser:
+    """Streaming FASTA / FASTQ parser of the request front end (include/ckm_server.h); host-only."""
+
+    def __init__(self, fastq: bool = False):
+        L = lib()
+        L.ckm_seq_parser_new.restype = C.c_void_p
+        L.ckm_seq_parser_new.argtypes = [C.c_int]
+        L.ckm_seq_parser_free.argtypes = [C.c_void_p]
+        L.ckm_seq_parser_feed.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+        L.ckm_seq_parser_complete.argtypes = [C.c_void_p]
+        L.ckm_seq_parser_pending.restype = C.c_uint64
+        L.ckm_seq_parser_pending.argtypes = [C.c_void_p]
+        L.ckm_seq_parser_take.argtypes = [C.c_void_p, C.POINTER(SeqBatchC)]
+        L.ckm_seq_parser_last_error.restype = C.c_char_p
+        L.ckm_seq_parser_last_error.argtypes = [C.c_void_p]
+        self._p = C.c_void_p(L.ckm_seq_parser_new(int(fastq)))
+        self.n_errors = 0
+
+    def feed(self, data: bytes):
+        lib().ckm_seq_parser_feed(self._p, data, len(data))
+
+    def complete(self):
+        lib().ckm_seq_parser_complete(self._p)
+
+    def pending(self) -> int:
+        return lib().ckm_seq_parser_pending(self._p)
+
+    def take(self) -> list:
+        """[(id, sequence)] completed since the last take, as bytes."""
+        b = SeqBatchC()
+        lib().ckm_seq_parser_take(self._p, C.byref(b))
+        self.n_errors = b.n_errors
+        res = C.string_at(b.residues, b.offsets[b.n]) if b.n else b""
+        return [(b.ids[i], res[b.offsets[i]:b.offsets[i + 1]]) for i in range(b.n)]
+
+    def last_error(self) -> str:
+        return lib().ckm_seq_parser_last_error(self._p).decode(errors="replace")
+
+    def __del__(self):
+        try:
+            lib().ckm_seq_parser_free(self._p)
+        except Exception:
+            pass
+
+
+def http_describe(head: bytes) -> dict:
+    """ckm_http_describe as a dict (repeated keys keep the last value)."""
+    L = lib()
+    L.ckm_http_describe.restype = C.c_void_p
+    L.ckm_http_describe.argtypes = [C.c_char_p, C.c_size_t]
+    L.ckm_free_text.argtypes = [C.c_void_p]
+    p = L.ckm_http_describe(head, len(head))
+    text = C.string_at(p).decode(errors="replace")
+    L.ckm_free_text(p)
+    return dict(line.split("=", 1) for line in text.split("\n") if "=" in line)
+
+
 def canonical_family_csr(kmers, fam_off, fam_ids) -> tuple:
     """Sort a k-mer -> family-list CSR by k-mer and each list by family id (the lists are sets: kmer.cc:216-230)."""
     kmers = np.asarray(kmers, np.uint64)

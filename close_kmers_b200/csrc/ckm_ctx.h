@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -68,6 +69,8 @@ struct ckm_ctx {
         uint32_t n_fams = 0, n_functions = 0, hypo_sid = 0;
         std::vector<std::string> pgf_names, plf;         // host strings for the response text
         DevBuf hit_fam, E, gcap, gofs, gscratch, matches;  // per-batch work buffers
+        DevBuf sofs, snd, sentries, sout_off, sout;        // ckm_family_scores: per-protein (family, count, weight) lists
+        PinBuf h_scores, h_score_off;
     } fam;
     PinBuf h_fam;
 
@@ -78,8 +81,18 @@ struct ckm_ctx {
         bool dirty = true;
         DevBuf tkeys, tcnt, tcur, toff, slots, ids, occ;                     // index built lazily
         DevBuf d_eids, d_first, rcap, rofs, nd, out_off, entries, out;      // per-request work buffers
-        PinBuf h_out;
+        PinBuf h_out, h_off;
+        void release_all() {
+            DevBuf *b[] = {&keys, &eids, &tkeys, &tcnt, &tcur, &toff, &slots, &ids, &occ, &d_eids, &d_first, &rcap, &rofs, &nd, &out_off,
+                           &entries, &out};
+            for (auto x : b) x->release();
+            h_out.release();
+            h_off.release();
+        }
     } post, famnr;  // famnr: (k-mer, family id) pairs being collected by ckm_family_nr_add
+    // postings of the mappings that are not selected (ckm_postings_select): one KmerPegMapping per "/mapping/<key>"
+    std::map<uint32_t, Post> post_store;
+    uint32_t post_key = 0;
     uint64_t famnr_compact_at = 1ull << 28, famnr_last_unique = 0;  // dedupe the collected pairs once this many are held
 
     // fastq path (ckm_fq.cuh)
@@ -98,15 +111,14 @@ struct ckm_ctx {
                        &otus_out};
         for (auto b : d) b->release();
         DevBuf *f[] = {&fam.table, &fam.ids, &fam.fam_func, &fam.fam_pgf, &fam.func_sid, &fam.hit_fam, &fam.E, &fam.gcap,
-                       &fam.gofs, &fam.gscratch, &fam.matches};
+                       &fam.gofs, &fam.gscratch, &fam.matches, &fam.sofs, &fam.snd, &fam.sentries, &fam.sout_off, &fam.sout};
         for (auto b : f) b->release();
-        DevBuf *pp[] = {&post.keys, &post.eids, &post.tkeys, &post.tcnt, &post.tcur, &post.toff, &post.slots, &post.ids,
-                        &post.d_eids, &post.d_first, &post.rcap, &post.rofs, &post.nd, &post.out_off, &post.entries, &post.out};
-        for (auto b : pp) b->release();
-        post.h_out.release();
-        DevBuf *pn[] = {&famnr.keys, &famnr.eids, &famnr.tkeys, &famnr.tcnt, &famnr.tcur, &famnr.toff, &famnr.slots, &famnr.ids, &famnr.occ, &post.occ,
-                        &famnr.d_eids, &famnr.d_first, &famnr.rcap, &famnr.rofs, &famnr.nd, &famnr.out_off, &famnr.entries, &famnr.out};
-        for (auto b : pn) b->release();
+        fam.h_scores.release();
+        fam.h_score_off.release();
+        post.release_all();
+        famnr.release_all();
+        for (auto &e : post_store) e.second.release_all();
+        post_store.clear();
         DevBuf *q[] = {&fq.nfrag, &fq.naa, &fq.frag_base, &fq.res_base, &fq.frag_off, &fq.frag_res, &fq.best_frame,
                        &fq.best_score, &fq.best_n, &fq.best_first, &fq.match_off, &fq.matches};
         for (auto b : q) b->release();

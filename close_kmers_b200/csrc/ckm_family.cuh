@@ -104,6 +104,32 @@ fam_lookup_kernel(FamTables ft, const uint64_t *__restrict__ offsets, const uint
     }
 }
 
+// optional second output of fam_vote_kernel: every (family, hit_count, weighted_total) of protein i at entries[ofs[i]...]
+struct FamScoreOut {
+    ckm_score_t *entries;
+    const uint64_t *ofs;  // exclusive prefix sum of E
+    uint32_t *n_distinct;
+};
+
+// compacts the per-protein score regions into CSR order, each protein's entries by ascending id (rank sort: ids are
+// distinct within a protein)
+__global__ void __launch_bounds__(256)
+score_export_kernel(const ckm_score_t *__restrict__ entries, const uint64_t *__restrict__ ofs, const uint32_t *__restrict__ n_distinct,
+                    const uint64_t *__restrict__ out_off, uint32_t n, ckm_score_t *__restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const ckm_score_t *src = entries + ofs[i];
+    const uint32_t nd = n_distinct[i];
+    ckm_score_t *dst = out + out_off[i];
+    for (uint32_t k = lane; k < nd; k += 32) {
+        const ckm_score_t e = src[k];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < nd; j++) rank += src[j].id < e.id;
+        dst[rank] = e;
+    }
+}
+
 // open-addressed insert-or-find of `id1` (id+1) in keys[0..mask]; returns the slot; *fresh = newly claimed
 __device__ __forceinline__ uint32_t map_slot(uint32_t *keys, uint32_t mask, uint32_t id1, bool *fresh) {
     uint32_t s = (id1 * 2654435761u) & mask;
@@ -120,7 +146,7 @@ __global__ void __launch_bounds__(FamVoteCfg<CAP>::kWarps * 32)
 fam_vote_kernel(FamTables ft, const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ n_hits,
                 const uint2 *__restrict__ hit_fam, const uint32_t *__restrict__ E, const uint32_t *__restrict__ gcap,
                 const uint64_t *__restrict__ gofs, uint32_t *__restrict__ gscratch, const ckm_best_t *__restrict__ best,
-                uint32_t n, ckm_family_match_t *__restrict__ out) {
+                uint32_t n, ckm_family_match_t *__restrict__ out, FamScoreOut so) {
     extern __shared__ __align__(16) uint32_t fam_smem[];  // FamVoteCfg<CAP>::kSmem bytes, carved per warp below
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     uint32_t *const my_smem = fam_smem + (size_t)wib * FamVoteCfg<CAP>::kWarpWords;
@@ -175,6 +201,30 @@ fam_vote_kernel(FamTables ft, const uint64_t *__restrict__ offsets, const uint32
                 }
                 __syncwarp();
             }
+        }
+
+        // ---- seq_score_ as it stands after the hits (LookupRequest::on_hit, lookup_request.cc:441-464), for callers
+        // that report every family: (id, hit_count, weighted_total) per distinct family, in map-slot order ----
+        if (so.entries != nullptr) {
+            ckm_score_t *dst = so.entries + so.ofs[i];
+            uint32_t total = 0;
+            if (E[i] != 0) {
+                for (uint32_t s0 = 0; s0 < cap; s0 += 32) {
+                    const uint32_t s = s0 + lane;
+                    const uint32_t key = keys[s];
+                    const bool q = key != 0u;
+                    const uint32_t m = __ballot_sync(0xffffffffu, q);
+                    if (q) {
+                        ckm_score_t e;
+                        e.id = key - 1;
+                        e.hit_count = cnt[s];
+                        e.weighted_total = wsum[s];
+                        dst[total + __popc(m & ((1u << lane) - 1u))] = e;
+                    }
+                    total += __popc(m);
+                }
+            }
+            if (lane == 0) so.n_distinct[i] = total;
         }
 
         // ---- F2: best call -> matching families -> best PLF / rolled-up PGF (family_mapper.cc:98-204) ----
@@ -377,7 +427,7 @@ extern "C" const char *ckm_family_function_name(const ckm_ctx *c, const ckm_fami
 }
 
 // K1 (hits + keys) and K2 (calls + best) must already have run on (d_res, d_off); leaves matches in c->fam.matches
-static int family_device(ckm_ctx *c, const uint64_t *d_off, uint32_t n, uint64_t total) {
+static int family_device(ckm_ctx *c, const uint64_t *d_off, uint32_t n, uint64_t total, bool want_scores = false) {
     ckm_ctx::Family &F = c->fam;
     RC(F.hit_fam.ensure((total + 1) * sizeof(uint2)));
     RC(F.E.ensure(((size_t)n + 1) * 4));
@@ -407,6 +457,20 @@ static int family_device(ckm_ctx *c, const uint64_t *d_off, uint32_t n, uint64_t
         RC(F.gscratch.ensure(gtotal * 5 * 4));
         CU(cudaMemsetAsync(F.gscratch.p, 0, gtotal * 5 * 4, c->stream));
     }
+    FamScoreOut so = {nullptr, nullptr, nullptr};
+    if (want_scores) {  // regions of E_i entries: a protein touches at most that many distinct families
+        RC(F.sofs.ensure(((size_t)n + 2) * 8));
+        RC(F.snd.ensure(((size_t)n + 1) * 4));
+        RC(F.sout_off.ensure(((size_t)n + 2) * 8));
+        RC(prefix_sum(c, (const uint32_t *)F.E.p, n, (uint64_t *)F.sofs.p));
+        uint64_t etotal = 0;
+        CU(cudaMemcpyAsync(&etotal, (const uint64_t *)F.sofs.p + n, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        RC(F.sentries.ensure((etotal + 1) * sizeof(ckm_score_t)));
+        so.entries = (ckm_score_t *)F.sentries.p;
+        so.ofs = (const uint64_t *)F.sofs.p;
+        so.n_distinct = (uint32_t *)F.snd.p;
+    }
     {
         typedef FamVoteCfg<kFamSmallCap> S;
         typedef FamVoteCfg<kFamSmemCap> L;
@@ -416,13 +480,60 @@ static int family_device(ckm_ctx *c, const uint64_t *d_off, uint32_t n, uint64_t
         const unsigned lb2 = (unsigned)std::min<uint64_t>(((uint64_t)n + L::kWarps - 1) / L::kWarps, (uint64_t)c->sm_count * 8);
         fam_vote_kernel<kFamSmallCap><<<sb, S::kWarps * 32, S::kSmem, c->stream>>>(
             ft, d_off, (const uint32_t *)c->n_hits.p, (const uint2 *)F.hit_fam.p, (const uint32_t *)F.E.p, (const uint32_t *)F.gcap.p,
-            (const uint64_t *)F.gofs.p, (uint32_t *)F.gscratch.p, (const ckm_best_t *)c->best.p, n, (ckm_family_match_t *)F.matches.p);
+            (const uint64_t *)F.gofs.p, (uint32_t *)F.gscratch.p, (const ckm_best_t *)c->best.p, n, (ckm_family_match_t *)F.matches.p, so);
         fam_vote_kernel<kFamSmemCap><<<lb2, L::kWarps * 32, L::kSmem, c->stream>>>(
             ft, d_off, (const uint32_t *)c->n_hits.p, (const uint2 *)F.hit_fam.p, (const uint32_t *)F.E.p, (const uint32_t *)F.gcap.p,
-            (const uint64_t *)F.gofs.p, (uint32_t *)F.gscratch.p, (const ckm_best_t *)c->best.p, n, (ckm_family_match_t *)F.matches.p);
+            (const uint64_t *)F.gofs.p, (uint32_t *)F.gscratch.p, (const ckm_best_t *)c->best.p, n, (ckm_family_match_t *)F.matches.p, so);
         c->launches += 2;
     }
     CU(cudaGetLastError());
+    return 0;
+}
+
+// LookupRequest's per-sequence accumulation in family mode (lookup_request.cc:138-166, 441-464): every family a
+// sequence's hits touch, with hit_count (= hit_total) and weighted_total, plus find_best_call and the FamilyMapper
+// match of ckm_family_batch, in one pass
+extern "C" int ckm_family_scores(ckm_ctx *c, const char *residues, const uint64_t *offsets, uint32_t n, ckm_family_scores_t *out) {
+    if (!c || !out) return ckm_fail(CKM_EINVAL, "NULL argument");
+    if (!c->fam.loaded) return ckm_fail(CKM_ESTATE, "ckm_family_scores before ckm_family_load");
+    memset(out, 0, sizeof *out);
+    ckm_ctx::Family &F = c->fam;
+    uint64_t total = 0;
+    uint32_t max_len = 0;
+    RC(upload_batch(c, residues, offsets, n, &total, &max_len));
+    RC(run_device(c, (const uint8_t *)c->in_res.p, (const uint64_t *)c->in_off.p, n, total, std::max(max_len, 1u),
+                  CKM_WANT_HITS | CKM_WANT_CALLS | CKM_WANT_BEST));
+    RC(family_device(c, (const uint64_t *)c->in_off.p, n, total, true));
+    uint64_t ns = 0;
+    if (n) {
+        RC(prefix_sum(c, (const uint32_t *)F.snd.p, n, (uint64_t *)F.sout_off.p));
+        CU(cudaMemcpyAsync(&ns, (const uint64_t *)F.sout_off.p + n, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    RC(F.sout.ensure((ns + 1) * sizeof(ckm_score_t)));
+    RC(F.h_scores.ensure((ns + 1) * sizeof(ckm_score_t)));
+    RC(F.h_score_off.ensure(((size_t)n + 2) * 8));
+    RC(c->h_fam.ensure(((size_t)n + 1) * sizeof(ckm_family_match_t)));
+    RC(c->h_best.ensure(((size_t)n + 1) * sizeof(ckm_best_t)));
+    if (n) {
+        score_export_kernel<<<(unsigned)(((uint64_t)n * 32 + 255) / 256), 256, 0, c->stream>>>(
+            (const ckm_score_t *)F.sentries.p, (const uint64_t *)F.sofs.p, (const uint32_t *)F.snd.p, (const uint64_t *)F.sout_off.p, n,
+            (ckm_score_t *)F.sout.p);
+        c->launches++;
+        if (ns) CU(cudaMemcpyAsync(F.h_scores.p, F.sout.p, ns * sizeof(ckm_score_t), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(F.h_score_off.p, F.sout_off.p, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(c->h_fam.p, F.matches.p, (size_t)n * sizeof(ckm_family_match_t), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(c->h_best.p, c->best.p, (size_t)n * sizeof(ckm_best_t), cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        *(uint64_t *)F.h_score_off.p = 0;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    out->n = n;
+    out->scores = (const ckm_score_t *)F.h_scores.p;
+    out->score_offsets = (const uint64_t *)F.h_score_off.p;
+    out->best = (const ckm_best_t *)c->h_best.p;
+    out->matches = (const ckm_family_match_t *)c->h_fam.p;
     return 0;
 }
 

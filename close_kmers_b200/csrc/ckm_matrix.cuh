@@ -72,10 +72,10 @@ post_pack_kernel(const unsigned long long *__restrict__ tkeys, const uint32_t *_
 
 // capacity of row i's output region: it has at most min(E_i, i) distinct partners
 __global__ void __launch_bounds__(256)
-matrix_rowcap_kernel(const uint32_t *__restrict__ E, uint32_t n_rows, uint32_t row_begin, uint32_t *__restrict__ rcap) {
+matrix_rowcap_kernel(const uint32_t *__restrict__ E, uint32_t n_rows, uint32_t row_begin, uint32_t *__restrict__ rcap, bool filter) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
-    rcap[r] = min(E[r], row_begin + r);
+    rcap[r] = filter ? min(E[r], row_begin + r) : E[r];
 }
 
 constexpr int kMatWarps = 8;
@@ -87,7 +87,7 @@ matrix_row_kernel(const uint32_t *__restrict__ post_ids, const uint64_t *__restr
                   const uint32_t *__restrict__ gcap, const uint64_t *__restrict__ gofs, uint32_t *__restrict__ gscratch,
                   const uint32_t *__restrict__ eids /* whole request */, const uint32_t *__restrict__ first_idx, uint32_t max_eid,
                   uint32_t n_rows, uint32_t row_begin, const uint64_t *__restrict__ rofs, ckm_pair_t *__restrict__ entries,
-                  uint32_t *__restrict__ n_distinct) {
+                  uint32_t *__restrict__ n_distinct, bool filter) {
     extern __shared__ __align__(16) uint32_t mat_smem[];
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     uint32_t *const my = mat_smem + (size_t)wib * (2 * kFamSmemCap + 32 * kFamStage);
@@ -95,7 +95,7 @@ matrix_row_kernel(const uint32_t *__restrict__ post_ids, const uint64_t *__restr
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t r = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < n_rows; r += n_warps) {
         const uint32_t i = row_begin + r;  // index in the request
-        const uint32_t me = eids[i];
+        const uint32_t me = filter ? eids[i] : i;  // unfiltered (LookupRequest::on_hit, lookup_request.cc:466-478): row index
         const uint64_t base = offsets[r];
         const uint32_t nh = n_hits[r];
         uint32_t *keys, *cnt, cap;
@@ -124,7 +124,7 @@ matrix_row_kernel(const uint32_t *__restrict__ post_ids, const uint64_t *__restr
                     for (uint32_t t = lane; t < cnt_j; t += 32) {
                         const uint32_t e = t < (uint32_t)kFamStage ? s_stage[j][t] : post_ids[off_j + t];
                         // eid != id, and eid already in matrix_proteins_ (set at line 90 before protein i runs)
-                        if (e == me || e > max_eid || first_idx[e] > i) continue;
+                        if (filter && (e == me || e > max_eid || first_idx[e] > i)) continue;
                         bool fresh;
                         atomicAdd(&cnt[map_slot(keys, mask, e + 1, &fresh)], 1u);
                     }
@@ -157,14 +157,21 @@ matrix_row_kernel(const uint32_t *__restrict__ post_ids, const uint64_t *__restr
 
 __global__ void __launch_bounds__(256)
 matrix_export_kernel(const uint64_t *__restrict__ rofs, const ckm_pair_t *__restrict__ entries,
-                     const uint64_t *__restrict__ out_off, uint32_t n_rows, ckm_pair_t *__restrict__ out) {
+                     const uint64_t *__restrict__ out_off, uint32_t n_rows, ckm_pair_t *__restrict__ out, bool sorted) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (r >= n_rows) return;
     const uint64_t o0 = out_off[r];
     const uint32_t cnt = (uint32_t)(out_off[r + 1] - o0);
     const ckm_pair_t *src = entries + rofs[r];
-    for (uint32_t k = lane; k < cnt; k += 32) out[o0 + k] = src[k];
+    for (uint32_t k = lane; k < cnt; k += 32) {
+        uint32_t dst = k;
+        if (sorted) {  // rank by partner id (distinct within a row)
+            dst = 0;
+            for (uint32_t j = 0; j < cnt; j++) dst += src[j].eid_j < src[k].eid_j;
+        }
+        out[o0 + dst] = src[k];
+    }
 }
 
 }  // namespace ckm
@@ -227,6 +234,23 @@ extern "C" void ckm_postings_clear(ckm_ctx *c) {
 }
 extern "C" uint64_t ckm_postings_count(const ckm_ctx *c) { return c->post.n; }
 
+// One set of postings per KmerPegMapping: the server keeps one mapping per "/mapping/<key>" (krequest2.cc:440-456) and the
+// root mapping under key 0.  Selecting parks the current set and brings in (or creates) the requested one.
+extern "C" int ckm_postings_select(ckm_ctx *c, uint32_t key) {
+    if (!c) return ckm_fail(CKM_EINVAL, "ctx is NULL");
+    if (key == c->post_key) return 0;
+    c->post_store[c->post_key] = c->post;  // buffers are plain handles: the struct moves by value
+    auto it = c->post_store.find(key);
+    if (it == c->post_store.end()) {
+        c->post = ckm_ctx::Post();
+    } else {
+        c->post = it->second;
+        c->post_store.erase(it);
+    }
+    c->post_key = key;
+    return 0;
+}
+
 static int postings_index(ckm_ctx *c, ckm_ctx::Post &P) {
     if (!P.dirty) return 0;
     if (P.n >= (1ull << 32)) return ckm_fail(CKM_EINVAL, "more than 2^32 postings");
@@ -270,23 +294,25 @@ static int postings_index(ckm_ctx *c, ckm_ctx::Post &P) {
     return 0;
 }
 
-extern "C" int ckm_matrix_rows(ckm_ctx *c, const uint32_t *eids, const char *residues, const uint64_t *offsets, uint32_t n,
-                               uint32_t row_begin, uint32_t row_end, const ckm_pair_t **pairs, uint64_t *n_pairs) {
-    if (!c || !pairs || !n_pairs || (n && (!eids || !offsets))) return ckm_fail(CKM_EINVAL, "NULL argument");
-    *pairs = nullptr;
-    *n_pairs = 0;
-    if (row_end > n) row_end = n;
-    if (row_begin >= row_end) return 0;
+// rows [row_begin, row_end) of the request against the selected postings.  filter: the /matrix rules (partner != self and
+// already a member of matrix_proteins_); without it every posting of every hit counts (the /lookup peg mode), eid_i is the
+// row index, each row's pairs come out by ascending partner id and *h_off (if given) receives the CSR offsets.
+static int matrix_rows_impl(ckm_ctx *c, const uint32_t *eids, const char *residues, const uint64_t *offsets, uint32_t n,
+                            uint32_t row_begin, uint32_t row_end, bool filter, const ckm_pair_t **pairs, uint64_t *n_pairs,
+                            const uint64_t **h_off) {
     CU(cudaSetDevice(c->device));
     ckm_ctx::Post &P = c->post;
     RC(postings_index(c, c->post));
     const uint32_t n_rows = row_end - row_begin;
     // matrix_proteins_ membership: first request index of every id (matrix_request.cc:88-90)
     uint32_t max_eid = 0;
-    for (uint32_t i = 0; i < n; i++) max_eid = std::max(max_eid, eids[i]);
-    std::vector<uint32_t> first((size_t)max_eid + 1, 0xffffffffu);
-    for (uint32_t i = 0; i < n; i++)
-        if (first[eids[i]] == 0xffffffffu) first[eids[i]] = i;
+    std::vector<uint32_t> first(1, 0xffffffffu);
+    if (filter) {
+        for (uint32_t i = 0; i < n; i++) max_eid = std::max(max_eid, eids[i]);
+        first.assign((size_t)max_eid + 1, 0xffffffffu);
+        for (uint32_t i = 0; i < n; i++)
+            if (first[eids[i]] == 0xffffffffu) first[eids[i]] = i;
+    }
     RC(P.d_first.ensure(first.size() * 4));
     RC(P.d_eids.ensure(((size_t)n + 1) * 4));
     // the row block's sequences are the batch; hits only (calls == 0, otu == 0: matrix_request.cc:92-94)
@@ -294,7 +320,7 @@ extern "C" int ckm_matrix_rows(ckm_ctx *c, const uint32_t *eids, const char *res
     uint32_t max_len = 0;
     RC(upload_batch(c, residues, offsets + row_begin, n_rows, &total, &max_len));
     CU(cudaMemcpyAsync(P.d_first.p, first.data(), first.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(P.d_eids.p, eids, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    if (filter) CU(cudaMemcpyAsync(P.d_eids.p, eids, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
     RC(run_device(c, (const uint8_t *)c->in_res.p, (const uint64_t *)c->in_off.p, n_rows, total, std::max(max_len, 1u), CKM_WANT_HITS));
     ckm_ctx::Family &F = c->fam;  // per-batch lookup buffers are shared with the family path
     RC(F.hit_fam.ensure((total + 1) * sizeof(uint2)));
@@ -312,7 +338,7 @@ extern "C" int ckm_matrix_rows(ckm_ctx *c, const uint32_t *eids, const char *res
     fam_lookup_kernel<<<(unsigned)(((uint64_t)n_rows * 32 + 255) / 256), 256, 0, c->stream>>>(
         ft, (const uint64_t *)c->in_off.p, (const uint64_t *)c->hit_keys.p, (const uint32_t *)c->n_hits.p, n_rows,
         (uint2 *)F.hit_fam.p, (uint32_t *)F.E.p, (uint32_t *)F.gcap.p);
-    matrix_rowcap_kernel<<<(n_rows + 255) / 256, 256, 0, c->stream>>>((const uint32_t *)F.E.p, n_rows, row_begin, (uint32_t *)P.rcap.p);
+    matrix_rowcap_kernel<<<(n_rows + 255) / 256, 256, 0, c->stream>>>((const uint32_t *)F.E.p, n_rows, row_begin, (uint32_t *)P.rcap.p, filter);
     c->launches += 2;
     RC(prefix_sum(c, (const uint32_t *)F.gcap.p, n_rows, (uint64_t *)F.gofs.p));
     RC(prefix_sum(c, (const uint32_t *)P.rcap.p, n_rows, (uint64_t *)P.rofs.p));
@@ -331,7 +357,7 @@ extern "C" int ckm_matrix_rows(ckm_ctx *c, const uint32_t *eids, const char *res
         (const uint32_t *)P.ids.p, (const uint64_t *)c->in_off.p, (const uint32_t *)c->n_hits.p, (const uint2 *)F.hit_fam.p,
         (const uint32_t *)F.E.p, (const uint32_t *)F.gcap.p, (const uint64_t *)F.gofs.p, (uint32_t *)F.gscratch.p,
         (const uint32_t *)P.d_eids.p, (const uint32_t *)P.d_first.p, max_eid, n_rows, row_begin, (const uint64_t *)P.rofs.p,
-        (ckm_pair_t *)P.entries.p, (uint32_t *)P.nd.p);
+        (ckm_pair_t *)P.entries.p, (uint32_t *)P.nd.p, filter);
     c->launches++;
     RC(prefix_sum(c, (const uint32_t *)P.nd.p, n_rows, (uint64_t *)P.out_off.p));
     uint64_t np = 0;
@@ -340,14 +366,42 @@ extern "C" int ckm_matrix_rows(ckm_ctx *c, const uint32_t *eids, const char *res
     RC(P.out.ensure((np + 1) * sizeof(ckm_pair_t)));
     RC(P.h_out.ensure((np + 1) * sizeof(ckm_pair_t)));
     matrix_export_kernel<<<(unsigned)(((uint64_t)n_rows * 32 + 255) / 256), 256, 0, c->stream>>>(
-        (const uint64_t *)P.rofs.p, (const ckm_pair_t *)P.entries.p, (const uint64_t *)P.out_off.p, n_rows, (ckm_pair_t *)P.out.p);
+        (const uint64_t *)P.rofs.p, (const ckm_pair_t *)P.entries.p, (const uint64_t *)P.out_off.p, n_rows, (ckm_pair_t *)P.out.p, !filter);
     c->launches++;
     if (np) CU(cudaMemcpyAsync(P.h_out.p, P.out.p, np * sizeof(ckm_pair_t), cudaMemcpyDeviceToHost, c->stream));
+    if (h_off) {
+        RC(P.h_off.ensure(((size_t)n_rows + 2) * 8));
+        CU(cudaMemcpyAsync(P.h_off.p, P.out_off.p, ((size_t)n_rows + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+        *h_off = (const uint64_t *)P.h_off.p;
+    }
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
     *pairs = (const ckm_pair_t *)P.h_out.p;
     *n_pairs = np;
     return 0;
+}
+
+extern "C" int ckm_matrix_rows(ckm_ctx *c, const uint32_t *eids, const char *residues, const uint64_t *offsets, uint32_t n,
+                               uint32_t row_begin, uint32_t row_end, const ckm_pair_t **pairs, uint64_t *n_pairs) {
+    if (!c || !pairs || !n_pairs || (n && (!eids || !offsets))) return ckm_fail(CKM_EINVAL, "NULL argument");
+    *pairs = nullptr;
+    *n_pairs = 0;
+    if (row_end > n) row_end = n;
+    if (row_begin >= row_end) return 0;
+    return matrix_rows_impl(c, eids, residues, offsets, n, row_begin, row_end, true, pairs, n_pairs, nullptr);
+}
+
+// LookupRequest::on_hit without families (lookup_request.cc:466-478): seq_score_[eid].hit_count++ for every posting of
+// every hit k-mer.  pairs[k] = {sequence index, peg id, hit_count}, CSR by sequence, ascending peg id.
+extern "C" int ckm_postings_scores(ckm_ctx *c, const char *residues, const uint64_t *offsets, uint32_t n, const ckm_pair_t **pairs,
+                                   const uint64_t **pair_offsets) {
+    if (!c || !pairs || !pair_offsets || !offsets) return ckm_fail(CKM_EINVAL, "NULL argument");
+    static const uint64_t zero = 0;
+    *pairs = nullptr;
+    *pair_offsets = &zero;
+    if (n == 0) return 0;
+    uint64_t np = 0;
+    return matrix_rows_impl(c, nullptr, residues, offsets, n, 0, n, false, pairs, &np, pair_offsets);
 }
 
 

@@ -160,6 +160,12 @@ uint32_t ckm_mapping_encode_id(ckm_mapping *m, const char *peg) {  // kmer.cc:27
     m->id_to_peg.emplace_back(peg);
     return id;
 }
+uint32_t ckm_mapping_assign_new_id(ckm_mapping *m, const char *peg) {  // kmer.h:109-116: a fresh id even for a known peg
+    const uint32_t id = (uint32_t)m->id_to_peg.size();
+    m->peg_to_id[peg] = id;
+    m->id_to_peg.emplace_back(peg);
+    return id;
+}
 const char *ckm_mapping_decode_id(const ckm_mapping *m, uint32_t id) {  // kmer.cc:288-295
     return id < m->id_to_peg.size() ? m->id_to_peg[id].c_str() : "";
 }

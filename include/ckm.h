@@ -231,6 +231,24 @@ typedef struct {
 int ckm_family_batch(ckm_ctx *ctx, const char *residues, const uint64_t *offsets, uint32_t n,
                      const ckm_family_match_t **matches);
 
+/* LookupRequest's seq_score_ in family mode (lookup_request.h:26-45, lookup_request.cc:441-464): for every sequence, every
+ * family its hits touch with hit_count (== hit_total for the vector flavour of family_counts_t) and weighted_total (f32 sum
+ * of 1/|families of the k-mer| in hit order), ascending family id; plus find_best_call of the sequence and the
+ * ckm_family_batch match.  Arrays are owned by ctx and valid until its next call. */
+typedef struct {
+    uint32_t id;
+    uint32_t hit_count;
+    float weighted_total;
+} ckm_score_t;
+typedef struct {
+    uint32_t n;
+    const ckm_score_t *scores;
+    const uint64_t *score_offsets; /* n + 1 */
+    const ckm_best_t *best;
+    const ckm_family_match_t *matches;
+} ckm_family_scores_t;
+int ckm_family_scores(ckm_ctx *ctx, const char *residues, const uint64_t *offsets, uint32_t n, ckm_family_scores_t *out);
+
 const char *ckm_family_pgf_name(const ckm_ctx *ctx, int32_t gfam);   /* "" if out of range */
 const char *ckm_family_plf_name(const ckm_ctx *ctx, int32_t lfam);
 /* best_match_t::function for a match: function.index name or "hypothetical protein" */
@@ -285,6 +303,9 @@ int ckm_postings_add(ckm_ctx *ctx, const uint32_t *eids, const char *residues, c
 int ckm_postings_append_last(ckm_ctx *ctx, const uint32_t *eids, uint32_t n);
 void ckm_postings_clear(ckm_ctx *ctx);
 uint64_t ckm_postings_count(const ckm_ctx *ctx); /* (k-mer, peg) entries held */
+/* one set of postings per KmerPegMapping (the server's "/mapping/<key>" routes, krequest2.cc:440-456); key 0 is selected
+ * initially.  The other ckm_postings_* calls and ckm_matrix_rows act on the selected set. */
+int ckm_postings_select(ckm_ctx *ctx, uint32_t key);
 
 typedef struct {
     uint32_t eid_i; /* the protein being processed */
@@ -298,6 +319,12 @@ typedef struct {
  * selected rows are probed -- this is the unit of row-block sharding across GPUs. */
 int ckm_matrix_rows(ckm_ctx *ctx, const uint32_t *eids, const char *residues, const uint64_t *offsets, uint32_t n,
                     uint32_t row_begin, uint32_t row_end, const ckm_pair_t **pairs, uint64_t *n_pairs);
+
+/* LookupRequest::on_hit without families (lookup_request.cc:466-478): for every sequence of the batch, the pegs of the
+ * selected postings that share a hit k-mer with it and how many postings did (seq_score_[eid].hit_count).  pairs[k] =
+ * {eid_i = sequence index in the batch, eid_j = peg id, count}; pair_offsets has n + 1 entries; pegs ascending per sequence. */
+int ckm_postings_scores(ckm_ctx *ctx, const char *residues, const uint64_t *offsets, uint32_t n, const ckm_pair_t **pairs,
+                        const uint64_t **pair_offsets);
 
 /* ---- image builder: KmerGuts(dir, nbuckets) + insert_kmer + save_kmer_hash_table (kguts.cc:77-115, 188-234).
  * Host-side; writes the reference's file bytes (header + nbuckets slots) into image_out, which must be

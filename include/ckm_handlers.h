@@ -28,6 +28,8 @@ typedef struct ckm_mapping ckm_mapping;
 ckm_mapping *ckm_mapping_new(void);
 void ckm_mapping_free(ckm_mapping *m);
 uint32_t ckm_mapping_encode_id(ckm_mapping *m, const char *peg);
+/* assign_new_peg_id (kmer.h:109-116), what load_families uses: always a fresh id; the name then maps to the newest one */
+uint32_t ckm_mapping_assign_new_id(ckm_mapping *m, const char *peg);
 const char *ckm_mapping_decode_id(const ckm_mapping *m, uint32_t id); /* "" when unknown */
 
 /* POST /add (add_request.cc:102-170): unless `silent`, "PROTEIN-ID", "CALL" lines, "OTU-COUNTS" and a

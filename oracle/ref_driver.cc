@@ -20,6 +20,8 @@
 #include "dna_seq.h"
 #include "kmer.h"
 #include "family_mapper.h"
+#include "fasta_parser.h"
+#include "fastq_parser.h"
 
 #include <chrono>
 #include <cstdint>
@@ -456,6 +458,38 @@ void ref_family_table(void *hv, uint64_t *kmers, uint64_t *fam_off, uint32_t *id
 void ref_family_clear(void *hv) {
     RefHandle *h = (RefHandle *)hv;
     if (h->mapping) h->mapping->kmer_to_family_id_.clear();
+}
+
+// The handlers' body parsing: parser_.parse_char over every byte of every packet, parse_complete after the last one
+// (query_request.cc:52-64, fq_process_request.cc:255-267).  `cuts` are the packet boundaries.  Each callback is dumped
+// as "<id length> <seq length>\n<id><seq>\n" so that any byte may appear in an id.
+char *ref_parse_text(int fastq, const char *text, uint64_t n, const uint64_t *cuts, uint32_t n_cuts, uint64_t *n_seqs) {
+    std::ostringstream os;
+    uint64_t count = 0;
+    auto cb = [&os, &count](const std::string &id, const std::string &seq) {
+        os << id.size() << " " << seq.size() << "\n" << id << seq << "\n";
+        count++;
+        return 0;
+    };
+    std::streambuf *old = std::cerr.rdbuf(nullptr);  // "Error found: ..." lines
+    FastaParser fa;
+    FastqParser fq;
+    fa.set_callback(cb);
+    fq.set_callback(cb);
+    uint64_t pos = 0;
+    for (uint32_t c = 0; c <= n_cuts; c++) {
+        const uint64_t end = c < n_cuts ? cuts[c] : n;
+        for (; pos < end; pos++) {
+            if (fastq) fq.parse_char(text[pos]);
+            else fa.parse_char(text[pos]);
+        }
+    }
+    if (fastq) fq.parse_complete();
+    else fa.parse_complete();
+    std::cerr.rdbuf(old);
+    std::cerr.clear();
+    if (n_seqs) *n_seqs = count;
+    return dup_text(os.str());
 }
 
 static void put_match(std::ostringstream &os, const FamilyMapper::best_match_t &b) { os << b; }

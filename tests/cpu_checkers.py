@@ -97,6 +97,18 @@ def _cstr_array(strs):
     return arr
 
 
+def parse_dump(raw: bytes, n: int):
+    out, pos = [], 0
+    for _ in range(n):
+        nl = raw.index(b"\n", pos)
+        a, b = (int(x) for x in raw[pos:nl].split())
+        pos = nl + 1
+        out.append((raw[pos:pos + a], raw[pos + a:pos + a + b]))
+        pos += a + b + 1
+    assert pos == len(raw)
+    return out
+
+
 class Ref:
     """The reference's own code.  Chatty on stdout/stderr (its own prints)."""
 
@@ -144,6 +156,8 @@ class Ref:
         L.ref_family_table_size.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.ref_family_table.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_family_clear.argtypes = [C.c_void_p]
+        L.ref_parse_text.restype = C.c_void_p
+        L.ref_parse_text.argtypes = [C.c_int, C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]
         L.ref_family_text.restype = C.c_void_p
         L.ref_family_text.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         L.ref_family_batch.restype = C.c_void_p
@@ -258,6 +272,15 @@ class Ref:
         fam_ids = np.ascontiguousarray(fam_ids, np.uint32)
         self.L.ref_family_load(self.h, len(kmers), kmers.ctypes.data, fam_off.ctypes.data, fam_ids.ctypes.data, len(pgf),
                                _cstr_array(pgf), _cstr_array(plf), _cstr_array(function))
+
+    def parse_text(self, fastq: bool, text: bytes, cuts=()):
+        """Reference FastaParser / FastqParser over `text` fed packet by packet; returns [(id, seq)] as bytes."""
+        cuts = np.ascontiguousarray(sorted(cuts), np.uint64)
+        n = C.c_uint64()
+        p = self.L.ref_parse_text(int(fastq), text, len(text), cuts.ctypes.data, len(cuts), C.byref(n))
+        raw = C.string_at(p)  # ids / sequences never contain NUL here
+        self.L.ref_free_text(C.c_void_p(p))
+        return parse_dump(raw, n.value)
 
     # NRLoader::thread_load in family mode (+ KmerInserter + add_fam_mapping) for one chunk
     def family_nr_add(self, fam_ids, batch):

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def declared_symbols():
     names = set()
-    for h in ("ckm.h", "ckm_handlers.h"):
+    for h in ("ckm.h", "ckm_handlers.h", "ckm_server.h"):
         text = open(os.path.join(ROOT, "include", h)).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
         for m in re.finditer(r"\b(ckm_[a-z0-9_]+)\s*\(", text):
