@@ -219,6 +219,23 @@ def merge_pairs(pairs: np.ndarray) -> np.ndarray:
     return pairs[:n]
 
 
+SCORE_DT = np.dtype([("id", "<u4"), ("hit_count", "<u4"), ("weighted_total", "<f4")])
+
+
+class FamilyScoresC(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("scores", C.c_void_p), ("score_offsets", C.c_void_p), ("best", C.c_void_p), ("matches", C.c_void_p)]
+
+
+class FamilyDataC(C.Structure):
+    _fields_ = [("pgf", C.c_char_p), ("plf", C.c_char_p), ("function", C.c_char_p), ("genus_id", C.c_uint64), ("total_size", C.c_uint64),
+                ("count", C.c_uint16)]
+
+
+class LookupOptionsC(C.Structure):
+    _fields_ = [("family_mode", C.c_int), ("kmer_hit_threshold", C.c_uint), ("find_best_match", C.c_int), ("find_reps", C.c_int),
+                ("allow_ambiguous_functions", C.c_int), ("target_genus_id", C.c_uint64)]
+
+
 class SeqBatchC(C.Structure):
     _fields_ = [("n", C.c_uint32), ("ids", C.POINTER(C.c_char_p)), ("residues", C.c_void_p), ("offsets", C.POINTER(C.c_uint64)),
                 ("n_errors", C.c_uint64)]
@@ -492,6 +509,57 @@ class KmerGuts:
         ids = np.zeros(max(n_entries, 1), np.uint32)
         _check(lib().ckm_family_export(self._h, n_kmers, n_entries, k.ctypes.data, o.ctypes.data, ids.ctypes.data))
         return canonical_family_csr(k, o, ids[:n_entries])
+
+    def family_scores(self, residues, offsets) -> dict:
+        """LookupRequest's per-sequence (family, hit_count, weighted_total) lists + best call + FamilyMapper match."""
+        residues = np.ascontiguousarray(residues, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        n = len(offsets) - 1
+        L = lib()
+        L.ckm_family_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(FamilyScoresC)]
+        o = FamilyScoresC()
+        _check(L.ckm_family_scores(self._h, residues.ctypes.data, offsets.ctypes.data, n, C.byref(o)))
+        off = _arr(o.score_offsets, n + 1, np.dtype("<u8"))
+        return dict(score_offsets=off, scores=_arr(o.scores, int(off[-1]), SCORE_DT), best=_arr(o.best, n, BEST_DT),
+                    matches=_arr(o.matches, n, FAMILY_DT))
+
+    def postings_scores(self, residues, offsets) -> tuple:
+        """(pairs, pair_offsets): per sequence, the pegs of the selected postings sharing hit k-mers, with counts."""
+        residues = np.ascontiguousarray(residues, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        n = len(offsets) - 1
+        L = lib()
+        L.ckm_postings_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        p, po = C.c_void_p(), C.c_void_p()
+        _check(L.ckm_postings_scores(self._h, residues.ctypes.data, offsets.ctypes.data, n, C.byref(p), C.byref(po)))
+        off = _arr(po.value, n + 1, np.dtype("<u8"))
+        return _arr(p.value, int(off[-1]), PAIR_DT), off
+
+    def postings_select(self, key: int):
+        L = lib()
+        L.ckm_postings_select.argtypes = [C.c_void_p, C.c_uint32]
+        _check(L.ckm_postings_select(self._h, key))
+
+    def lookup_text(self, ids, residues, offsets, families=None, mapping=None, family_mode=True, kmer_hit_threshold=3,
+                    find_best_match=False, find_reps=False, allow_ambiguous_functions=False, target_genus_id=0) -> str:
+        """POST /lookup for one chunk.  families: list of (pgf, plf, function, genus_id, total_size, count)."""
+        residues = np.ascontiguousarray(residues, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        fams = families or []
+        arr = (FamilyDataC * max(len(fams), 1))()
+        for k, f in enumerate(fams):
+            arr[k] = FamilyDataC(f[0].encode(), f[1].encode(), f[2].encode(), f[3], f[4], f[5])
+        opt = LookupOptionsC(int(family_mode), kmer_hit_threshold, int(find_best_match), int(find_reps), int(allow_ambiguous_functions),
+                             target_genus_id)
+        bs = [s.encode() if isinstance(s, str) else s for s in ids]
+        idarr = (C.c_char_p * max(len(bs), 1))(*bs)
+        L = lib()
+        L.ckm_lookup_text.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_uint32, C.POINTER(C.c_void_p)]
+        t = C.c_void_p()
+        _check(L.ckm_lookup_text(self._h, mapping._m if mapping is not None else None, arr, len(fams), C.byref(opt), idarr,
+                                 residues.ctypes.data, offsets.ctypes.data, len(offsets) - 1, C.byref(t)))
+        return self._take_text(t)
 
     def find_best_family_match_batch(self, residues, offsets) -> np.ndarray:
         """FamilyMapper::find_best_family_match (family_mapper.cc:65-205) for every sequence."""

@@ -613,7 +613,8 @@ void handle_post(Server &s, Conn &c, const Request &r, const Decision &d) {
             return 0;
         }
     }() : 0;
-    ckm_lookup::Options lopt;
+    ckm_lookup_options_t lopt;
+    memset(&lopt, 0, sizeof lopt);
     if (is_lookup) lopt = ckm_lookup::options_from(r, s.fams, s.family_mode);
 
     ckm_seq_parser *parser = ckm_seq_parser_new(is_fq ? CKM_FORMAT_FASTQ : CKM_FORMAT_FASTA);
@@ -666,9 +667,9 @@ void handle_post(Server &s, Conn &c, const Request &r, const Decision &d) {
                 rc = ckm_fq_text(e.ctx, b.ids, b.residues, b.offsets, b.n, &text);
             } else {
                 if (!s.family_mode) rc = ckm_postings_select(e.ctx, mapping.post_key);
-                std::string t;
-                if (!rc) rc = ckm_lookup::lookup_text(e.ctx, mapping.ids, s.fams, lopt, b, t);
-                out += t;
+                if (!rc)
+                    rc = ckm_lookup_text(e.ctx, mapping.ids, s.fams.flat.data(), (uint32_t)s.fams.flat.size(), &lopt, b.ids, b.residues,
+                                         b.offsets, b.n, &text);
             }
         }
         if (rc) {
@@ -812,6 +813,7 @@ extern "C" int ckm_kser_main(int argc, char **argv) {
         if (load_nr_file(s, f, s.opt.families_nr.size())) return 1;
     }
     if (install_families(s)) return 1;
+    s.fams.flatten();
     if (s.opt.no_listen) {
         std::cerr << "Quitting due to --no-listen being set\n";
         return 0;

@@ -6,13 +6,16 @@
 #include "lookup.h"
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <sstream>
 #include <stdexcept>
 
 namespace ckm_lookup {
 
-Options options_from(const ckm_http::Request &r, const FamilyInfo &fams, bool family_mode) {
-    Options o;
+ckm_lookup_options_t options_from(const ckm_http::Request &r, const FamilyInfo &fams, bool family_mode) {
+    ckm_lookup_options_t o;
+    memset(&o, 0, sizeof o);
     o.family_mode = family_mode;
     auto take = [&r](const char *name, int &v) {
         try {
@@ -43,11 +46,9 @@ Options options_from(const ckm_http::Request &r, const FamilyInfo &fams, bool fa
     return o;
 }
 
-static std::string seq_id(const ckm_seq_batch_t &b, uint32_t i) { return b.ids[i]; }
-
 // find_best_match && family_mode, lookup_request.cc:201-327
-static void best_match_line(std::ostream &os, ckm_ctx *ctx, const FamilyInfo &fams, const Options &o, const std::string &id,
-                            const ckm_score_t *sc, uint64_t n, const ckm_best_t &best) {
+static void best_match_line(std::ostream &os, ckm_ctx *ctx, const ckm_family_data_t *fams, uint32_t n_fams, const ckm_lookup_options_t &o,
+                            const char *id, const ckm_score_t *sc, uint64_t n, const ckm_best_t &best) {
     char *fn = ckm_best_function(ctx, &best);
     std::string best_call_function = fn ? fn : "";
     ckm_free_text(fn);
@@ -75,10 +76,10 @@ static void best_match_line(std::ostream &os, ckm_ctx *ctx, const FamilyInfo &fa
     std::map<std::string, float> pgf_rollup, pgf_rollup_ambig;
     for (uint64_t k = 0; k < n; k++) {
         if (sc[k].hit_count < o.kmer_hit_threshold) continue;  // hit_total == hit_count
-        if (sc[k].id >= fams.data.size()) continue;
-        const FamilyData &fd = fams.data[sc[k].id];
-        if (fd.function == best_call_function) pgf_rollup[fd.pgf] += sc[k].weighted_total;
-        else if (do_ambig_test && fd.function == ambig_function) pgf_rollup_ambig[fd.pgf] += sc[k].weighted_total;
+        if (sc[k].id >= n_fams) continue;
+        const ckm_family_data_t &fd = fams[sc[k].id];
+        if (best_call_function == fd.function) pgf_rollup[fd.pgf] += sc[k].weighted_total;
+        else if (do_ambig_test && ambig_function == fd.function) pgf_rollup_ambig[fd.pgf] += sc[k].weighted_total;
         else continue;
         if (sc[k].weighted_total > best_lf.score && fd.genus_id == o.target_genus_id) {
             best_lf.score = sc[k].weighted_total;
@@ -97,28 +98,36 @@ static void best_match_line(std::ostream &os, ckm_ctx *ctx, const FamilyInfo &fa
        << (do_ambig_test ? best_lf.function : best_call_function) << "\t" << best.score << "\t" << best.weighted_score << "\n";
 }
 
-int lookup_text(ckm_ctx *ctx, ckm_mapping *pegs, const FamilyInfo &fams, const Options &o, const ckm_seq_batch_t &b, std::string &out) {
+}  // namespace ckm_lookup
+
+extern "C" int ckm_lookup_text(ckm_ctx *ctx, ckm_mapping *pegs, const ckm_family_data_t *fams, uint32_t n_fams,
+                               const ckm_lookup_options_t *opt, const char *const *ids, const char *residues, const uint64_t *offsets,
+                               uint32_t n, char **text) {
+    using namespace ckm_lookup;
+    if (!text || !opt) return CKM_EINVAL;
+    *text = nullptr;
+    const ckm_lookup_options_t &o = *opt;
     std::ostringstream os;
     if (o.family_mode) {
         ckm_family_scores_t fs;
-        int rc = ckm_family_scores(ctx, b.residues, b.offsets, b.n, &fs);
+        int rc = ckm_family_scores(ctx, residues, offsets, n, &fs);
         if (rc) return rc;
         std::vector<ckm_score_t> vec;
-        for (uint32_t i = 0; i < b.n; i++) {
+        for (uint32_t i = 0; i < n; i++) {
             const ckm_score_t *sc = fs.scores + fs.score_offsets[i];
-            const uint64_t n = fs.score_offsets[i + 1] - fs.score_offsets[i];
+            const uint64_t ns = fs.score_offsets[i + 1] - fs.score_offsets[i];
             if (o.find_best_match) {
-                best_match_line(os, ctx, fams, o, seq_id(b, i), sc, n, fs.best[i]);
+                best_match_line(os, ctx, fams, n_fams, o, ids[i], sc, ns, fs.best[i]);
                 continue;
             }
             // every family, best weighted_total first, up to the first one under the hit threshold (329-377)
-            vec.assign(sc, sc + n);
+            vec.assign(sc, sc + ns);
             std::stable_sort(vec.begin(), vec.end(), [](const ckm_score_t &l, const ckm_score_t &r) { return l.weighted_total > r.weighted_total; });
-            os << seq_id(b, i) << "\n";
+            os << ids[i] << "\n";
             for (const auto &e : vec) {
                 if (e.hit_count < o.kmer_hit_threshold) break;
-                static const FamilyData none{"", "", "", 0, 0, 0};
-                const FamilyData &fd = e.id < fams.data.size() ? fams.data[e.id] : none;
+                static const ckm_family_data_t none = {"", "", "", 0, 0, 0};
+                const ckm_family_data_t &fd = e.id < n_fams ? fams[e.id] : none;
                 const float scaled = (float)e.hit_count / (float)fd.total_size;
                 os << e.hit_count << "\t" << e.hit_count << "\t" << e.weighted_total << "\t" << fd.pgf << "\t" << fd.plf << "\t" << fd.total_size
                    << "\t" << fd.count << "\t" << scaled << "\t" << fd.function << "\n";
@@ -132,19 +141,22 @@ int lookup_text(ckm_ctx *ctx, ckm_mapping *pegs, const FamilyInfo &fams, const O
         const ckm_pair_t *pairs = nullptr;
         const uint64_t *poff = nullptr;
         if (o.kmer_hit_threshold == 0) {
-            int rc = ckm_postings_scores(ctx, b.residues, b.offsets, b.n, &pairs, &poff);
+            if (!pegs) return CKM_EINVAL;
+            int rc = ckm_postings_scores(ctx, residues, offsets, n, &pairs, &poff);
             if (rc) return rc;
         }
-        for (uint32_t i = 0; i < b.n; i++) {
-            os << seq_id(b, i) << "\n";
+        for (uint32_t i = 0; i < n; i++) {
+            os << ids[i] << "\n";
             if (pairs)
                 for (uint64_t k = poff[i]; k < poff[i + 1]; k++)
                     os << ckm_mapping_decode_id(pegs, pairs[k].eid_j) << "\t" << pairs[k].count << "\n";
             os << "//\n";
         }
     }
-    out += os.str();
+    const std::string s = os.str();
+    char *p = (char *)malloc(s.size() + 1);
+    if (!p) return CKM_ENOMEM;
+    memcpy(p, s.data(), s.size() + 1);
+    *text = p;
     return 0;
 }
-
-}  // namespace ckm_lookup

@@ -22,19 +22,15 @@ struct FamilyData {  // KmerPegMapping::family_data_t, kmer.h:58-68
 struct FamilyInfo {
     std::vector<FamilyData> data;                // family_data_, by encoded family id
     std::map<std::string, std::string> genus_map;  // genus_map_
+    std::vector<ckm_family_data_t> flat;         // `data` as the C ABI takes it (pointers into `data`)
+    void flatten() {
+        flat.clear();
+        for (const auto &f : data) flat.push_back({f.pgf.c_str(), f.plf.c_str(), f.function.c_str(), f.genus_id, f.total_size, f.count});
+    }
 };
 
-struct Options {  // LookupRequest's members, lookup_request.cc:36-80
-    bool family_mode = false;
-    unsigned int kmer_hit_threshold = 3;
-    bool find_best_match = false, find_reps = false, allow_ambiguous_functions = false;
-    unsigned long target_genus_id = 0;
-};
-
-Options options_from(const ckm_http::Request &r, const FamilyInfo &fams, bool family_mode);
-
-// the response text of one batch (lookup_request.cc:155-400), appended to `out`
-int lookup_text(ckm_ctx *ctx, ckm_mapping *pegs, const FamilyInfo &fams, const Options &o, const ckm_seq_batch_t &b, std::string &out);
+// LookupRequest's constructor, lookup_request.cc:36-80
+ckm_lookup_options_t options_from(const ckm_http::Request &r, const FamilyInfo &fams, bool family_mode);
 
 }  // namespace ckm_lookup
 #endif

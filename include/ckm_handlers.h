@@ -54,6 +54,32 @@ uint64_t ckm_matrix_merge_pairs(ckm_pair_t *pairs, uint64_t n_pairs);
  * reads with an empty id are skipped.  Needs ckm_family_load. */
 int ckm_fq_text(ckm_ctx *ctx, const char *const *ids, const char *bases, const uint64_t *offsets, uint32_t n, char **text);
 
+/* POST /lookup (lookup_request.cc:132-400).  Options are the LookupRequest members its constructor reads from the request
+ * parameters ("kmer_hit_threhsold" [sic], find_best_match, find_reps, allow_ambiguous_functions, target_genus via
+ * genus_map_).  fams[f] is family_data_[f] (kmer.h:58-68).
+ *   family_mode && find_best_match: one line per sequence "<id>\t<best PGF>\t<score>\t<best PLF of the target genus>\t<score>\t
+ *     <function>\t<best call score>\t<weighted>\n" (201-327);
+ *   family_mode: "<id>\n", then per family, best weighted_total first and stopping at the first one under the hit threshold,
+ *     "<hits>\t<hits>\t<weighted>\t<pgf>\t<plf>\t<total_size>\t<count>\t<hits/total_size>\t<function>\n" (+ "///\n" with find_reps),
+ *     then "//\n" (329-377);
+ *   otherwise (peg mode): "<id>\n", "<peg>\t<hit count>\n" per peg of the mapping's postings -- only when the threshold is 0,
+ *     because that mode never increments hit_total (466-478) -- then "//\n".
+ * Where the reference leaves an order to std::unordered_map iteration or to std::sort on equal keys (tied weighted_total,
+ * the order of the PGF roll-up's f32 additions), ids ascend here. */
+typedef struct {
+    const char *pgf, *plf, *function;
+    uint64_t genus_id, total_size;
+    uint16_t count;
+} ckm_family_data_t;
+typedef struct {
+    int family_mode;
+    unsigned int kmer_hit_threshold; /* default 3 */
+    int find_best_match, find_reps, allow_ambiguous_functions;
+    uint64_t target_genus_id;
+} ckm_lookup_options_t;
+int ckm_lookup_text(ckm_ctx *ctx, ckm_mapping *m, const ckm_family_data_t *fams, uint32_t n_fams, const ckm_lookup_options_t *opt,
+                    const char *const *ids, const char *residues, const uint64_t *offsets, uint32_t n, char **text);
+
 /* FamilyMapper::find_best_family_match as text, one "<gfam>\t<gscore>\t<lfam>\t<lscore>\t<function>\t<score>\n"
  * line per sequence (operator<< of best_match_t, family_mapper.h:70-75) */
 int ckm_family_text(ckm_ctx *ctx, const char *residues, const uint64_t *offsets, uint32_t n, char **text);

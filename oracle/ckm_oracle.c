@@ -602,6 +602,46 @@ void orc_family_batch(const orc_table *t, const orc_params_t *p, const orc_famil
     free(hit_total); free(weighted); free(seen); free(rollup); free(pseen);
 }
 
+/* LookupRequest::on_hit in family mode (lookup_request.cc:441-464): per sequence, every family touched with hit_count and
+ * weighted_total (f32 sum of 1/|list| in hit order), ascending family id; *scores / *score_off are malloc'ed. */
+void orc_family_scores(const orc_table *t, const orc_params_t *p, const orc_family *f, const char *residues,
+                       const uint64_t *offsets, uint32_t n, ckm_score_t **scores, uint64_t **score_off) {
+    uint32_t *hit_count = calloc(f->n_fams ? f->n_fams : 1, 4);
+    float *weighted = calloc(f->n_fams ? f->n_fams : 1, 4);
+    uint64_t cap = 1024, ns = 0;
+    ckm_score_t *out = malloc(cap * sizeof *out);
+    uint64_t *off = malloc(((size_t)n + 1) * 8);
+    off[0] = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        uint64_t off2[2] = {0, offsets[i + 1] - offsets[i]};
+        orc_out_t *o = orc_call_batch(t, p, residues + offsets[i], off2, 1, CKM_WANT_HITS);
+        for (uint64_t h = 0; h < o->o.hit_offsets[1]; h++) {
+            int64_t ki = fam_find(f, o->o.hits[h].which_kmer);
+            if (ki < 0) continue;
+            uint32_t cnt = f->perm_cnt[ki];
+            float weight = 1.0f / (float)cnt;
+            for (uint32_t e = 0; e < cnt; e++) {
+                uint32_t fam = f->fam_ids[f->perm_off[ki] + e];
+                if (fam >= f->n_fams) continue;
+                hit_count[fam]++;
+                weighted[fam] += weight;
+            }
+        }
+        for (uint32_t fam = 0; fam < f->n_fams; fam++) {
+            if (!hit_count[fam]) continue;
+            if (ns == cap) out = realloc(out, (cap *= 2) * sizeof *out);
+            out[ns++] = (ckm_score_t){fam, hit_count[fam], weighted[fam]};
+            hit_count[fam] = 0;
+            weighted[fam] = 0;
+        }
+        off[i + 1] = ns;
+        orc_out_free(o);
+    }
+    free(hit_count); free(weighted);
+    *scores = out;
+    *score_off = off;
+}
+
 /* ---- D1: TranslationTable, trans_table.cc:8-63.  NCBI genetic code 11 listed in TCAG order; the table is
  * re-indexed by encode_triple (A=0,C=1,G=2,T/U=3 -> 16*b1+4*b2+b3), slot 64 = 'X' for ambiguous codons ---- */
 static const char NCBI11_AAS[65] = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";

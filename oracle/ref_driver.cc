@@ -460,6 +460,176 @@ void ref_family_clear(void *hv) {
     if (h->mapping) h->mapping->kmer_to_family_id_.clear();
 }
 
+// family_data_t fields ref_family_load leaves at zero: genus_id, total_size, count (kmer.h:58-68)
+void ref_family_set_extra(void *hv, uint32_t n_fams, const uint64_t *genus_id, const uint64_t *total_size, const uint16_t *count) {
+    RefHandle *h = (RefHandle *)hv;
+    for (uint32_t f = 0; f < n_fams; f++) {
+        auto &d = h->mapping->family_data_[f];
+        d.genus_id = genus_id[f];
+        d.total_size = total_size[f];
+        d.count = count[f];
+    }
+}
+
+// POST /lookup: the worker lambda of LookupRequest::on_data (lookup_request.cc:138-400) with on_hit (441-481), restated
+// over the reference's KmerGuts / KmerPegMapping because lookup_request.cc itself needs Boost.Asio.  seq_score_ is the
+// same std::unordered_map<encoded_id_t, sequence_accumulated_score_t>, the listing uses the same std::sort.
+namespace {
+struct sequence_accumulated_score_t {  // lookup_request.h:26-44
+    unsigned int hit_count;
+    unsigned int hit_total;
+    float weighted_total;
+    inline void increment(KmerPegMapping::encoded_family_id_t val, float weight) {
+        hit_count++;
+        hit_total++;
+        weighted_total += weight;
+    }
+};
+}  // namespace
+
+char *ref_lookup_text(void *hv, const char *const *ids, const char *residues, const uint64_t *offsets, uint32_t n, int family_mode,
+                      unsigned int kmer_hit_threshold, int find_best_match, int find_reps, int allow_ambiguous_functions,
+                      uint64_t target_genus_id) {
+    RefHandle *h = (RefHandle *)hv;
+    KmerGuts *kguts = h->guts[0];
+    kguts->set_parameters(h->params);
+    if (!h->mapping) h->mapping = std::make_shared<KmerPegMapping>();
+    std::shared_ptr<KmerPegMapping> mapping_ = h->mapping;
+    std::unordered_map<KmerPegMapping::encoded_id_t, sequence_accumulated_score_t> seq_score_;
+    std::ostringstream os;
+    auto on_hit = [&](KmerGuts::hit_in_sequence_t kmer) {
+        if (family_mode) {
+            auto ki = mapping_->kmer_to_family_id_.find(kmer.hit.which_kmer);
+            if (ki != mapping_->kmer_to_family_id_.end()) {
+                KmerPegMapping::family_counts_t &counts = ki->second;
+                float weight = 1.0f / (float)counts.size();
+                for (KmerPegMapping::encoded_family_id_t ent : ki->second) {
+                    sequence_accumulated_score_t &s = seq_score_[ent];
+                    s.increment(ent, weight);
+                }
+            }
+        } else {
+            auto ki = mapping_->kmer_to_id_.find(kmer.hit.which_kmer);
+            if (ki != mapping_->kmer_to_id_.end())
+                for (auto eid : ki->second) seq_score_[eid].hit_count++;
+        }
+    };
+    for (uint32_t w = 0; w < n; w++) {
+        std::string id = ids[w];
+        std::string seq = seq_at(residues, offsets, w);
+        seq_score_.clear();
+        typedef std::vector<KmerCall> call_vector_t;
+        std::shared_ptr<call_vector_t> calls = 0;
+        if (find_best_match && family_mode) calls = std::make_shared<call_vector_t>();
+        kguts->process_aa_seq(id, seq, calls, on_hit, 0);
+        if (find_best_match && family_mode) {
+            int best_call_fi;
+            float best_call_score, best_call_score_offset;
+            std::string best_call_function;
+            float best_call_weighted_score;
+            kguts->find_best_call(*calls, best_call_fi, best_call_function, best_call_score, best_call_weighted_score,
+                                  best_call_score_offset);
+            std::string ambig_function;
+            bool do_ambig_test = false;
+            if (best_call_function.empty())
+                best_call_function = "hypothetical protein";
+            else {
+                size_t where = best_call_function.find(" ?? ");
+                if (where != std::string::npos) {
+                    if (allow_ambiguous_functions) {
+                        ambig_function = best_call_function.substr(where + 4);
+                        best_call_function = best_call_function.substr(0, where);
+                        do_ambig_test = true;
+                    } else {
+                        best_call_function = "hypothetical protein";
+                    }
+                }
+            }
+            struct top_score {
+                float score;
+                std::string fam;
+                std::string function;
+            };
+            top_score best_lf({0.0});
+            top_score best_gf({0.0});
+            std::unordered_map<std::string, float> pgf_rollup, pgf_rollup_ambig;
+            for (auto hit_ent : seq_score_) {
+                KmerPegMapping::encoded_id_t eid = hit_ent.first;
+                const sequence_accumulated_score_t &score_ent = hit_ent.second;
+                if (score_ent.hit_total < kmer_hit_threshold) continue;
+                auto fent = mapping_->family_data_.find(eid);
+                if (fent == mapping_->family_data_.end()) continue;
+                const KmerPegMapping::family_data_t &fam_data = fent->second;
+                if (do_ambig_test) {
+                    if (fam_data.function == best_call_function)
+                        pgf_rollup[fam_data.pgf] += score_ent.weighted_total;
+                    else if (fam_data.function == ambig_function)
+                        pgf_rollup_ambig[fam_data.pgf] += score_ent.weighted_total;
+                    else
+                        continue;
+                } else {
+                    if (fam_data.function == best_call_function)
+                        pgf_rollup[fam_data.pgf] += score_ent.weighted_total;
+                    else
+                        continue;
+                }
+                if (score_ent.weighted_total > best_lf.score && fam_data.genus_id == target_genus_id) {
+                    best_lf.score = score_ent.weighted_total;
+                    best_lf.fam = fam_data.plf;
+                    best_lf.function = fam_data.function;
+                }
+            }
+            std::unordered_map<std::string, float> *matching_rollup = &pgf_rollup;
+            if (do_ambig_test && best_lf.function == ambig_function) matching_rollup = &pgf_rollup_ambig;
+            for (auto pgf_ent : *matching_rollup) {
+                const std::string &pgf = pgf_ent.first;
+                const float &score = pgf_ent.second;
+                if (score > best_gf.score) {
+                    best_gf.score = score;
+                    best_gf.fam = pgf;
+                }
+            }
+            os << id << "\t" << best_gf.fam << "\t" << best_gf.score << "\t" << best_lf.fam << "\t" << best_lf.score << "\t"
+               << (do_ambig_test ? best_lf.function : best_call_function) << "\t" << best_call_score << "\t"
+               << best_call_weighted_score << "\n";
+        } else {
+            typedef std::pair<KmerPegMapping::encoded_id_t, sequence_accumulated_score_t> data_t;
+            std::vector<data_t> vec;
+            for (auto it : seq_score_) vec.push_back(it);
+            std::sort(vec.begin(), vec.end(),
+                      [](const data_t &lhs, const data_t &rhs) { return lhs.second.weighted_total > rhs.second.weighted_total; });
+            os << id << "\n";
+            for (auto it : vec) {
+                auto eid = it.first;
+                const sequence_accumulated_score_t &score_ent = it.second;
+                if (score_ent.hit_total < kmer_hit_threshold) break;
+                if (family_mode) {
+                    unsigned int score = score_ent.hit_count;
+                    unsigned int total = score_ent.hit_total;
+                    float weighted = score_ent.weighted_total;
+                    auto fent = mapping_->family_data_[eid];
+                    float scaled = (float)score / (float)fent.total_size;
+                    os << score << "\t" << total << "\t" << weighted << "\t" << fent.pgf << "\t" << fent.plf << "\t" << fent.total_size
+                       << "\t" << fent.count << "\t" << scaled << "\t" << fent.function << "\n";
+                    if (find_reps) os << "///\n";  // owner_->server()->family_reps() is null without --family-reps
+                } else {
+                    std::string peg = mapping_->decode_id(eid);
+                    os << peg << "\t" << score_ent.hit_count;
+                    auto fhit = mapping_->peg_to_family_.find(eid);
+                    if (fhit != mapping_->peg_to_family_.end()) {
+                        auto fam = mapping_->family_data_[fhit->second];
+                        os << "\t" << fam.pgf << "\t" << fam.plf << "\t" << fam.function << "\n";
+                    } else {
+                        os << "\n";
+                    }
+                }
+            }
+            os << "//\n";
+        }
+    }
+    return dup_text(os.str());
+}
+
 // The handlers' body parsing: parser_.parse_char over every byte of every packet, parse_complete after the last one
 // (query_request.cc:52-64, fq_process_request.cc:255-267).  `cuts` are the packet boundaries.  Each callback is dumped
 // as "<id length> <seq length>\n<id><seq>\n" so that any byte may appear in an id.

@@ -156,6 +156,10 @@ class Ref:
         L.ref_family_table_size.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.ref_family_table.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_family_clear.argtypes = [C.c_void_p]
+        L.ref_family_set_extra.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_lookup_text.restype = C.c_void_p
+        L.ref_lookup_text.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_uint, C.c_int, C.c_int,
+                                      C.c_int, C.c_uint64]
         L.ref_parse_text.restype = C.c_void_p
         L.ref_parse_text.argtypes = [C.c_int, C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]
         L.ref_family_text.restype = C.c_void_p
@@ -272,6 +276,21 @@ class Ref:
         fam_ids = np.ascontiguousarray(fam_ids, np.uint32)
         self.L.ref_family_load(self.h, len(kmers), kmers.ctypes.data, fam_off.ctypes.data, fam_ids.ctypes.data, len(pgf),
                                _cstr_array(pgf), _cstr_array(plf), _cstr_array(function))
+
+    def family_set_extra(self, genus_id, total_size, count):
+        g = np.ascontiguousarray(genus_id, np.uint64)
+        t = np.ascontiguousarray(total_size, np.uint64)
+        c = np.ascontiguousarray(count, np.uint16)
+        self.L.ref_family_set_extra(self.h, len(g), g.ctypes.data, t.ctypes.data, c.ctypes.data)
+
+    def lookup_text(self, ids, batch, family_mode=True, kmer_hit_threshold=3, find_best_match=False, find_reps=False,
+                    allow_ambiguous_functions=False, target_genus_id=0):
+        """LookupRequest's worker loop (lookup_request.cc:138-400) over the reference engine."""
+        res = np.ascontiguousarray(batch.residues, np.uint8)
+        off = np.ascontiguousarray(batch.offsets, np.uint64)
+        return self._text(self.L.ref_lookup_text(self.h, _cstr_array(ids), res.ctypes.data, off.ctypes.data, batch.n, int(family_mode),
+                                                 kmer_hit_threshold, int(find_best_match), int(find_reps),
+                                                 int(allow_ambiguous_functions), target_genus_id))
 
     def parse_text(self, fastq: bool, text: bytes, cuts=()):
         """Reference FastaParser / FastqParser over `text` fed packet by packet; returns [(id, seq)] as bytes."""
@@ -469,6 +488,23 @@ class Oracle:
         self.L.orc_family_batch(self.t, C.byref(self.params), self.fam, res.ctypes.data, off.ctypes.data, batch.n,
                                 out.ctypes.data)
         return out
+
+    def family_scores(self, batch):
+        """(scores[SCORE_DT], score_offsets): LookupRequest::on_hit in family mode, ascending family id."""
+        from close_kmers_b200.api import SCORE_DT
+        res = np.ascontiguousarray(batch.residues, np.uint8)
+        off = np.ascontiguousarray(batch.offsets, np.uint64)
+        L = self.L
+        L.orc_family_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.orc_free.argtypes = [C.c_void_p]
+        ps, po = C.c_void_p(), C.c_void_p()
+        L.orc_family_scores(self.t, C.byref(self.params), self.fam, res.ctypes.data, off.ctypes.data, batch.n, C.byref(ps), C.byref(po))
+        so = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_uint64)), (batch.n + 1,)).copy()
+        ns = int(so[-1])
+        sc = np.frombuffer(C.string_at(ps, ns * SCORE_DT.itemsize), SCORE_DT).copy() if ns else np.zeros(0, SCORE_DT)
+        L.orc_free(ps)
+        L.orc_free(po)
+        return sc, so
 
     def family_nr_build(self, chunks):
         """chunks: iterable of (fam_ids, batch).  Returns (kmers, fam_off, fam_ids) sorted by (k-mer, family)."""

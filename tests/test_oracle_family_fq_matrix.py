@@ -138,3 +138,61 @@ def test_family_nr_load_matches_reference(checkers, world):
                            "oracle vs reference on the nr-loaded table")
     ref.close()
     orc.close()
+
+
+def family_rows(fam):
+    """family_data_ rows for the /lookup checks: genus ids cycle over 0..2, sizes and counts are arbitrary but distinct."""
+    return [(fam.pgf[f], fam.plf[f], fam.function[f], f % 3, 1000 + 37 * f, 1 + f % 50) for f in range(fam.n_fams)]
+
+
+def parse_lookup_blocks(text):
+    """/lookup listing -> [(id, [row fields...])]"""
+    blocks, cur = [], None
+    for line in text.split("\n")[:-1]:
+        if cur is None:
+            cur = (line, [])
+        elif line == "//":
+            blocks.append(cur)
+            cur = None
+        else:
+            cur[1].append(tuple(line.split("\t")))
+    assert cur is None
+    return blocks
+
+
+def assert_lookup_listing_equal(got, want, weight_col=2):
+    """Same blocks; rows may be permuted among equal weighted_total (the reference's std::sort over an unordered_map leaves
+    that order open), and a listing that stops inside such a tie group may hold a different subset of it."""
+    g, w = parse_lookup_blocks(got), parse_lookup_blocks(want)
+    assert [b[0] for b in g] == [b[0] for b in w]
+    lenient = 0
+    for (sid, a), (_, b) in zip(g, w):
+        if sorted(a) == sorted(b):
+            assert [float(r[weight_col]) for r in a] == sorted((float(r[weight_col]) for r in a), reverse=True)
+            continue
+        lenient += 1
+        floor = max(float(a[-1][weight_col]) if a else np.inf, float(b[-1][weight_col]) if b else np.inf)
+        assert sorted(r for r in a if float(r[weight_col]) > floor) == sorted(r for r in b if float(r[weight_col]) > floor), sid
+    assert lenient <= max(2, len(g) // 20), lenient
+
+
+def test_lookup_family_scores_match_reference(checkers, world):
+    """N3: LookupRequest::on_hit accumulation (family mode) restated by the oracle, against the reference's listing."""
+    protos, sig, fam, ref, orc = world
+    rows = family_rows(fam)
+    ref.family_load(fam.kmers, fam.fam_off, fam.fam_ids, fam.pgf, fam.plf, fam.function)  # the matrix test replaced the mapping
+    ref.family_set_extra([r[3] for r in rows], [r[4] for r in rows], [r[5] for r in rows])
+    batch = wl.concat_batches(wl.edge_batch(protos), synth.make_proteins(31, protos, 400))
+    ids = [f"s{i}" for i in range(batch.n)]
+    sc, so = orc.family_scores(batch)
+    # threshold 0 lists every family the sequence touched
+    blocks = parse_lookup_blocks(ref.lookup_text(ids, batch, family_mode=True, kmer_hit_threshold=0))
+    assert len(blocks) == batch.n
+    fmt = lambda x: "%g" % np.float32(x)
+    for i, (sid, got_rows) in enumerate(blocks):
+        assert sid == ids[i]
+        mine = sorted((str(e["hit_count"]), str(e["hit_count"]), fmt(e["weighted_total"]), rows[e["id"]][0], rows[e["id"]][1],
+                       str(rows[e["id"]][4]), str(rows[e["id"]][5]), fmt(np.float32(e["hit_count"]) / np.float32(rows[e["id"]][4])),
+                       rows[e["id"]][2]) for e in sc[int(so[i]):int(so[i + 1])])
+        assert mine == sorted(got_rows), sid
+    assert int(so[-1]) > 2000
