@@ -154,6 +154,8 @@ def parse_lookup_blocks(text):
         elif line == "//":
             blocks.append(cur)
             cur = None
+        elif line == "///":  # end of a family's representative rows (find_reps)
+            cur[1][-1] = cur[1][-1] + ("///",)
         else:
             cur[1].append(tuple(line.split("\t")))
     assert cur is None

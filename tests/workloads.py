@@ -161,12 +161,20 @@ def matrix_text_from_pairs(pairs, eids, batch, id_to_peg):
     return "".join(out)
 
 
-def assert_fq_text_equal(got: str, want: str, max_tie_diffs: int = None):
-    """/fq_lookup text: same reads reported; lines byte-identical except where two families tie exactly (the reference
-    breaks those by unordered_map order)."""
-    a = {ln.split("\t")[0]: ln for ln in got.splitlines()}
-    b = {ln.split("\t")[0]: ln for ln in want.splitlines()}
-    assert a.keys() == b.keys() and len(a) == len(got.splitlines())
-    diff = [k for k in a if a[k] != b[k]]
-    limit = max(10, len(a) // 50) if max_tie_diffs is None else max_tie_diffs
-    assert len(diff) <= limit, (len(diff), [(a[k], b[k]) for k in diff[:3]])
+def assert_fq_text_equal(got: str, want: str):
+    """/fq_lookup text: same reads, every numeric field and function byte-identical.  The PGF / PLF *names* may differ where
+    two families tie exactly on the printed score (the reference breaks ties by unordered_map iteration order, here the
+    smallest id wins); returns how many lines did."""
+    a, b = got.splitlines(), want.splitlines()
+    assert len(a) == len(b)
+    named = 0
+    for x, y in zip(a, b):
+        if x == y:
+            continue
+        fx, fy = x.split("\t"), y.split("\t")
+        assert len(fx) == len(fy), (x, y)
+        for k, (u, v) in enumerate(zip(fx, fy)):
+            if u != v:
+                assert k >= 3 and (k - 3) % 7 in (1, 3), (k, x, y)  # a family name; its score (next field) is compared like the rest
+        named += 1
+    return named
