@@ -330,6 +330,17 @@ class KmerGuts:
         self._h = h
         self.device = device
 
+    def clone(self) -> "KmerGuts":
+        """A second engine over the same tables (one KmerGuts per worker thread, threadpool.cc:33); close it first."""
+        L = lib()
+        L.ckm_clone.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        h = C.c_void_p()
+        _check(L.ckm_clone(self._h, C.byref(h)))
+        other = object.__new__(KmerGuts)
+        other._h = h
+        other.device = self.device
+        return other
+
     def close(self):
         if getattr(self, "_h", None):
             lib().ckm_close(self._h)

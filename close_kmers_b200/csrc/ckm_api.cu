@@ -361,6 +361,52 @@ extern "C" int ckm_open(const char *kmer_dir, int device, ckm_ctx **out) {
     return 0;
 }
 
+// One KmerGuts per worker thread over one shared KmerImage (threadpool.cc:33, kguts.h:312): a second context on the same
+// device with its own streams, parameters and work buffers, reading the parent's signature table, occupancy bitmap and
+// (if loaded) family tables in place.  The parent must outlive its clones.
+extern "C" int ckm_clone(ckm_ctx *parent, ckm_ctx **out) {
+    if (!parent || !out) return ckm_fail(CKM_EINVAL, "NULL argument");
+    *out = nullptr;
+    ckm_ctx *c = nullptr;
+    RC(ctx_create(parent->device, &c));
+    c->shares_tables = true;
+    c->table = parent->table;
+    c->occupied = parent->occupied;
+    c->num_sigs = parent->num_sigs;
+    c->magic = parent->magic;
+    c->slot_bytes = parent->slot_bytes;
+    c->force_raw = parent->force_raw;
+    c->tuning = parent->tuning;
+    c->functions = parent->functions;
+    c->otu_names = parent->otu_names;
+    c->prm = parent->prm;
+    if (parent->has_l2_window) {
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof attr);
+        attr.accessPolicyWindow = parent->l2_window;
+        if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) (void)cudaGetLastError();
+        c->l2_window = parent->l2_window;
+        c->has_l2_window = true;
+    }
+    ckm_ctx::Family &F = c->fam, &P = parent->fam;
+    if (P.loaded) {
+        F.loaded = true;
+        F.table = P.table;
+        F.ids = P.ids;
+        F.fam_func = P.fam_func;
+        F.fam_pgf = P.fam_pgf;
+        F.func_sid = P.func_sid;
+        F.mask = P.mask;
+        F.n_fams = P.n_fams;
+        F.n_functions = P.n_functions;
+        F.hypo_sid = P.hypo_sid;
+        F.pgf_names = P.pgf_names;
+        F.plf = P.plf;
+    }
+    *out = c;
+    return 0;
+}
+
 extern "C" void ckm_close(ckm_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);

@@ -36,6 +36,7 @@ struct ckm_ctx {
     int l2_fetch = 0;  // cudaLimitMaxL2FetchGranularity in effect
 
     // signature table in HBM
+    bool shares_tables = false;  // a ckm_clone: table / occupied / family tables belong to the parent
     DevBuf table, occupied;  // occupied: 1 bit per slot, only for tables larger than L2
     int l2_bytes = 0;
     bool has_l2_window = false;
@@ -106,6 +107,12 @@ struct ckm_ctx {
     PinBuf h_off, h_totals, h_hit_off, h_hits, h_call_off, h_calls, h_otu_off, h_otus, h_best;
 
     void free_all() {
+        if (shares_tables) {  // drop the borrowed handles before the common release below
+            table = DevBuf();
+            occupied = DevBuf();
+            DevBuf *borrowed[] = {&fam.table, &fam.ids, &fam.fam_func, &fam.fam_pgf, &fam.func_sid};
+            for (auto b : borrowed) *b = DevBuf();
+        }
         DevBuf *d[] = {&table, &occupied, &in_res, &in_off, &totals, &hits, &hit_keys, &hit_avg, &n_hits, &stored_idx, &calls, &calls_work,
                        &n_calls, &otus, &n_otus, &best, &ps_blocks, &hit_off, &call_off, &otu_off, &hits_out, &calls_out,
                        &otus_out};

@@ -371,6 +371,7 @@ extern "C" int ckm_family_load(ckm_ctx *c, uint64_t n_kmers, const uint64_t *kme
                                const char *const *function) {
     if (!c) return ckm_fail(CKM_EINVAL, "ctx is NULL");
     if (n_kmers && (!kmers || !fam_offsets || !fam_ids)) return ckm_fail(CKM_EINVAL, "NULL family table");
+    if (c->shares_tables) return ckm_fail(CKM_ESTATE, "a clone reads its parent's family tables and cannot load its own");
     CU(cudaSetDevice(c->device));
     const uint64_t n_entries = n_kmers ? fam_offsets[n_kmers] : 0;
     if (n_entries >= (1ull << 32)) return ckm_fail(CKM_EINVAL, "more than 2^32 k-mer->family entries");

@@ -504,6 +504,7 @@ extern "C" int ckm_family_nr_add(ckm_ctx *c, const uint32_t *fam_ids, const char
 extern "C" int ckm_family_nr_finish(ckm_ctx *c, uint32_t n_families, const char *const *pgf, const char *const *plf,
                                     const char *const *function, uint64_t *n_kmers_out, uint64_t *n_entries_out) {
     if (!c) return ckm_fail(CKM_EINVAL, "ctx is NULL");
+    if (c->shares_tables) return ckm_fail(CKM_ESTATE, "a clone reads its parent's family tables and cannot load its own");
     CU(cudaSetDevice(c->device));
     ckm_ctx::Post &P = c->famnr;
     // 1. (k-mer, family) pairs, each once

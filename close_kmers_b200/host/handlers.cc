@@ -1,7 +1,8 @@
 // Host side of the request handlers, written only against the C ABI (include/ckm.h): one batch call per
 // body chunk, then the reference's response text rebuilt from the flat results.  Floats are printed
-// through std::ostream exactly like the reference (default precision 6), so the text is byte-identical.
+// exactly as std::ostream prints them in the reference (default precision 6; see text.h), so the text is byte-identical.
 #include "../../include/ckm_handlers.h"
+#include "text.h"
 
 #include <algorithm>
 #include <cstdlib>
@@ -24,14 +25,14 @@ char *dup_text(const std::string &s) {
 }
 
 // KmerGuts::format_call, kguts.cc:939-947
-void put_call(std::ostream &os, const ckm_ctx *ctx, const ckm_call_t &c) {
+void put_call(ckm_text::Text &os, const ckm_ctx *ctx, const ckm_call_t &c) {
     os << "CALL\t" << c.start << "\t" << c.end << "\t" << c.count;
     os << "\t" << c.function_index << "\t" << ckm_function_at_index(ctx, (int32_t)c.function_index);
     os << "\t" << c.weighted_hits << "\n";
 }
 
 // KmerGuts::format_hit, kguts.cc:949-959
-void put_hit(std::ostream &os, const ckm_ctx *ctx, const ckm_hit_t &h) {
+void put_hit(ckm_text::Text &os, const ckm_ctx *ctx, const ckm_hit_t &h) {
     char dc[CKM_KMER_SIZE + 1];
     ckm_decoded_kmer(h.which_kmer, dc);
     os << "HIT\t" << h.offset << "\t" << dc << "\t" << h.avg_from_end << "\t" << ckm_function_at_index(ctx, h.function_index)
@@ -39,7 +40,7 @@ void put_hit(std::ostream &os, const ckm_ctx *ctx, const ckm_hit_t &h) {
 }
 
 // KmerOtuStats::finalize (kguts.h:214-218) + format_otu_stats (kguts.cc:961-973)
-void put_otu_stats(std::ostream &os, const std::string &id, uint64_t size, const ckm_otu_t *otus, uint64_t n) {
+void put_otu_stats(ckm_text::Text &os, const std::string &id, uint64_t size, const ckm_otu_t *otus, uint64_t n) {
     std::vector<std::pair<int, int>> by_count;
     by_count.reserve(n);
     for (uint64_t i = 0; i < n; i++) by_count.emplace_back(otus[i].otu_index, otus[i].count);
@@ -78,7 +79,7 @@ int ckm_query_text(ckm_ctx *ctx, const char *const *ids, const char *residues, c
     ckm_batch_out_t o;
     int rc = ckm_call_batch(ctx, residues, offsets, n, flags, &o);
     if (rc) return rc;
-    std::ostringstream os;
+    ckm_text::Text os;
     for (uint32_t i = 0; i < n; i++) {
         const std::string id = ids[i];
         const uint64_t len = offsets[i + 1] - offsets[i];
@@ -93,12 +94,12 @@ int ckm_query_text(ckm_ctx *ctx, const char *const *ids, const char *residues, c
             put_otu_stats(os, id, len, o.otus + o.otu_offsets[i], o.otu_offsets[i + 1] - o.otu_offsets[i]);
         }
     }
-    *text = dup_text(os.str());
+    *text = os.dup();
     return *text ? 0 : CKM_ENOMEM;
 }
 
 // operator<<(ostream&, best_match_t), family_mapper.h:70-75
-static void put_match(std::ostream &os, const ckm_ctx *ctx, const ckm_family_match_t &m) {
+static void put_match(ckm_text::Text &os, const ckm_ctx *ctx, const ckm_family_match_t &m) {
     os << ckm_family_pgf_name(ctx, m.gfam) << "\t" << m.gfam_score << "\t" << ckm_family_plf_name(ctx, m.lfam) << "\t"
        << m.lfam_score << "\t" << ckm_family_function_name(ctx, &m) << "\t" << m.score;
 }
@@ -109,12 +110,12 @@ int ckm_family_text(ckm_ctx *ctx, const char *residues, const uint64_t *offsets,
     const ckm_family_match_t *m = nullptr;
     int rc = ckm_family_batch(ctx, residues, offsets, n, &m);
     if (rc) return rc;
-    std::ostringstream os;
+    ckm_text::Text os;
     for (uint32_t i = 0; i < n; i++) {
         put_match(os, ctx, m[i]);
         os << "\n";
     }
-    *text = dup_text(os.str());
+    *text = os.dup();
     return *text ? 0 : CKM_ENOMEM;
 }
 
@@ -124,7 +125,7 @@ int ckm_fq_text(ckm_ctx *ctx, const char *const *ids, const char *bases, const u
     ckm_fq_out_t o;
     int rc = ckm_fq_batch(ctx, bases, offsets, n, &o);
     if (rc) return rc;
-    std::ostringstream os;
+    ckm_text::Text os;
     for (uint32_t r = 0; r < n; r++) {
         const std::string id = ids[r];
         if (id.empty()) continue;                // fq_process_request.cc:301-302
@@ -135,9 +136,9 @@ int ckm_fq_text(ckm_ctx *ctx, const char *const *ids, const char *bases, const u
             os << o.matches[k].length << "\t";
             put_match(os, ctx, o.matches[k].m);
         }
-        os << std::endl;
+        os << "\n";
     }
-    *text = dup_text(os.str());
+    *text = os.dup();
     return *text ? 0 : CKM_ENOMEM;
 }
 
@@ -178,7 +179,7 @@ int ckm_add_text(ckm_ctx *ctx, ckm_mapping *m, const char *const *ids, const cha
     ckm_batch_out_t o;
     int rc = ckm_call_batch(ctx, residues, offsets, n, CKM_WANT_CALLS | CKM_WANT_HITS | CKM_WANT_OTU | CKM_WANT_BEST, &o);
     if (rc) return rc;
-    std::ostringstream os;
+    ckm_text::Text os;
     std::vector<uint32_t> eids(n);
     for (uint32_t i = 0; i < n; i++) {
         const std::string id = ids[i];
@@ -196,7 +197,7 @@ int ckm_add_text(ckm_ctx *ctx, ckm_mapping *m, const char *const *ids, const cha
     }
     rc = ckm_postings_append_last(ctx, eids.data(), n);  // 165-170
     if (rc) return rc;
-    *text = dup_text(os.str());
+    *text = os.dup();
     return *text ? 0 : CKM_ENOMEM;
 }
 
@@ -230,31 +231,31 @@ int ckm_matrix_text(ckm_ctx *ctx, ckm_mapping *m, const char *const *ids, const 
     if (rc) return rc;
     std::vector<ckm_pair_t> v(pairs, pairs + np);
     v.resize(ckm_matrix_merge_pairs(v.data(), v.size()));
-    std::ostringstream os;
+    ckm_text::Text os;
     for (const ckm_pair_t &p : v) {  // process_results, matrix_request.cc:171-184
         const size_t l1 = matrix_proteins[p.eid_i], l2 = matrix_proteins[p.eid_j];
         const float score = (float)p.count / ((float)(l1 + l2));
         os << ckm_mapping_decode_id(m, p.eid_i) << "\t" << ckm_mapping_decode_id(m, p.eid_j) << "\t" << p.count << "\t" << score
            << "\n";
     }
-    *text = dup_text(os.str());
+    *text = os.dup();
     return *text ? 0 : CKM_ENOMEM;
 }
 
 char *ckm_format_call(const ckm_ctx *ctx, const ckm_call_t *call) {
-    std::ostringstream os;
+    ckm_text::Text os;
     put_call(os, ctx, *call);
-    return dup_text(os.str());
+    return os.dup();
 }
 char *ckm_format_hit(const ckm_ctx *ctx, const ckm_hit_t *hit) {
-    std::ostringstream os;
+    ckm_text::Text os;
     put_hit(os, ctx, *hit);
-    return dup_text(os.str());
+    return os.dup();
 }
 char *ckm_format_otu_stats(const char *id, uint64_t seq_len, const ckm_otu_t *otus, uint64_t n_otus) {
-    std::ostringstream os;
+    ckm_text::Text os;
     put_otu_stats(os, id, seq_len, otus, n_otus);
-    return dup_text(os.str());
+    return os.dup();
 }
 char *ckm_best_function(const ckm_ctx *ctx, const ckm_best_t *best) { return dup_text(best_function(ctx, *best)); }
 

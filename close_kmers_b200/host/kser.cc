@@ -54,7 +54,7 @@ struct Options {
         pid_file;
     std::vector<std::string> families_nr;
     bool have_kmer_version = false, have_families_version = false, no_listen = false, daemonize = false, debug_http = false, help = false;
-    int n_load_threads = 1;
+    int n_load_threads = 1, n_kmer_threads = 4;
     std::vector<int> devices;
     size_t batch_bytes = 32u << 20;
 };
@@ -72,13 +72,15 @@ const char *USAGE =
     "  --families-nr arg...           families NR data\n"
     "  --families-version arg         families data version string\n"
     "  --n-load-threads arg (=1)      sizes the NR load chunks exactly like the reference's thread pool\n"
+    "  --n-kmer-threads arg (=4)      engines per device (one KmerGuts per worker thread in the reference): requests on\n"
+    "                                 different connections overlap their GPU work and response formatting\n"
     "  --no-listen                    don't listen - just load data and quit\n"
     "  --daemonize                    run the service in the background\n"
     "  --pid-file arg                 write the process id to this file\n"
     "  --debug-http                   debug HTTP protocol\n"
     "  --device arg (=0)              CUDA device(s), comma separated: one engine per device\n"
     "  --batch-mb arg (=32)           residues handed to the GPU per batch\n"
-    "accepted and ignored (CPU scheduling of the reference): --n-family-file-threads --n-inserter-threads --n-kmer-threads\n"
+    "accepted and ignored (CPU scheduling of the reference): --n-family-file-threads --n-inserter-threads\n"
     "  --peg-kmer-data --reserve-mapping --no-populate-mmap; not supported: --family-reps --kmer-family-distribution-file\n"
     "If the kmer data directory contains files families.dat and a\n"
     "directory families.nr it will be assumed that these files contain\n"
@@ -151,6 +153,7 @@ bool parse_options(int argc, char **argv, Options &o, std::string &err) {
             else if (name == "families-genus-mapping") o.genus_mapping = value;
             else if (name == "families-file") o.families_file = value;
             else if (name == "n-load-threads") o.n_load_threads = std::max(1, std::stoi(value));
+            else if (name == "n-kmer-threads") o.n_kmer_threads = std::max(1, std::stoi(value));
             else if (name == "no-listen") o.no_listen = true;
             else if (name == "daemonize") o.daemonize = true;
             else if (name == "debug-http") o.debug_http = true;
@@ -162,7 +165,7 @@ bool parse_options(int argc, char **argv, Options &o, std::string &err) {
                 while (std::getline(ss, tok, ',')) o.devices.push_back(std::stoi(tok));
             } else if (name == "family-reps" || name == "kmer-family-distribution-file") {
                 std::cerr << "Warning: --" << name << " is not supported and is ignored\n";
-            } else if (name == "n-family-file-threads" || name == "n-inserter-threads" || name == "n-kmer-threads" ||
+            } else if (name == "n-family-file-threads" || name == "n-inserter-threads" ||
                        name == "peg-kmer-data" || name == "reserve-mapping" || name == "no-populate-mmap") {
             } else {
                 err = "unrecognised option '--" + name + "'";
@@ -814,6 +817,16 @@ extern "C" int ckm_kser_main(int argc, char **argv) {
     }
     if (install_families(s)) return 1;
     s.fams.flatten();
+    // the worker engines: clones share the tables of their device's first engine (threadpool.cc:33)
+    {
+        const size_t n_dev = s.engines.size();
+        for (int k = 1; k < s.opt.n_kmer_threads; k++)
+            for (size_t dv = 0; dv < n_dev; dv++) {
+                std::unique_ptr<Engine> e(new Engine());
+                if (ckm_clone(s.engines[dv]->ctx, &e->ctx)) return fail_ckm("ckm_clone");
+                s.engines.push_back(std::move(e));
+            }
+    }
     if (s.opt.no_listen) {
         std::cerr << "Quitting due to --no-listen being set\n";
         return 0;
@@ -871,7 +884,7 @@ extern "C" int ckm_kser_main(int argc, char **argv) {
     s.stopping = true;
     for (int i = 0; i < 3000 && s.active.load() > 0; i++) usleep(10000);  // let the requests in flight finish
     if (s.active.load() == 0) {
-        for (auto &e : s.engines) ckm_close(e->ctx);
+        for (size_t e = s.engines.size(); e-- > 0;) ckm_close(s.engines[e]->ctx);  // clones first
         for (auto &m : s.mappings) ckm_mapping_free(m.second.ids);
     }
     g_server = nullptr;

@@ -4,6 +4,7 @@
 // only; where it leaves the order of equal elements to the container / sort implementation, the order here is ascending
 // id.  Sums over that walk (the PGF roll-up) are f32 sums in ascending family id.
 #include "lookup.h"
+#include "text.h"
 
 #include <algorithm>
 #include <cstdlib>
@@ -47,7 +48,7 @@ ckm_lookup_options_t options_from(const ckm_http::Request &r, const FamilyInfo &
 }
 
 // find_best_match && family_mode, lookup_request.cc:201-327
-static void best_match_line(std::ostream &os, ckm_ctx *ctx, const ckm_family_data_t *fams, uint32_t n_fams, const ckm_lookup_options_t &o,
+static void best_match_line(ckm_text::Text &os, ckm_ctx *ctx, const ckm_family_data_t *fams, uint32_t n_fams, const ckm_lookup_options_t &o,
                             const char *id, const ckm_score_t *sc, uint64_t n, const ckm_best_t &best) {
     char *fn = ckm_best_function(ctx, &best);
     std::string best_call_function = fn ? fn : "";
@@ -107,7 +108,7 @@ extern "C" int ckm_lookup_text(ckm_ctx *ctx, ckm_mapping *pegs, const ckm_family
     if (!text || !opt) return CKM_EINVAL;
     *text = nullptr;
     const ckm_lookup_options_t &o = *opt;
-    std::ostringstream os;
+    ckm_text::Text os;
     if (o.family_mode) {
         ckm_family_scores_t fs;
         int rc = ckm_family_scores(ctx, residues, offsets, n, &fs);
@@ -153,10 +154,6 @@ extern "C" int ckm_lookup_text(ckm_ctx *ctx, ckm_mapping *pegs, const ckm_family
             os << "//\n";
         }
     }
-    const std::string s = os.str();
-    char *p = (char *)malloc(s.size() + 1);
-    if (!p) return CKM_ENOMEM;
-    memcpy(p, s.data(), s.size() + 1);
-    *text = p;
-    return 0;
+    *text = os.dup();
+    return *text ? 0 : CKM_ENOMEM;
 }

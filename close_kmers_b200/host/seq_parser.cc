@@ -20,7 +20,7 @@ struct ckm_seq_parser {
     int format;
     State state = s_start;
     int line_number = 1;
-    std::string cur_id, cur_seq;
+    std::string cur_id;  // the sequence in progress is the tail of `residues`, past offsets.back()
     uint64_t n_errors = 0;
     std::string last_error;
 
@@ -32,10 +32,32 @@ struct ckm_seq_parser {
 
     void emit() {  // call_callback + reset (fasta_parser.h:112-116, 158-164)
         ids.push_back(cur_id);
-        residues += cur_seq;
         offsets.push_back(residues.size());
         cur_id.clear();
-        cur_seq.clear();
+    }
+    // Appends the longest prefix of d[0..n) made of sequence characters and returns its length.  Whole lines are taken
+    // with one memchr + one vectorisable validity pass + one copy.
+    template <bool STAR>
+    size_t take_run(const char *d, size_t n) {
+        size_t done = 0;
+        while (done < n) {
+            const char *nl = (const char *)memchr(d + done, '\n', n - done);
+            const size_t end = nl ? (size_t)(nl - d) : n;
+            unsigned bad = 0;
+            for (size_t k = done; k < end; k++) {
+                const unsigned char c = (unsigned char)d[k];
+                bad |= !(((unsigned)((c | 0x20u) - 'a') < 26u) | (STAR & (c == '*')));
+            }
+            if (bad) {  // stop at the first character that is not sequence data
+                size_t k = done;
+                while (is_alpha((unsigned char)d[k]) || (STAR && d[k] == '*')) k++;
+                residues.append(d + done, k - done);
+                return k;
+            }
+            residues.append(d + done, end - done);
+            return end;  // at the newline (or the end of the block): the state machine takes it from here
+        }
+        return done;
     }
     void error(const std::string &what) {
         n_errors++;
@@ -50,10 +72,8 @@ void ckm_seq_parser::feed_fasta(const char *d, size_t n) {
     while (i < n) {
         if (state == s_data) {
             // bulk of the body: letters and '*' up to the end of the line
-            size_t j = i;
-            while (j < n && (is_alpha((unsigned char)d[j]) || d[j] == '*')) j++;
+            const size_t j = i + take_run<true>(d + i, n - i);
             if (j > i) {
-                cur_seq.append(d + i, j - i);
                 i = j;
                 continue;
             }
@@ -89,7 +109,7 @@ void ckm_seq_parser::feed_fasta(const char *d, size_t n) {
                 state = s_id;
             } else if (ch == '\n') {
             } else if (is_alpha(ch)) {
-                cur_seq.push_back((char)ch);
+                residues.push_back((char)ch);
                 state = s_data;
             } else {
                 error(std::string("Bad id or data character '") + (char)ch + "'");
@@ -105,10 +125,8 @@ void ckm_seq_parser::feed_fastq(const char *d, size_t n) {
     size_t i = 0;
     while (i < n) {
         if (state == s_data) {
-            size_t j = i;
-            while (j < n && is_alpha((unsigned char)d[j])) j++;
+            const size_t j = i + take_run<false>(d + i, n - i);
             if (j > i) {
-                cur_seq.append(d + i, j - i);
                 i = j;
                 continue;
             }
@@ -172,13 +190,15 @@ extern "C" void ckm_seq_parser_feed(ckm_seq_parser *p, const char *data, size_t 
 extern "C" void ckm_seq_parser_complete(ckm_seq_parser *p) {
     if (p) p->emit();
 }
-extern "C" uint64_t ckm_seq_parser_pending(const ckm_seq_parser *p) { return p ? p->residues.size() : 0; }
+extern "C" uint64_t ckm_seq_parser_pending(const ckm_seq_parser *p) { return p ? p->offsets.back() : 0; }
 extern "C" void ckm_seq_parser_take(ckm_seq_parser *p, ckm_seq_batch_t *out) {
     p->out_ids.swap(p->ids);
     p->out_residues.swap(p->residues);
     p->out_offsets.swap(p->offsets);
     p->ids.clear();
-    p->residues.clear();
+    const size_t completed = (size_t)p->out_offsets.back();
+    p->residues.assign(p->out_residues, completed, std::string::npos);  // the sequence in progress stays with the parser
+    p->out_residues.resize(completed);
     p->offsets.assign(1, 0);
     p->out_ptrs.clear();
     for (const auto &s : p->out_ids) p->out_ptrs.push_back(s.c_str());

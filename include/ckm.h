@@ -133,6 +133,12 @@ int ckm_open_image(const void *image, size_t image_bytes, int device, const char
                    int32_t n_functions, const char *const *otu_names, int32_t n_otus, ckm_ctx **out);
 
 void ckm_close(ckm_ctx *ctx);
+/* A second context over the SAME tables: the reference builds one KmerGuts per worker thread over one shared KmerImage
+ * (threadpool.cc:33, kguts.h:312).  The clone has its own stream, parameters, postings and result buffers and reads the
+ * parent's signature table and family tables (as loaded at the time of the call) in place; nothing is copied.  Calls on
+ * different contexts may run concurrently from different threads.  Close clones before the parent.  A clone must not load
+ * family tables itself. */
+int ckm_clone(ckm_ctx *parent, ckm_ctx **out);
 
 /* thread-local text of the last error (also valid when ctx creation failed) */
 const char *ckm_last_error(void);

@@ -46,3 +46,12 @@ def test_wrapper_loop_matches_reference_text(tmp_path, checkers):
             ref.set_params()
             assert r.stdout == ref.query_text(ids, batch, details, fbc)
     guts.close()
+
+
+def test_text_builder_prints_like_ostream(tmp_path):
+    """The handlers build responses with ckm_text::Text (to_chars); the reference uses std::ostream: same bytes."""
+    exe = os.path.join(str(tmp_path), "text_check")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-Werror", os.path.join(ROOT, "tests", "cpp", "text_check.cc"), "-o", exe],
+                   check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr[-2000:]

@@ -134,6 +134,42 @@ def test_peg_mode_lookup(checkers, world):
         ref.close()
 
 
+def test_clones_share_tables_and_run_concurrently(checkers, world):
+    protos, sig, img, fam, d = world
+    orc = checkers.Oracle().open_image(img)
+    orc.family_load(fam)
+    guts = api.KmerGuts(kmer_dir=d)
+    guts.family_load(fam.kmers, fam.fam_off, fam.fam_ids, fam.pgf, fam.plf, fam.function)
+    clones = [guts.clone() for _ in range(3)]
+    try:
+        batches = [wl.concat_batches(wl.edge_batch(protos), synth.make_proteins(90 + k, protos, 4000)) for k in range(4)]
+        params = [dict(), dict(min_hits=3), dict(max_gap=50), dict(order_constraint=1)]
+        out = [None] * 4
+
+        def work(k):
+            g = ([guts] + clones)[k]
+            g.set_parameters(params[k])  # parameters are per engine
+            for _ in range(5):
+                calls = g.process_aa_seq_batch(batches[k].residues, batches[k].offsets, api.WANT_CALLS | api.WANT_BEST)
+                fams = g.find_best_family_match_batch(batches[k].residues, batches[k].offsets)
+            out[k] = (calls, fams)
+
+        ts = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        for k in range(4):
+            orc.set_params(**params[k])
+            wl.assert_results_equal(out[k][0], orc.call_batch(batches[k], checkers.WANT_CALLS | checkers.WANT_BEST), f"clone {k}")
+            wl.assert_family_records_equal(out[k][1], orc.family_batch(batches[k]), f"clone {k} families")
+        with pytest.raises(api.CkmError):
+            clones[0].family_load(fam.kmers, fam.fam_off, fam.fam_ids, fam.pgf, fam.plf, fam.function)
+    finally:
+        for c in clones:
+            c.close()
+        guts.close()
+        orc.close()
+
+
 # ---- the server --------------------------------------------------------------------------------------------------------
 
 def http(port, head: bytes, body: bytes = b"", piecewise=0):
