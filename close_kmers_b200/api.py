@@ -298,6 +298,17 @@ def http_describe(head: bytes) -> dict:
     return dict(line.split("=", 1) for line in text.split("\n") if "=" in line)
 
 
+def pinned_empty(nbytes: int) -> np.ndarray:
+    """A uint8 array in page-locked host memory (ckm_host_alloc); it is released when the array is collected."""
+    p = C.c_void_p()
+    _check(lib().ckm_host_alloc(C.byref(p), max(nbytes, 1)))
+    buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, np.uint8)[:nbytes]
+    import weakref
+    weakref.finalize(buf, lib().ckm_host_free, p)
+    return arr
+
+
 def canonical_family_csr(kmers, fam_off, fam_ids) -> tuple:
     """Sort a k-mer -> family-list CSR by k-mer and each list by family id (the lists are sets: kmer.cc:216-230)."""
     kmers = np.asarray(kmers, np.uint64)

@@ -71,7 +71,7 @@ struct FamTables {
 __global__ void __launch_bounds__(256)
 fam_lookup_kernel(FamTables ft, const uint64_t *__restrict__ offsets, const uint64_t *__restrict__ hit_keys,
                   const uint32_t *__restrict__ n_hits, uint32_t n, uint2 *__restrict__ hit_fam, uint32_t *__restrict__ E,
-                  uint32_t *__restrict__ gcap) {
+                  uint32_t *__restrict__ gcap, uint32_t *__restrict__ class_seen = nullptr) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= n) return;
@@ -101,6 +101,12 @@ fam_lookup_kernel(FamTables ft, const uint64_t *__restrict__ offsets, const uint
             while (cap < 2u * e && cap < 0x80000000u) cap <<= 1;
         }
         gcap[w] = cap;
+        if (class_seen) {  // which fam_vote_kernel instantiations have work: [0] small maps, [1] large / global maps
+            uint32_t scap = 32u;
+            while (scap < 2u * e) scap <<= 1;
+            const uint32_t cls = (cap == 0 && scap <= kFamSmallCap) ? 0u : 1u;
+            if (*((volatile uint32_t *)class_seen + cls) == 0u) class_seen[cls] = 1u;
+        }
     }
 }
 
@@ -447,12 +453,17 @@ static int family_device(ckm_ctx *c, const uint64_t *d_off, uint32_t n, uint64_t
     ft.n_functions = F.n_functions;
     ft.hypo_sid = F.hypo_sid;
     const unsigned lb = (unsigned)(((uint64_t)n * 32 + 255) / 256);
+    RC(F.class_seen.ensure(64));
+    CU(cudaMemsetAsync(F.class_seen.p, 0, 8, c->stream));
     fam_lookup_kernel<<<lb, 256, 0, c->stream>>>(ft, d_off, (const uint64_t *)c->hit_keys.p, (const uint32_t *)c->n_hits.p, n,
-                                                 (uint2 *)F.hit_fam.p, (uint32_t *)F.E.p, (uint32_t *)F.gcap.p);
+                                                 (uint2 *)F.hit_fam.p, (uint32_t *)F.E.p, (uint32_t *)F.gcap.p,
+                                                 (uint32_t *)F.class_seen.p);
     c->launches++;
     RC(prefix_sum(c, (const uint32_t *)F.gcap.p, n, (uint64_t *)F.gofs.p));
     uint64_t gtotal = 0;
+    uint32_t class_seen[2] = {1u, 1u};
     CU(cudaMemcpyAsync(&gtotal, (const uint64_t *)F.gofs.p + n, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(class_seen, F.class_seen.p, 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (gtotal) {
         RC(F.gscratch.ensure(gtotal * 5 * 4));
@@ -479,13 +490,22 @@ static int family_device(ckm_ctx *c, const uint64_t *d_off, uint32_t n, uint64_t
         CU(cudaFuncSetAttribute(fam_vote_kernel<kFamSmallCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kSmem));
         const unsigned sb = (unsigned)std::min<uint64_t>(((uint64_t)n + S::kWarps - 1) / S::kWarps, (uint64_t)c->sm_count * 32);
         const unsigned lb2 = (unsigned)std::min<uint64_t>(((uint64_t)n + L::kWarps - 1) / L::kWarps, (uint64_t)c->sm_count * 8);
-        fam_vote_kernel<kFamSmallCap><<<sb, S::kWarps * 32, S::kSmem, c->stream>>>(
-            ft, d_off, (const uint32_t *)c->n_hits.p, (const uint2 *)F.hit_fam.p, (const uint32_t *)F.E.p, (const uint32_t *)F.gcap.p,
-            (const uint64_t *)F.gofs.p, (uint32_t *)F.gscratch.p, (const ckm_best_t *)c->best.p, n, (ckm_family_match_t *)F.matches.p, so);
-        fam_vote_kernel<kFamSmemCap><<<lb2, L::kWarps * 32, L::kSmem, c->stream>>>(
-            ft, d_off, (const uint32_t *)c->n_hits.p, (const uint2 *)F.hit_fam.p, (const uint32_t *)F.E.p, (const uint32_t *)F.gcap.p,
-            (const uint64_t *)F.gofs.p, (uint32_t *)F.gscratch.p, (const ckm_best_t *)c->best.p, n, (ckm_family_match_t *)F.matches.p, so);
-        c->launches += 2;
+        // each instantiation walks the whole batch and skips the other one's proteins: launch it only if it has any
+        // (every fastq fragment is "small")
+        if (class_seen[0]) {
+            fam_vote_kernel<kFamSmallCap><<<sb, S::kWarps * 32, S::kSmem, c->stream>>>(
+                ft, d_off, (const uint32_t *)c->n_hits.p, (const uint2 *)F.hit_fam.p, (const uint32_t *)F.E.p,
+                (const uint32_t *)F.gcap.p, (const uint64_t *)F.gofs.p, (uint32_t *)F.gscratch.p, (const ckm_best_t *)c->best.p, n,
+                (ckm_family_match_t *)F.matches.p, so);
+            c->launches++;
+        }
+        if (class_seen[1]) {
+            fam_vote_kernel<kFamSmemCap><<<lb2, L::kWarps * 32, L::kSmem, c->stream>>>(
+                ft, d_off, (const uint32_t *)c->n_hits.p, (const uint2 *)F.hit_fam.p, (const uint32_t *)F.E.p,
+                (const uint32_t *)F.gcap.p, (const uint64_t *)F.gofs.p, (uint32_t *)F.gscratch.p, (const ckm_best_t *)c->best.p, n,
+                (ckm_family_match_t *)F.matches.p, so);
+            c->launches++;
+        }
     }
     CU(cudaGetLastError());
     return 0;

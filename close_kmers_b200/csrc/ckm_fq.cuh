@@ -50,6 +50,7 @@ __device__ __forceinline__ char frame_aa(const uint8_t *read, uint32_t len, uint
 
 constexpr uint32_t kFqReadsPerBlock = 42;   // 252 of the block's 256 threads
 constexpr uint32_t kFqStageBytes = 12 * 1024;
+constexpr uint32_t kFqOutBytes = 16 * 1024;  // 42 reads x 6 frames x 50 residues = 12.6 KB for 150-base reads
 
 template <bool FILL>
 __global__ void __launch_bounds__(256)
@@ -59,6 +60,7 @@ fq_frames_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__
                  uint64_t *__restrict__ frag_off, uint8_t *__restrict__ frag_res) {
     __shared__ char tbl[65];
     __shared__ __align__(16) uint8_t s_bases[kFqStageBytes + 16];
+    __shared__ __align__(16) uint8_t s_out[FILL ? kFqOutBytes + 32 : 16];
     fill_aa11(tbl);
     // the block's reads (kFqReadsPerBlock consecutive ones, six threads each) are staged in shared memory with
     // coalesced word loads when they fit; every base is then read six times (once per frame) from there
@@ -72,33 +74,89 @@ fq_frames_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__
         const uint32_t words = (uint32_t)((blk1 - blk0) + mis + 3u) >> 2;
         for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) reinterpret_cast<uint32_t *>(s_bases)[w] = __ldg(src + w);
     }
-    __syncthreads();
-    if (threadIdx.x >= 6u * kFqReadsPerBlock) return;
-    const uint32_t r = r0 + threadIdx.x / 6u, slot = threadIdx.x % 6u;
-    if (r >= n) return;
-    const uint64_t t = 6ull * r + slot;
-    const uint64_t b0 = offsets[r];
-    const uint32_t len = (uint32_t)(offsets[r + 1] - b0);
-    const uint8_t *read = staged ? s_bases + mis + (b0 - blk0) : bases + b0;
-    const uint32_t skip = slot % 3u;
-    const uint32_t ncod = len >= skip + 3u ? (len - skip) / 3u : 0u;  // complete codons only (trans_table.cc:70-81)
-    uint32_t cnt = 0, aa_total = 0, run = 0;
-    uint64_t fcur = FILL ? frag_base[t] : 0, rcur = FILL ? res_base[t] : 0;
-    // boost::split(.., "*", token_compress_on) (dna_seq.cc:17): fragments are the maximal stop-free runs
-    for (uint32_t k = 0; k <= ncod; k++) {
-        const char a = k < ncod ? frame_aa(read, len, slot, k, tbl) : '*';
-        if (a != '*') { run++; continue; }
-        if (run > min_len) {  // prot.length() > 10 (fq_process_request.cc:331)
-            if (FILL) {
-                frag_off[fcur++] = rcur;
-                for (uint32_t j = k - run; j < k; j++) frag_res[rcur++] = (uint8_t)frame_aa(read, len, slot, j, tbl);
-            }
-            cnt++;
-            aa_total += run;
-        }
-        run = 0;
+    // fill pass: the block's fragments are one contiguous range of the output (frames are laid out in thread order), so
+    // residues are assembled in shared memory, at the same 16-byte phase as their destination, and leave as whole
+    // 16-byte stores instead of one byte per thread per instruction
+    uint64_t out0 = 0, out1 = 0;
+    uint32_t ophase = 0;
+    bool out_staged = false;
+    if (FILL && r0 < n) {
+        out0 = res_base[6ull * r0];
+        out1 = res_base[6ull * r1];
+        ophase = (uint32_t)(reinterpret_cast<uintptr_t>(frag_res + out0) & 15u);
+        out_staged = (out1 - out0) + ophase <= kFqOutBytes;
     }
-    if (!FILL) { nfrag[t] = cnt; naa[t] = aa_total; }
+    __syncthreads();
+    const uint32_t r = r0 + threadIdx.x / 6u, slot = threadIdx.x % 6u;
+    if (threadIdx.x < 6u * kFqReadsPerBlock && r < n) {
+        const uint64_t t = 6ull * r + slot;
+        const uint64_t b0 = offsets[r];
+        const uint32_t len = (uint32_t)(offsets[r + 1] - b0);
+        const uint8_t *read = staged ? s_bases + mis + (b0 - blk0) : bases + b0;
+        const uint32_t skip = slot % 3u;
+        const uint32_t ncod = len >= skip + 3u ? (len - skip) / 3u : 0u;  // complete codons only (trans_table.cc:70-81)
+        uint32_t cnt = 0, aa_total = 0, run = 0;
+        uint64_t fcur = FILL ? frag_base[t] : 0, rcur = FILL ? res_base[t] : 0;
+        // boost::split(.., "*", token_compress_on) (dna_seq.cc:17): fragments are the maximal stop-free runs
+        if (FILL && out_staged && ncod <= 64u) {
+            // Lanes meet their stops at different codons, so copying "the run that just ended" would serialise the warp.
+            // Instead: one pass marks the codons of kept runs in a 64-bit mask (and emits the fragment offsets), a second
+            // pass -- the same trip count in every lane -- stores the marked residues.
+            unsigned long long keep = 0ull;
+            const uint64_t r_begin = rcur;
+            for (uint32_t k = 0; k <= ncod; k++) {
+                const char a = k < ncod ? frame_aa(read, len, slot, k, tbl) : '*';
+                if (a != '*') { run++; continue; }
+                if (run > min_len) {
+                    frag_off[fcur++] = rcur;
+                    rcur += run;
+                    keep |= (run >= 64u ? ~0ull : ((1ull << run) - 1ull)) << (k - run);
+                }
+                run = 0;
+            }
+            uint8_t *dst = s_out + ophase + (uint32_t)(r_begin - out0);
+            for (uint32_t k = 0; k < ncod; k++)
+                if ((keep >> k) & 1ull) *dst++ = (uint8_t)frame_aa(read, len, slot, k, tbl);
+        } else {
+            for (uint32_t k = 0; k <= ncod; k++) {
+                const char a = k < ncod ? frame_aa(read, len, slot, k, tbl) : '*';
+                if (a != '*') { run++; continue; }
+                if (run > min_len) {  // prot.length() > 10 (fq_process_request.cc:331)
+                    if (FILL) {
+                        frag_off[fcur++] = rcur;
+                        if (out_staged) {
+                            uint8_t *dst = s_out + ophase + (uint32_t)(rcur - out0);
+                            for (uint32_t j = k - run; j < k; j++) *dst++ = (uint8_t)frame_aa(read, len, slot, j, tbl);
+                            rcur += run;
+                        } else {
+                            for (uint32_t j = k - run; j < k; j++) frag_res[rcur++] = (uint8_t)frame_aa(read, len, slot, j, tbl);
+                        }
+                    }
+                    cnt++;
+                    aa_total += run;
+                }
+                run = 0;
+            }
+        }
+        if (!FILL) { nfrag[t] = cnt; naa[t] = aa_total; }
+    }
+    if (FILL) {
+        __syncthreads();
+        if (out_staged && out1 > out0) {
+            uint8_t *gbase = frag_res + out0 - ophase;  // 16-byte aligned
+            const uint32_t span = ophase + (uint32_t)(out1 - out0);
+            const uint32_t first_full = ophase ? 1u : 0u, n_vec = span >> 4;  // vectors [first_full, n_vec) are fully ours
+            for (uint32_t v = first_full + threadIdx.x; v < n_vec; v += blockDim.x)
+                reinterpret_cast<uint4 *>(gbase)[v] = reinterpret_cast<const uint4 *>(s_out)[v];
+            // the partial vectors at both ends belong partly to the neighbouring blocks: bytes
+            if (ophase) {
+                const uint32_t e = min(16u, span);
+                for (uint32_t b = ophase + threadIdx.x; b < e; b += blockDim.x) gbase[b] = s_out[b];
+            }
+            const uint32_t tail0 = max(n_vec << 4, ophase ? 16u : 0u);
+            for (uint32_t b = tail0 + threadIdx.x; b < span; b += blockDim.x) gbase[b] = s_out[b];
+        }
+    }
 }
 
 // best frame per read (fq_process_request.cc:319-348): frames in slot order, score is a double sum of the
