@@ -20,6 +20,7 @@
 #include "ckm_common.cuh"
 #include "ckm_ctx.h"
 #include "ckm_probe.cuh"
+#include "ckm_probe_group.cuh"
 #include "ckm_scan.cuh"
 #include "ckm_util.cuh"
 
@@ -549,6 +550,7 @@ static int prefix_sum(ckm_ctx *c, const uint32_t *d_in, uint64_t n, uint64_t *d_
 
 struct RunPlan {
     bool want_scan, general, want_keys, want_avg;
+    uint32_t probe_group;  // lanes per sequence in K1: 32 (probe_kernel) or 8 / 16 (probe_group_kernel, short sequences)
 };
 
 // size the per-batch regions (indexed by residue offset / sequence index, so chunked launches can share them)
@@ -557,6 +559,15 @@ static int prepare_regions(ckm_ctx *c, uint32_t n, uint64_t total, uint32_t max_
     c->cur_total = total;
     c->cur_flags = flags;
     plan->want_scan = flags & (CKM_WANT_CALLS | CKM_WANT_OTU | CKM_WANT_BEST);
+    {
+        // by mean length: a group step covers 4*G start positions
+        const uint64_t mean = n ? total / n : 0;
+        plan->probe_group = (n >= 64 && mean <= 48) ? 8u : (n >= 64 && mean <= 96) ? 16u : 32u;
+        if (const char *pg = getenv("CKM_PROBE_GROUP")) {
+            const int g = atoi(pg);
+            if (g == 8 || g == 16 || g == 32) plan->probe_group = (uint32_t)g;
+        }
+    }
     plan->general = plan->want_scan && (c->prm.order_constraint != 0 || max_len == 0 || max_len > kHitCap + CKM_KMER_SIZE);
     plan->want_keys = flags & CKM_WANT_HITS;
     plan->want_avg = (flags & CKM_WANT_HITS) || (plan->want_scan && c->prm.order_constraint != 0);
@@ -602,7 +613,20 @@ static int launch_range(ckm_ctx *c, cudaStream_t stream, const uint8_t *d_res, c
         blocks = std::min<uint64_t>(blocks, ((uint64_t)c->sm_count * (bps ? bps : 8)) << (gshift ? gshift - 1 : 3));
         uint64_t *keys = plan.want_keys ? (uint64_t *)c->hit_keys.p : nullptr;
         uint16_t *avg = plan.want_avg ? (uint16_t *)c->hit_avg.p : nullptr;
-        if (c->slot_bytes == kPackedSlotBytes)
+        // short sequences (fastq fragments, peptides): a group of 8 or 16 lanes per sequence instead of a warp
+        const uint32_t group = plan.probe_group;
+        if (group < 32u) {
+            const uint32_t per_block = warps_per_block * (32u / group);
+            const unsigned gb = (unsigned)std::min<uint64_t>(((uint64_t)cnt + per_block - 1) / per_block, (uint64_t)c->sm_count * 64);
+            HitRec *hp = (HitRec *)c->hits.p;
+            uint32_t *nh = (uint32_t *)c->n_hits.p + i0;
+            unsigned long long *tot = (unsigned long long *)c->totals.p;
+            const bool packed = c->slot_bytes == kPackedSlotBytes;
+            if (packed && group == 8u) probe_group_kernel<true, 8><<<gb, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
+            else if (packed) probe_group_kernel<true, 16><<<gb, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
+            else if (group == 8u) probe_group_kernel<false, 8><<<gb, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
+            else probe_group_kernel<false, 16><<<gb, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
+        } else if (c->slot_bytes == kPackedSlotBytes)
             probe_kernel<true><<<(unsigned)blocks, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, (HitRec *)c->hits.p, keys, avg,
                                                                                (uint32_t *)c->n_hits.p + i0,
                                                                                (unsigned long long *)c->totals.p);

@@ -51,6 +51,44 @@ def test_call_batch_bit_exact(checkers, world, prm):
     assert len(want["calls"]) > 100
 
 
+@pytest.mark.parametrize("group", ["8", "16"])
+def test_group_probe_kernel_bit_exact(checkers, world, group):
+    """probe_group_kernel (8 / 16 lanes per sequence, chosen for batches of short sequences) against the oracle: forced on
+    the mixed edge + protein batch, with and without the occupancy bitmap, and picked by itself on short peptides."""
+    protos, sig, img, orc, guts, guts_raw = world
+    batch = wl.concat_batches(wl.edge_batch(protos), synth.make_proteins(4, protos, 3000))
+    rng = np.random.default_rng(8)
+    full = synth.make_proteins(14, protos, 4000)
+    cuts = [full.seq(i)[int(a):int(a) + int(l)] for i, (a, l) in enumerate(zip(rng.integers(0, 200, full.n), rng.integers(0, 70, full.n)))]
+    short = synth.batch_from_strings(cuts)  # mean ~35 residues, many under 9 (no window) and some empty
+    os.environ["CKM_PROBE_GROUP"] = group
+    try:
+        for prm in (dict(), dict(order_constraint=1, min_hits=2, max_gap=30)):
+            orc.set_params(**prm)
+            for b in (batch, short):
+                want = orc.call_batch(b, ALL)
+                for g, nm in ((guts, "packed16"), (guts_raw, "raw24")):
+                    g.set_parameters(prm)
+                    got = g.process_aa_seq_batch(b.residues, b.offsets, ALL)
+                    wl.assert_results_equal(got, want, f"group {group} [{nm}] {prm}")
+                    assert got["n_probes"] == want["n_probes"] and got["n_hits"] == len(want["hits"])
+        os.environ["CKM_OCCUPANCY_BITMAP"] = "1"
+        g = api.KmerGuts(image=img, function_names=synth.function_names(sig.n_functions))
+        g.set_parameters(prm)
+        wl.assert_results_equal(g.process_aa_seq_batch(short.residues, short.offsets, ALL), orc.call_batch(short, ALL), "group + bitmap")
+        g.close()
+    finally:
+        os.environ.pop("CKM_PROBE_GROUP", None)
+        os.environ.pop("CKM_OCCUPANCY_BITMAP", None)
+        orc.set_params()
+        guts.set_default_parameters()
+        guts_raw.set_default_parameters()
+    # without the override the short batch selects a group kernel on its own (mean length <= 48), the proteins do not
+    want = orc.call_batch(short, ALL)
+    wl.assert_results_equal(guts.process_aa_seq_batch(short.residues, short.offsets, ALL), want, "auto group")
+    assert len(want["hits"]) > 1000
+
+
 def test_occupancy_bitmap_and_pipelined_host_path(checkers, world):
     """The two large-table mechanisms, forced on a small table: the L2-resident slot-occupancy bitmap (skips the
     DRAM read of empty slots) and the chunked two-stream host path used for find_best_call-only batches."""
