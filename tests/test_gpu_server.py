@@ -363,6 +363,56 @@ def test_server_family_paths(checkers, world, server):
     assert hits > 20, hits
 
 
+def test_server_two_devices_concurrent_connections(checkers, world, server):
+    """--device 0,1: the family table built on device 0 is replicated to device 1 (export + load), engines on both devices
+    serve concurrent connections; every response still equals the reference's."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    protos, sig, img, fam, d = world
+    ref = server[1]
+    pf = os.path.join(d, "port2")
+    log = open(pf + ".log", "w")
+    proc = subprocess.Popen([os.path.join(os.path.dirname(build.LIB), "kser_b200"), "--listen-port-file", pf, "--device", "0,1",
+                             "--n-kmer-threads", "2", "--batch-mb", "1", "0", d], stdout=log, stderr=subprocess.STDOUT)
+    try:
+        port = None
+        for _ in range(1200):
+            if proc.poll() is not None:
+                break
+            if os.path.exists(pf) and open(pf).read().strip():
+                port = int(open(pf).read())
+                break
+            time.sleep(0.1)
+        assert port is not None, open(pf + ".log").read()[-3000:]
+        batch = clean_batch(protos, 62, 2000)
+        ids = [f"fig|9.9.peg.{i}" for i in range(batch.n)]
+        body = fasta(ids, batch)
+        want = OK_HEADER + ref.query_text(ids, batch, 0, 0)
+        prot = clean_batch(protos, 72, 400)
+        pids = [f"p{i}" for i in range(prot.n)]
+        want_lookup = ref.lookup_text(pids, prot)
+        out = [None] * 8
+
+        def one(k):
+            out[k] = post(port, "/query", body) if k % 2 == 0 else post(port, "/lookup", fasta(pids, prot))
+
+        ts = [threading.Thread(target=one, args=(k,)) for k in range(8)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        for k in range(8):
+            if k % 2 == 0:
+                assert out[k] == want
+            else:
+                assert out[k].startswith(OK_HEADER)
+                assert_lookup_listing_equal(out[k][len(OK_HEADER):], want_lookup)
+        assert http(port, b"GET /quit HTTP/1.1\r\n\r\n").endswith("OK, quitting\n")
+        assert proc.wait(timeout=60) == 0
+    finally:
+        if proc.poll() is None:
+            proc.kill()
+
+
 def test_server_add_and_matrix(world, server):
     protos = world[0]
     port, ref = server[0], server[1]
