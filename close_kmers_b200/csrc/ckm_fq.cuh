@@ -35,17 +35,25 @@ __device__ __forceinline__ void fill_aa11(char *tbl /* 65, shared */) {
     if (threadIdx.x == 64) tbl[64] = 'X';
 }
 
-// amino acid of codon k of frame slot `slot` (0..2 forward, 3..5 reverse complement) of read[0..len)
-__device__ __forceinline__ char frame_aa(const uint8_t *read, uint32_t len, uint32_t slot, uint32_t k, const char *tbl) {
+// base_code for every byte value, for branch-free lookups
+__device__ __forceinline__ void fill_base_lut(uint8_t *lut /* 256, shared */) {
+    for (uint32_t c = threadIdx.x; c < 256u; c += blockDim.x) lut[c] = (uint8_t)base_code((uint8_t)c);
+}
+
+// amino acid of codon k of frame slot `slot` (0..2 forward, 3..5 reverse complement) of read[0..len).  CODES: `read`
+// already holds base codes (the staged copy), else raw bytes that go through `blut`.  No branches: lanes of one warp
+// serve forward and reverse frames side by side.
+template <bool CODES>
+__device__ __forceinline__ char frame_aa(const uint8_t *read, uint32_t len, uint32_t slot, uint32_t k, const char *tbl,
+                                         const uint8_t *blut) {
     const uint32_t off = (slot % 3u) + 3u * k;
-    uint32_t c0, c1, c2;
-    if (slot < 3u) {
-        c0 = base_code(read[off]); c1 = base_code(read[off + 1]); c2 = base_code(read[off + 2]);
-    } else {  // reverse_seq(): complement of the reversed read; complement() keeps non-ACGTU letters ambiguous
-        c0 = base_code(read[len - 1 - off]); c1 = base_code(read[len - 2 - off]); c2 = base_code(read[len - 3 - off]);
-        c0 = c0 < 4u ? 3u - c0 : 4u; c1 = c1 < 4u ? 3u - c1 : 4u; c2 = c2 < 4u ? 3u - c2 : 4u;
-    }
-    return tbl[(c0 < 4u && c1 < 4u && c2 < 4u) ? c0 * 16u + c1 * 4u + c2 : 64u];
+    const bool rev = slot >= 3u;
+    // reverse_seq(): complement of the reversed read; complement() keeps non-ACGTU letters ambiguous
+    const uint32_t i0 = rev ? len - 1u - off : off, i1 = rev ? i0 - 1u : i0 + 1u, i2 = rev ? i0 - 2u : i0 + 2u;
+    uint32_t c0 = CODES ? read[i0] : blut[read[i0]], c1 = CODES ? read[i1] : blut[read[i1]], c2 = CODES ? read[i2] : blut[read[i2]];
+    const bool ok = (c0 | c1 | c2) < 4u;
+    if (rev) { c0 = 3u - c0; c1 = 3u - c1; c2 = 3u - c2; }
+    return tbl[ok ? c0 * 16u + c1 * 4u + c2 : 64u];
 }
 
 constexpr uint32_t kFqReadsPerBlock = 42;   // 252 of the block's 256 threads
@@ -59,9 +67,11 @@ fq_frames_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__
                  const uint64_t *__restrict__ frag_base, const uint64_t *__restrict__ res_base,  // fill pass inputs
                  uint64_t *__restrict__ frag_off, uint8_t *__restrict__ frag_res) {
     __shared__ char tbl[65];
+    __shared__ uint8_t blut[256];
     __shared__ __align__(16) uint8_t s_bases[kFqStageBytes + 16];
     __shared__ __align__(16) uint8_t s_out[FILL ? kFqOutBytes + 32 : 16];
     fill_aa11(tbl);
+    fill_base_lut(blut);
     // the block's reads (kFqReadsPerBlock consecutive ones, six threads each) are staged in shared memory with
     // coalesced word loads when they fit; every base is then read six times (once per frame) from there
     const uint32_t r0 = blockIdx.x * kFqReadsPerBlock;
@@ -69,10 +79,15 @@ fq_frames_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__
     const uint64_t blk0 = r0 < n ? offsets[r0] : 0, blk1 = r0 < n ? offsets[r1] : 0;
     const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(bases + blk0) & 3u);
     const bool staged = (blk1 - blk0) + mis <= kFqStageBytes;
-    if (staged) {
+    __syncthreads();  // blut is read below
+    if (staged) {  // ... as base codes (trans_table.h:47-68), four per word
         const uint32_t *src = reinterpret_cast<const uint32_t *>(bases + blk0 - mis);
         const uint32_t words = (uint32_t)((blk1 - blk0) + mis + 3u) >> 2;
-        for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) reinterpret_cast<uint32_t *>(s_bases)[w] = __ldg(src + w);
+        for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) {
+            const uint32_t v = __ldg(src + w);
+            reinterpret_cast<uint32_t *>(s_bases)[w] = (uint32_t)blut[v & 0xFFu] | ((uint32_t)blut[(v >> 8) & 0xFFu] << 8) |
+                                                       ((uint32_t)blut[(v >> 16) & 0xFFu] << 16) | ((uint32_t)blut[v >> 24] << 24);
+        }
     }
     // fill pass: the block's fragments are one contiguous range of the output (frames are laid out in thread order), so
     // residues are assembled in shared memory, at the same 16-byte phase as their destination, and leave as whole
@@ -105,7 +120,7 @@ fq_frames_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__
             unsigned long long keep = 0ull;
             const uint64_t r_begin = rcur;
             for (uint32_t k = 0; k <= ncod; k++) {
-                const char a = k < ncod ? frame_aa(read, len, slot, k, tbl) : '*';
+                const char a = k < ncod ? (staged ? frame_aa<true>(read, len, slot, k, tbl, blut) : frame_aa<false>(read, len, slot, k, tbl, blut)) : '*';
                 if (a != '*') { run++; continue; }
                 if (run > min_len) {
                     frag_off[fcur++] = rcur;
@@ -116,20 +131,20 @@ fq_frames_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__
             }
             uint8_t *dst = s_out + ophase + (uint32_t)(r_begin - out0);
             for (uint32_t k = 0; k < ncod; k++)
-                if ((keep >> k) & 1ull) *dst++ = (uint8_t)frame_aa(read, len, slot, k, tbl);
+                if ((keep >> k) & 1ull) *dst++ = (uint8_t)(staged ? frame_aa<true>(read, len, slot, k, tbl, blut) : frame_aa<false>(read, len, slot, k, tbl, blut));
         } else {
             for (uint32_t k = 0; k <= ncod; k++) {
-                const char a = k < ncod ? frame_aa(read, len, slot, k, tbl) : '*';
+                const char a = k < ncod ? (staged ? frame_aa<true>(read, len, slot, k, tbl, blut) : frame_aa<false>(read, len, slot, k, tbl, blut)) : '*';
                 if (a != '*') { run++; continue; }
                 if (run > min_len) {  // prot.length() > 10 (fq_process_request.cc:331)
                     if (FILL) {
                         frag_off[fcur++] = rcur;
                         if (out_staged) {
                             uint8_t *dst = s_out + ophase + (uint32_t)(rcur - out0);
-                            for (uint32_t j = k - run; j < k; j++) *dst++ = (uint8_t)frame_aa(read, len, slot, j, tbl);
+                            for (uint32_t j = k - run; j < k; j++) *dst++ = (uint8_t)(staged ? frame_aa<true>(read, len, slot, j, tbl, blut) : frame_aa<false>(read, len, slot, j, tbl, blut));
                             rcur += run;
                         } else {
-                            for (uint32_t j = k - run; j < k; j++) frag_res[rcur++] = (uint8_t)frame_aa(read, len, slot, j, tbl);
+                            for (uint32_t j = k - run; j < k; j++) frag_res[rcur++] = (uint8_t)(staged ? frame_aa<true>(read, len, slot, j, tbl, blut) : frame_aa<false>(read, len, slot, j, tbl, blut));
                         }
                     }
                     cnt++;
