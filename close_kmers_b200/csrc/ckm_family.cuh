@@ -20,7 +20,8 @@ namespace ckm {
 
 constexpr uint32_t kFamSmemCap = 1024;  // slots of the per-warp shared-memory maps
 constexpr uint32_t kFamSmemE = 512;     // use them when the protein has at most this many list entries (cap = 2E)
-constexpr int kFamStage = 8;            // list entries prefetched per hit
+constexpr int kFamStage = 8;            // list entries prefetched per hit (matrix_row_kernel)
+constexpr uint32_t kFamEntries = 256;   // (family, weight) entries of 32 hits staged per step by fam_vote_kernel
 // Two instantiations of fam_vote_kernel share one batch: SMALL (maps of <= kFamSmallCap slots, 8 warps per block, 4
 // blocks per SM) takes the proteins whose map fits -- every fastq fragment does -- and LARGE (1024-slot maps, 4 warps per
 // block, 2 blocks per SM) takes the rest, including those whose maps live in global scratch.
@@ -28,7 +29,7 @@ constexpr uint32_t kFamSmallCap = 256;
 template <uint32_t CAP>
 struct FamVoteCfg {
     static constexpr int kWarps = CAP <= kFamSmallCap ? 8 : 4;
-    static constexpr uint32_t kWarpWords = 5 * CAP + 32 * kFamStage;
+    static constexpr uint32_t kWarpWords = 5 * CAP + 2 * kFamEntries;
     static constexpr size_t kSmem = (size_t)kWarps * kWarpWords * 4;
 };
 
@@ -160,7 +161,8 @@ fam_vote_kernel(FamTables ft, const uint64_t *__restrict__ offsets, const uint32
     float *const s_w = reinterpret_cast<float *>(my_smem + 2 * CAP);
     uint32_t *const s_pkeys = my_smem + 3 * CAP;
     float *const s_pw = reinterpret_cast<float *>(my_smem + 4 * CAP);
-    uint32_t(*const s_stage)[kFamStage] = reinterpret_cast<uint32_t(*)[kFamStage]>(my_smem + 5 * CAP);
+    uint32_t *const s_fam = my_smem + 5 * CAP;
+    float *const s_wt = reinterpret_cast<float *>(my_smem + 5 * CAP + kFamEntries);
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t i = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < n; i += n_warps) {
         uint32_t *keys, *cnt, *pkeys, cap;
@@ -184,26 +186,68 @@ fam_vote_kernel(FamTables ft, const uint64_t *__restrict__ offsets, const uint32
         __syncwarp();
 
         // ---- F1: on_hit for every hit, in position order (family_mapper.cc:287-330) ----
+        // A family's weighted_total is an f32 sum in hit order, so additions to ONE family are a serial chain -- but the
+        // map look-ups are not.  Per step of 32 hits: every hit lane writes its (family, 1/|list|) entries, in hit order,
+        // into a shared-memory list; then lanes = entries: each finds or claims its family's slot (one atomicCAS latency
+        // for 32 entries instead of one per hit), entries that share a slot are ranked by lane (= hit order) with
+        // match.any, and the additions are applied rank by rank.
         if (E[i] != 0) {
             for (uint32_t k0 = 0; k0 < nh; k0 += 32) {
                 const uint2 my = (k0 + lane < nh) ? hit_fam[base + k0 + lane] : make_uint2(0u, 0u);
-                for (uint32_t t = 0; t < min(my.y, (uint32_t)kFamStage); t++) s_stage[lane][t] = ft.fam_ids[my.x + t];
-                __syncwarp();
-                const uint32_t lim = min(32u, nh - k0);
-                for (uint32_t j = 0; j < lim; j++) {
-                    const uint32_t off_j = __shfl_sync(0xffffffffu, my.x, j);
-                    const uint32_t cnt_j = __shfl_sync(0xffffffffu, my.y, j);
-                    if (cnt_j == 0) continue;
-                    const float weight = 1.0f / (float)cnt_j;  // 1.0f / counts.size(), family_mapper.cc:300
-                    for (uint32_t t = lane; t < cnt_j; t += 32) {
-                        const uint32_t fam = t < (uint32_t)kFamStage ? s_stage[j][t] : ft.fam_ids[off_j + t];
-                        if (fam >= ft.n_fams) continue;  // no family_data_ entry: never reported (146-148)
-                        bool fresh;
-                        const uint32_t s = map_slot(keys, mask, fam + 1, &fresh);
-                        if (fresh) { cnt[s] = 1u; wsum[s] = 0.0f + weight; }
-                        else { cnt[s] += 1u; wsum[s] += weight; }
+                uint32_t incl = my.y;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= (uint32_t)d) incl += t;
+                }
+                const uint32_t n_ent = __shfl_sync(0xffffffffu, incl, 31);
+                if (n_ent == 0) continue;
+                if (n_ent <= kFamEntries) {
+                    const float weight = 1.0f / (float)my.y;  // 1.0f / counts.size(), family_mapper.cc:300
+                    uint32_t e = incl - my.y;
+                    for (uint32_t t = 0; t < my.y; t++, e++) {
+                        s_fam[e] = ft.fam_ids[my.x + t];
+                        s_wt[e] = weight;
                     }
                     __syncwarp();
+                    for (uint32_t e0 = 0; e0 < n_ent; e0 += 32) {
+                        const uint32_t me = e0 + lane;
+                        const uint32_t fam = me < n_ent ? s_fam[me] : 0xffffffffu;
+                        const bool ok = fam < ft.n_fams;  // no family_data_ entry: never reported (146-148)
+                        uint32_t slot = 0x80000000u | lane;  // distinct for idle lanes
+                        float w = 0.0f;
+                        if (ok) {
+                            bool fresh;
+                            slot = map_slot(keys, mask, fam + 1, &fresh);
+                            if (fresh) { cnt[slot] = 0u; wsum[slot] = 0.0f; }
+                            w = s_wt[me];
+                        }
+                        __syncwarp();
+                        const uint32_t peers = __match_any_sync(0xffffffffu, slot);
+                        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+                        const uint32_t last = __reduce_max_sync(0xffffffffu, ok ? rank : 0u);
+                        for (uint32_t r = 0; r <= last; r++) {
+                            if (ok && rank == r) { cnt[slot] += 1u; wsum[slot] += w; }
+                            __syncwarp();
+                        }
+                    }
+                } else {  // a step with very long lists: hit by hit, lanes = entries of one hit
+                    const uint32_t lim = min(32u, nh - k0);
+                    for (uint32_t j = 0; j < lim; j++) {
+                        const uint32_t off_j = __shfl_sync(0xffffffffu, my.x, j);
+                        const uint32_t cnt_j = __shfl_sync(0xffffffffu, my.y, j);
+                        if (cnt_j == 0) continue;
+                        const float weight = 1.0f / (float)cnt_j;
+                        for (uint32_t t = lane; t < cnt_j; t += 32) {
+                            const uint32_t fam = ft.fam_ids[off_j + t];
+                            if (fam >= ft.n_fams) continue;
+                            bool fresh;
+                            const uint32_t sl = map_slot(keys, mask, fam + 1, &fresh);
+                            if (fresh) { cnt[sl] = 1u; wsum[sl] = 0.0f + weight; }
+                            else { cnt[sl] += 1u; wsum[sl] += weight; }
+                        }
+                        __syncwarp();
+                    }
                 }
                 __syncwarp();
             }
