@@ -15,6 +15,8 @@
 
 #include <algorithm>
 #include <string>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "ckm_common.cuh"
@@ -740,6 +742,59 @@ extern "C" int ckm_read_totals(ckm_ctx *c, uint64_t totals[3]) {
 }
 
 // H2D of one batch: residues (+32 zeroed bytes of slack) and offsets rebased to 0
+// Host-to-device copy of a large PAGEABLE buffer.  cudaMemcpyAsync from pageable memory is staged by the driver on the
+// calling thread at ~10 GB/s; here kStageThreads workers copy alternate 8 MB chunks into their own page-locked buffers and
+// queue the DMA behind them, so the host-side copies run in parallel and overlap the transfers.  ctx->stream is made to
+// wait for every chunk.  (Page-locked caller memory goes straight to cudaMemcpyAsync.)
+static int staged_upload(ckm_ctx *c, void *dst, const char *src, size_t bytes) {
+    constexpr int T = ckm_ctx::kStageThreads;
+    constexpr size_t CH = ckm_ctx::kStageChunk;
+    for (int t = 0; t < T; t++) {
+        if (!c->stage_stream[t]) CU(cudaStreamCreateWithFlags(&c->stage_stream[t], cudaStreamNonBlocking));
+        for (int k = 0; k < 2; k++) {
+            RC(c->stage_buf[t][k].ensure(CH));
+            if (!c->stage_ev[t][k]) CU(cudaEventCreateWithFlags(&c->stage_ev[t][k], cudaEventDisableTiming));
+        }
+    }
+    // the destination may still be read by work queued on ctx->stream
+    if (!c->ev_ready) CU(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
+    CU(cudaEventRecord(c->ev_ready, c->stream));
+    const size_t n_chunks = (bytes + CH - 1) / CH;
+    std::atomic<int> failed{0};
+    auto worker = [&](int t) {
+        if (cudaSetDevice(c->device) != cudaSuccess) { failed = 1; return; }
+        if (cudaStreamWaitEvent(c->stage_stream[t], c->ev_ready, 0) != cudaSuccess) { failed = 1; return; }
+        int k = 0;
+        for (size_t i = (size_t)t; i < n_chunks; i += T, k ^= 1) {
+            const size_t o = i * CH, len = std::min(CH, bytes - o);
+            if (cudaEventSynchronize(c->stage_ev[t][k]) != cudaSuccess) { failed = 1; return; }  // buffer k free again
+            memcpy(c->stage_buf[t][k].p, src + o, len);
+            if (cudaMemcpyAsync((char *)dst + o, c->stage_buf[t][k].p, len, cudaMemcpyHostToDevice, c->stage_stream[t]) != cudaSuccess ||
+                cudaEventRecord(c->stage_ev[t][k], c->stage_stream[t]) != cudaSuccess) { failed = 1; return; }
+        }
+    };
+    std::thread th[T];
+    for (int t = 1; t < T; t++) th[t] = std::thread(worker, t);
+    worker(0);
+    for (int t = 1; t < T; t++) th[t].join();
+    if (failed) {
+        (void)cudaGetLastError();
+        return ckm_fail(CKM_ECUDA, "staged host-to-device copy failed");
+    }
+    for (int t = 0; t < T; t++)
+        for (int k = 0; k < 2; k++) CU(cudaStreamWaitEvent(c->stream, c->stage_ev[t][k], 0));
+    return 0;
+}
+
+static bool is_pageable(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
 static int upload_batch(ckm_ctx *c, const char *residues, const uint64_t *offsets, uint32_t n, uint64_t *total_out,
                         uint32_t *max_len_out) {
     if (!offsets || (n && !residues && offsets[n] != offsets[0])) return ckm_fail(CKM_EINVAL, "NULL argument");
@@ -754,7 +809,10 @@ static int upload_batch(ckm_ctx *c, const char *residues, const uint64_t *offset
     const uint64_t total = offsets[n] - offsets[0];
     RC(c->in_res.ensure(total + 32));
     RC(c->in_off.ensure(((size_t)n + 1) * 8));
-    if (total) CU(cudaMemcpyAsync(c->in_res.p, residues + offsets[0], total, cudaMemcpyHostToDevice, c->stream));
+    if (total >= (32u << 20) && !getenv("CKM_NO_STAGED_UPLOAD") && is_pageable(residues + offsets[0]))
+        RC(staged_upload(c, c->in_res.p, residues + offsets[0], total));
+    else if (total)
+        CU(cudaMemcpyAsync(c->in_res.p, residues + offsets[0], total, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemsetAsync((uint8_t *)c->in_res.p + total, 0, 32, c->stream));
     const uint64_t *h_off = offsets;
     if (offsets[0] != 0) {

@@ -104,6 +104,13 @@ struct ckm_ctx {
         PinBuf h_frag_base, h_frag_off, h_frag_res, h_best_frame, h_best_score, h_match_off, h_matches;
     } fq;
 
+    // staged upload of pageable caller memory (upload_batch): per worker thread two pinned buffers, a stream and two events
+    static constexpr int kStageThreads = 4;
+    static constexpr size_t kStageChunk = 8u << 20;
+    PinBuf stage_buf[kStageThreads][2];
+    cudaStream_t stage_stream[kStageThreads] = {};
+    cudaEvent_t stage_ev[kStageThreads][2] = {};
+
     // pinned host buffers handed out through ckm_batch_out_t
     PinBuf h_off, h_totals, h_hit_off, h_hits, h_call_off, h_calls, h_otu_off, h_otus, h_best;
 
@@ -133,6 +140,15 @@ struct ckm_ctx {
         PinBuf *qh[] = {&fq.h_frag_base, &fq.h_frag_off, &fq.h_frag_res, &fq.h_best_frame, &fq.h_best_score, &fq.h_match_off,
                         &fq.h_matches};
         for (auto b : qh) b->release();
+        for (int t = 0; t < kStageThreads; t++) {
+            for (int k = 0; k < 2; k++) {
+                stage_buf[t][k].release();
+                if (stage_ev[t][k]) cudaEventDestroy(stage_ev[t][k]);
+                stage_ev[t][k] = nullptr;
+            }
+            if (stage_stream[t]) cudaStreamDestroy(stage_stream[t]);
+            stage_stream[t] = nullptr;
+        }
         PinBuf *h[] = {&h_off, &h_totals, &h_hit_off, &h_hits, &h_call_off, &h_calls, &h_otu_off, &h_otus, &h_best, &h_fam};
         for (auto b : h) b->release();
     }
