@@ -190,6 +190,29 @@ def build_image(nbuckets: int, keys, fI, oI, avg, wt) -> np.ndarray:
     return img
 
 
+def build_image_device(nbuckets: int, keys, fI, oI, avg, wt, device: int = 0) -> np.ndarray:
+    """The same file bytes built on the GPU (write_hashtable, build_signature_kmers.cc:860-898)."""
+    keys = np.ascontiguousarray(keys, np.uint64)
+    fI = np.ascontiguousarray(fI, np.int32)
+    oI = np.ascontiguousarray(oI, np.int32)
+    avg = np.ascontiguousarray(avg, np.uint16)
+    wt = np.ascontiguousarray(wt, np.float32)
+    img = np.empty(24 + 24 * nbuckets, dtype=np.uint8)
+    L = lib()
+    L.ckm_image_build_device.argtypes = [C.c_int, C.c_uint64, C.c_uint64] + [C.c_void_p] * 6 + [C.c_size_t]
+    _check(L.ckm_image_build_device(device, nbuckets, len(keys), keys.ctypes.data, fI.ctypes.data, oI.ctypes.data, avg.ctypes.data,
+                                    wt.ctypes.data, img.ctypes.data, img.nbytes))
+    return img
+
+
+def signature_weight(NSF, KS, NSi, NFj, NSiFj) -> float:
+    """compute_weight_of_signature (build_signature_kmers.cc:841-853)."""
+    L = lib()
+    L.ckm_signature_weight.restype = C.c_float
+    L.ckm_signature_weight.argtypes = [C.c_float] * 5
+    return L.ckm_signature_weight(NSF, KS, NSi, NFj, NSiFj)
+
+
 def save_kmer_hash_table(image: np.ndarray, kmer_dir: str) -> None:
     image.tofile(os.path.join(kmer_dir, "kmer.table.mem_map"))
 
@@ -327,10 +350,26 @@ class KmerGuts:
     """Batch mirror of ``KmerGuts(kmer_dir, image)`` (kguts.cc:34-58)."""
 
     def __init__(self, kmer_dir: str | None = None, image: np.ndarray | None = None, device: int = 0,
-                 function_names=None, otu_names=None):
+                 function_names=None, otu_names=None, built=None):
+        """built = (nbuckets, keys, fI, oI, avg, wt): build the table on the GPU and open it (ckm_open_built)."""
         L = lib()
         h = C.c_void_p()
-        if image is not None:
+        if built is not None:
+            nb, keys, fI, oI, avg, wt = built
+            keys = np.ascontiguousarray(keys, np.uint64)
+            fI = np.ascontiguousarray(fI, np.int32)
+            oI = np.ascontiguousarray(oI, np.int32)
+            avg = np.ascontiguousarray(avg, np.uint16)
+            wt = np.ascontiguousarray(wt, np.float32)
+            fn = [s.encode() for s in (function_names or [])]
+            on = [s.encode() for s in (otu_names or [])]
+            fa = (C.c_char_p * len(fn))(*fn)
+            oa = (C.c_char_p * len(on))(*on)
+            L.ckm_open_built.argtypes = [C.c_int, C.c_uint64, C.c_uint64] + [C.c_void_p] * 5 + [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                                                                           C.POINTER(C.c_void_p)]
+            _check(L.ckm_open_built(device, nb, len(keys), keys.ctypes.data, fI.ctypes.data, oI.ctypes.data, avg.ctypes.data,
+                                    wt.ctypes.data, fa, len(fn), oa, len(on), C.byref(h)))
+        elif image is not None:
             fn = [s.encode() for s in (function_names or [])]
             on = [s.encode() for s in (otu_names or [])]
             fa = (C.c_char_p * len(fn))(*fn)

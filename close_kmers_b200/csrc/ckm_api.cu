@@ -5,6 +5,7 @@
 // compute entry point launches the sm_100a kernels or fails with CKM_ECUDA.
 #include <cuda_runtime.h>
 #include <fcntl.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -164,6 +165,8 @@ static int select_device(int device) {
     return 0;
 }
 
+static int install_table(ckm_ctx *c, DevBuf raw, uint64_t n);
+
 static int upload_table(ckm_ctx *c, const ckm_image_header_t *hdr) {
     const uint64_t n = hdr->num_sigs;
     const uint8_t *src = reinterpret_cast<const uint8_t *>(hdr + 1);
@@ -173,6 +176,12 @@ static int upload_table(ckm_ctx *c, const ckm_image_header_t *hdr) {
     const size_t chunk = (size_t)1 << 28;
     for (size_t o = 0; o < raw_bytes; o += chunk)
         CU(cudaMemcpyAsync((uint8_t *)raw.p + o, src + o, std::min(chunk, raw_bytes - o), cudaMemcpyHostToDevice, c->stream));
+    return install_table(c, raw, n);
+}
+
+// the verbatim 24-byte slots are on the device (uploaded, or built there): repack, choose the slot format, build the
+// occupancy bitmap.  Takes ownership of `raw`.
+static int install_table(ckm_ctx *c, DevBuf raw, uint64_t n) {
     DevBuf packed, flag;
     RC(packed.ensure((size_t)n * kPackedSlotBytes + 64));
     RC(flag.ensure(256));
@@ -1107,3 +1116,4 @@ extern "C" int ckm_calibrate_gather(ckm_ctx *c, int bytes, int unroll, uint32_t 
 #include "ckm_family.cuh"
 #include "ckm_fq.cuh"
 #include "ckm_matrix.cuh"
+#include "ckm_build.cuh"

@@ -339,6 +339,21 @@ int ckm_image_build(uint64_t nbuckets, uint64_t n, const uint64_t *keys, const i
                     const int32_t *otu_index, const uint16_t *avg_from_end, const float *function_wt, void *image_out,
                     size_t image_bytes);
 
+/* The same image built on the GPU ("next" row N4; write_hashtable, build_signature_kmers.cc:860-898).  Byte-identical to
+ * ckm_image_build -- and to the reference's sequential insert_kmer loop -- by priority linear probing with priority =
+ * insertion index (see csrc/ckm_build.cuh).  n < 2^32 - 1. */
+int ckm_image_build_device(int device, uint64_t nbuckets, uint64_t n, const uint64_t *keys, const int32_t *function_index,
+                           const int32_t *otu_index, const uint16_t *avg_from_end, const float *function_wt, void *image_out,
+                           size_t image_bytes);
+/* ... and opened directly, without the file or its host copy: the context ckm_open_image would give for that image. */
+int ckm_open_built(int device, uint64_t nbuckets, uint64_t n, const uint64_t *keys, const int32_t *function_index,
+                   const int32_t *otu_index, const uint16_t *avg_from_end, const float *function_wt,
+                   const char *const *function_names, int32_t n_functions, const char *const *otu_names, int32_t n_otus,
+                   ckm_ctx **out);
+/* compute_weight_of_signature (build_signature_kmers.cc:841-853): NSF = sequences with a signature, KS = distinct
+ * signatures, NSi = sequences containing this k-mer, NFj = sequences with its function, NSiFj = sequences with both. */
+float ckm_signature_weight(float NSF, float KS, float NSi, float NFj, float NSiFj);
+
 /* Calibration for roofline reports: independent random `bytes`-sized (16 or 32) reads over the resident
  * table, `unroll` (1, 4 or 8) in flight per thread, `rounds` rounds, blocks_per_sm x SM-count blocks of 256
  * threads.  Returns accesses per second -- the gather ceiling this GPU sustains at this table size. */

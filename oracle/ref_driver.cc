@@ -29,6 +29,8 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <cmath>
+#include <type_traits>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -628,6 +630,18 @@ char *ref_lookup_text(void *hv, const char *const *ids, const char *residues, co
         }
     }
     return dup_text(os.str());
+}
+
+// compute_weight_of_signature (build_signature_kmers.cc:841-853) with kmer_stats' three numbers passed in; the statement
+// is the reference's, character for character.  The second logarithm's argument is a float expression; like the reference
+// this file sees <cmath> but not <math.h>, so the call is ::log(double) (asserted below).
+static_assert(std::is_same<decltype(log(1.0f)), double>::value,
+              "with the reference's includes an unqualified log(float) is the double function");
+float ref_signature_weight(float NSF, float KS, float NSi, float NFj, float NSiFj) {
+    float weight;
+    weight = log((NSiFj + 1.0) / (NSi - NSiFj + 1.0)) +
+	log((NSF - NFj + KS) / (NFj + KS));
+    return weight;
 }
 
 // The handlers' body parsing: parser_.parse_char over every byte of every packet, parse_complete after the last one

@@ -70,3 +70,23 @@ def test_no_gpu_means_loud_failure_not_fallback():
         assert e.code == -4 and "no CPU fallback" in str(e)
     else:
         g.close()
+
+
+def test_signature_weight_formula(checkers):
+    """compute_weight_of_signature: the library's statement against the reference's, compiled by the reference's compiler."""
+    import ctypes as C
+    if not os.path.exists(checkers.REF_SO):
+        pytest.skip("oracle/_ref/libckm_ref.so not built (needs /root/reference)")
+    R = checkers.Ref().L
+    R.ref_signature_weight.restype = C.c_float
+    R.ref_signature_weight.argtypes = [C.c_float] * 5
+    rng = np.random.default_rng(4)
+    cases = [(1000, 5000, 10, 40, 9), (123456, 9876543, 1, 1, 1), (50, 10, 50, 50, 50), (7, 3, 5, 2, 0)]
+    for _ in range(20000):
+        nsf = int(rng.integers(1, 10**7))
+        nfj = int(rng.integers(1, nsf + 1))
+        nsi = int(rng.integers(1, nsf + 1))
+        cases.append((nsf, int(rng.integers(1, 10**8)), nsi, nfj, int(rng.integers(0, min(nsi, nfj) + 1))))
+    for c in cases:
+        got, want = api.signature_weight(*c), R.ref_signature_weight(*c)
+        assert np.float32(got).tobytes() == np.float32(want).tobytes(), c

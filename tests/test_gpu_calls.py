@@ -256,3 +256,40 @@ def test_randomised_parameters_and_shapes(checkers, world):
             wl.assert_results_equal(g.process_aa_seq_batch(batch.residues, batch.offsets, flags), want, f"trial {trial} {prm} flags={flags}")
     guts.set_default_parameters()
     guts_raw.set_default_parameters()
+
+
+def test_image_built_on_gpu_is_byte_identical(checkers, world):
+    """N4: priority linear probing on the GPU reproduces the sequential insert_kmer loop's file bytes (the host builder is
+    pinned to the reference's own builder in tests/test_oracle_vs_ref.py)."""
+    protos, sig, img, orc, guts, _ = world
+    nb = int(img[:8].view(np.uint64)[0])
+    assert api.build_image_device(nb, sig.keys, sig.fI, sig.oI, sig.avg, sig.wt).tobytes() == img.tobytes()
+    rng = np.random.default_rng(77)
+    cases = []
+    # duplicates, keys that are not inserted, and long collision chains: many keys congruent modulo the bucket count
+    n, nbk = 40_000, 101533
+    keys = rng.integers(0, 20**8, n).astype(np.uint64)
+    keys[::7] = keys[3]                                  # the same key many times: each takes its own slot, in order
+    keys[5::11] = (rng.integers(0, 1000, len(keys[5::11])).astype(np.uint64) * np.uint64(nbk) + np.uint64(17))  # one home bucket
+    keys[9::13] = np.uint64(20**8 + 5)                   # > MAX_ENCODED: skipped
+    cases.append((nbk, keys))
+    # probe chains that wrap around the end of the table
+    nbk2 = 3769
+    k2 = (rng.integers(0, 50, 1500).astype(np.uint64) * np.uint64(nbk2) + np.uint64(nbk2) - rng.integers(1, 40, 1500).astype(np.uint64))
+    cases.append((nbk2, k2))
+    cases.append((3769, np.zeros(0, np.uint64)))
+    for nbk_, k_ in cases:
+        m = len(k_)
+        fI, oI = rng.integers(0, 5000, m).astype(np.int32), rng.integers(-1, 300, m).astype(np.int32)
+        avg, wt = rng.integers(0, 65536, m).astype(np.uint16), rng.random(m).astype(np.float32)
+        for _ in range(3):  # whatever the thread schedule
+            assert api.build_image_device(nbk_, k_, fI, oI, avg, wt).tobytes() == api.build_image(nbk_, k_, fI, oI, avg, wt).tobytes()
+    with pytest.raises(api.CkmError):  # half full: refused like kguts.cc:213-216
+        api.build_image_device(16, np.arange(9, dtype=np.uint64), [0] * 9, [0] * 9, [0] * 9, [0.0] * 9)
+    # opened straight from the device-built table: same calls as the context opened on the image
+    g2 = api.KmerGuts(built=(nb, sig.keys, sig.fI, sig.oI, sig.avg, sig.wt), function_names=synth.function_names(sig.n_functions))
+    batch = wl.concat_batches(wl.edge_batch(protos), synth.make_proteins(21, protos, 2000))
+    orc.set_params()
+    wl.assert_results_equal(g2.process_aa_seq_batch(batch.residues, batch.offsets, ALL), orc.call_batch(batch, ALL), "ckm_open_built")
+    assert g2.slot_bytes == guts.slot_bytes
+    g2.close()
