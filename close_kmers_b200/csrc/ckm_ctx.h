@@ -70,7 +70,7 @@ struct ckm_ctx {
         uint32_t n_fams = 0, n_functions = 0, hypo_sid = 0;
         std::vector<std::string> pgf_names, plf;         // host strings for the response text
         DevBuf hit_fam, E, gcap, gofs, gscratch, matches;  // per-batch work buffers
-        DevBuf class_seen;                                 // which fam_vote_kernel classes the batch contains
+        DevBuf class_seen, overflow;                       // fam_vote_kernel: classes present; proteins SMALL hands to LARGE
         DevBuf sofs, snd, sentries, sout_off, sout;        // ckm_family_scores: per-protein (family, count, weight) lists
         PinBuf h_scores, h_score_off;
     } fam;
@@ -126,7 +126,7 @@ struct ckm_ctx {
                        &otus_out};
         for (auto b : d) b->release();
         DevBuf *f[] = {&fam.table, &fam.ids, &fam.fam_func, &fam.fam_pgf, &fam.func_sid, &fam.hit_fam, &fam.E, &fam.gcap,
-                       &fam.gofs, &fam.gscratch, &fam.matches, &fam.sofs, &fam.snd, &fam.sentries, &fam.sout_off, &fam.sout, &fam.class_seen};
+                       &fam.gofs, &fam.gscratch, &fam.matches, &fam.sofs, &fam.snd, &fam.sentries, &fam.sout_off, &fam.sout, &fam.class_seen, &fam.overflow};
         for (auto b : f) b->release();
         fam.h_scores.release();
         fam.h_score_off.release();

@@ -102,10 +102,8 @@ fam_lookup_kernel(FamTables ft, const uint64_t *__restrict__ offsets, const uint
             while (cap < 2u * e && cap < 0x80000000u) cap <<= 1;
         }
         gcap[w] = cap;
-        if (class_seen) {  // which fam_vote_kernel instantiations have work: [0] small maps, [1] large / global maps
-            uint32_t scap = 32u;
-            while (scap < 2u * e) scap <<= 1;
-            const uint32_t cls = (cap == 0 && scap <= kFamSmallCap) ? 0u : 1u;
+        if (class_seen) {  // which fam_vote_kernel instantiations have work: [0] shared-memory maps, [1] global-scratch maps
+            const uint32_t cls = cap == 0 ? 0u : 1u;
             if (*((volatile uint32_t *)class_seen + cls) == 0u) class_seen[cls] = 1u;
         }
     }
@@ -153,7 +151,8 @@ __global__ void __launch_bounds__(FamVoteCfg<CAP>::kWarps * 32)
 fam_vote_kernel(FamTables ft, const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ n_hits,
                 const uint2 *__restrict__ hit_fam, const uint32_t *__restrict__ E, const uint32_t *__restrict__ gcap,
                 const uint64_t *__restrict__ gofs, uint32_t *__restrict__ gscratch, const ckm_best_t *__restrict__ best,
-                uint32_t n, ckm_family_match_t *__restrict__ out, FamScoreOut so) {
+                uint32_t n, ckm_family_match_t *__restrict__ out, FamScoreOut so, uint32_t *__restrict__ overflow,
+                uint32_t *__restrict__ any_overflow) {
     extern __shared__ __align__(16) uint32_t fam_smem[];  // FamVoteCfg<CAP>::kSmem bytes, carved per warp below
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     uint32_t *const my_smem = fam_smem + (size_t)wib * FamVoteCfg<CAP>::kWarpWords;
@@ -167,11 +166,22 @@ fam_vote_kernel(FamTables ft, const uint64_t *__restrict__ offsets, const uint32
     for (uint32_t i = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < n; i += n_warps) {
         uint32_t *keys, *cnt, *pkeys, cap;
         float *wsum, *pw;
-        // shared-memory maps sized to the protein: at most E distinct families, kept at most half full
+        // shared-memory maps sized to the protein: at most E distinct families, kept at most half full.  E counts list
+        // ENTRIES; a protein usually touches far fewer distinct families, so the SMALL instantiation takes every protein
+        // whose map may live in shared memory with at most kFamSmallCap slots and hands the few that really hold more
+        // than kFamSmallCap/2 families over to the LARGE one (overflow[i]), which runs after it.
         cap = 32u;
         while (cap < 2u * E[i]) cap <<= 1;
-        const bool small = gcap[i] == 0 && cap <= kFamSmallCap;
-        if (small != (CAP <= kFamSmallCap)) continue;  // the other instantiation's protein
+        constexpr bool kSmall = CAP <= kFamSmallCap;
+        if (kSmall) {
+            if (gcap[i] != 0) continue;
+            cap = min(cap, CAP);
+        } else if (gcap[i] == 0 && overflow[i] == 0u) {
+            continue;  // done by the SMALL instantiation
+        }
+        const bool may_overflow = kSmall && 2u * E[i] > cap;
+        uint32_t n_fresh = 0;
+        bool bailed = false;
         const uint64_t base = offsets[i];
         const uint32_t nh = n_hits[i];
         if (gcap[i] == 0) {
@@ -202,6 +212,10 @@ fam_vote_kernel(FamTables ft, const uint64_t *__restrict__ offsets, const uint32
                 }
                 const uint32_t n_ent = __shfl_sync(0xffffffffu, incl, 31);
                 if (n_ent == 0) continue;
+                if (may_overflow && (n_ent > kFamEntries || n_fresh > cap / 2u)) {  // warp-uniform
+                    bailed = true;
+                    break;
+                }
                 if (n_ent <= kFamEntries) {
                     const float weight = 1.0f / (float)my.y;  // 1.0f / counts.size(), family_mapper.cc:300
                     uint32_t e = incl - my.y;
@@ -211,18 +225,21 @@ fam_vote_kernel(FamTables ft, const uint64_t *__restrict__ offsets, const uint32
                     }
                     __syncwarp();
                     for (uint32_t e0 = 0; e0 < n_ent; e0 += 32) {
+                        // SMALL: at most kFamSmallCap/2 families before a tile and 32 more in it -- the map cannot fill up
+                        if (may_overflow && n_fresh > cap / 2u) break;
                         const uint32_t me = e0 + lane;
                         const uint32_t fam = me < n_ent ? s_fam[me] : 0xffffffffu;
                         const bool ok = fam < ft.n_fams;  // no family_data_ entry: never reported (146-148)
                         uint32_t slot = 0x80000000u | lane;  // distinct for idle lanes
                         float w = 0.0f;
+                        bool fresh = false;
                         if (ok) {
-                            bool fresh;
                             slot = map_slot(keys, mask, fam + 1, &fresh);
                             if (fresh) { cnt[slot] = 0u; wsum[slot] = 0.0f; }
                             w = s_wt[me];
                         }
                         __syncwarp();
+                        if (may_overflow) n_fresh += __popc(__ballot_sync(0xffffffffu, fresh));
                         const uint32_t peers = __match_any_sync(0xffffffffu, slot);
                         const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
                         const uint32_t last = __reduce_max_sync(0xffffffffu, ok ? rank : 0u);
@@ -250,6 +267,18 @@ fam_vote_kernel(FamTables ft, const uint64_t *__restrict__ offsets, const uint32
                     }
                 }
                 __syncwarp();
+            }
+        }
+
+        if (kSmall) {
+            if (may_overflow && n_fresh > cap / 2u) bailed = true;
+            if (lane == 0) {
+                overflow[i] = bailed ? 1u : 0u;
+                if (bailed && *((volatile uint32_t *)any_overflow) == 0u) *any_overflow = 1u;
+            }
+            if (bailed) {
+                __syncwarp();
+                continue;
             }
         }
 
@@ -498,7 +527,8 @@ static int family_device(ckm_ctx *c, const uint64_t *d_off, uint32_t n, uint64_t
     ft.hypo_sid = F.hypo_sid;
     const unsigned lb = (unsigned)(((uint64_t)n * 32 + 255) / 256);
     RC(F.class_seen.ensure(64));
-    CU(cudaMemsetAsync(F.class_seen.p, 0, 8, c->stream));
+    RC(F.overflow.ensure(((size_t)n + 1) * 4));
+    CU(cudaMemsetAsync(F.class_seen.p, 0, 16, c->stream));
     fam_lookup_kernel<<<lb, 256, 0, c->stream>>>(ft, d_off, (const uint64_t *)c->hit_keys.p, (const uint32_t *)c->n_hits.p, n,
                                                  (uint2 *)F.hit_fam.p, (uint32_t *)F.E.p, (uint32_t *)F.gcap.p,
                                                  (uint32_t *)F.class_seen.p);
@@ -534,20 +564,29 @@ static int family_device(ckm_ctx *c, const uint64_t *d_off, uint32_t n, uint64_t
         CU(cudaFuncSetAttribute(fam_vote_kernel<kFamSmallCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kSmem));
         const unsigned sb = (unsigned)std::min<uint64_t>(((uint64_t)n + S::kWarps - 1) / S::kWarps, (uint64_t)c->sm_count * 32);
         const unsigned lb2 = (unsigned)std::min<uint64_t>(((uint64_t)n + L::kWarps - 1) / L::kWarps, (uint64_t)c->sm_count * 8);
-        // each instantiation walks the whole batch and skips the other one's proteins: launch it only if it has any
-        // (every fastq fragment is "small")
+        // SMALL takes every protein whose map fits shared memory and flags the few that hold more than kFamSmallCap/2
+        // distinct families; LARGE takes those and the proteins with global-scratch maps.  Each instantiation walks the
+        // whole batch, so it is launched only if it has something to do (every fastq fragment is "small").
+        uint32_t *ovf = (uint32_t *)F.overflow.p, *any_ovf = (uint32_t *)F.class_seen.p + 2;
         if (class_seen[0]) {
             fam_vote_kernel<kFamSmallCap><<<sb, S::kWarps * 32, S::kSmem, c->stream>>>(
                 ft, d_off, (const uint32_t *)c->n_hits.p, (const uint2 *)F.hit_fam.p, (const uint32_t *)F.E.p,
                 (const uint32_t *)F.gcap.p, (const uint64_t *)F.gofs.p, (uint32_t *)F.gscratch.p, (const ckm_best_t *)c->best.p, n,
-                (ckm_family_match_t *)F.matches.p, so);
+                (ckm_family_match_t *)F.matches.p, so, ovf, any_ovf);
             c->launches++;
         }
-        if (class_seen[1]) {
+        bool need_large = class_seen[1] != 0;
+        if (!need_large && class_seen[0]) {
+            uint32_t any = 0;
+            CU(cudaMemcpyAsync(&any, any_ovf, 4, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            need_large = any != 0;
+        }
+        if (need_large) {
             fam_vote_kernel<kFamSmemCap><<<lb2, L::kWarps * 32, L::kSmem, c->stream>>>(
                 ft, d_off, (const uint32_t *)c->n_hits.p, (const uint2 *)F.hit_fam.p, (const uint32_t *)F.E.p,
                 (const uint32_t *)F.gcap.p, (const uint64_t *)F.gofs.p, (uint32_t *)F.gscratch.p, (const ckm_best_t *)c->best.p, n,
-                (ckm_family_match_t *)F.matches.p, so);
+                (ckm_family_match_t *)F.matches.p, so, ovf, any_ovf);
             c->launches++;
         }
     }

@@ -118,6 +118,40 @@ def test_family_large_fanout_uses_global_maps(checkers):
     orc.close()
 
 
+def test_family_many_distinct_families_overflow_small_maps(checkers):
+    """Proteins whose map could live in shared memory (E <= 512 entries) but that touch more distinct families than the
+    optimistic 256-slot map takes: the SMALL vote kernel hands them to the LARGE one.  Mixed with proteins that stay small
+    and proteins with global-scratch maps (E > 512)."""
+    protos, sig, img = wl.small_world(seed=37, n_protos=300, n_sigs=24_000, n_functions=3, otu_mode="minus1", mean_len=90)
+    fam = synth.make_families(9, sig, fams_per_function=1500, max_list=8, coverage=1.0)
+    rng = np.random.default_rng(3)
+    cnt = rng.integers(4, 9, len(fam.kmers))
+    fam.fam_off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.uint64)
+    # every list: distinct ids spread over all 4500 families
+    start = rng.integers(0, fam.n_fams, len(cnt))
+    owner = np.repeat(np.arange(len(cnt)), cnt)
+    rank = np.arange(int(fam.fam_off[-1])) - fam.fam_off[:-1].astype(np.int64)[owner]
+    fam.fam_ids = ((start[owner] + rank * 517) % fam.n_fams).astype(np.uint32)
+    orc = checkers.Oracle().open_image(img)
+    orc.family_load(fam)
+    guts = api.KmerGuts(image=img, function_names=synth.function_names(sig.n_functions))
+    guts.family_load(fam.kmers, fam.fam_off, fam.fam_ids, fam.pgf, fam.plf, fam.function)
+    try:
+        batch = wl.concat_batches(synth.make_proteins(4, protos, 1500), wl.edge_batch(protos))
+        want_sc, want_off = orc.family_scores(batch)
+        per_protein = np.diff(want_off.astype(np.int64))
+        assert int((per_protein > 128).sum()) > 200 and int((per_protein <= 128).sum()) > 20  # both classes present
+        got = guts.family_scores(batch.residues, batch.offsets)
+        np.testing.assert_array_equal(got["score_offsets"], want_off)
+        for f in ("id", "hit_count", "weighted_total"):
+            np.testing.assert_array_equal(got["scores"][f], want_sc[f], err_msg=f)
+        wl.assert_family_records_equal(guts.find_best_family_match_batch(batch.residues, batch.offsets), orc.family_batch(batch),
+                                       "overflow hand-off")
+    finally:
+        guts.close()
+        orc.close()
+
+
 def test_six_frame_translation(checkers, world):
     protos, _, _, orc, guts, _, _ = world
     rng = np.random.default_rng(5)
