@@ -1116,4 +1116,5 @@ extern "C" int ckm_calibrate_gather(ckm_ctx *c, int bytes, int unroll, uint32_t 
 #include "ckm_family.cuh"
 #include "ckm_fq.cuh"
 #include "ckm_matrix.cuh"
+#include "ckm_family_nr.cuh"
 #include "ckm_build.cuh"

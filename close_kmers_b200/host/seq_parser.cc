@@ -39,25 +39,20 @@ struct ckm_seq_parser {
     // with one memchr + one vectorisable validity pass + one copy.
     template <bool STAR>
     size_t take_run(const char *d, size_t n) {
-        size_t done = 0;
-        while (done < n) {
-            const char *nl = (const char *)memchr(d + done, '\n', n - done);
-            const size_t end = nl ? (size_t)(nl - d) : n;
-            unsigned bad = 0;
-            for (size_t k = done; k < end; k++) {
-                const unsigned char c = (unsigned char)d[k];
-                bad |= !(((unsigned)((c | 0x20u) - 'a') < 26u) | (STAR & (c == '*')));
-            }
-            if (bad) {  // stop at the first character that is not sequence data
-                size_t k = done;
-                while (is_alpha((unsigned char)d[k]) || (STAR && d[k] == '*')) k++;
-                residues.append(d + done, k - done);
-                return k;
-            }
-            residues.append(d + done, end - done);
-            return end;  // at the newline (or the end of the block): the state machine takes it from here
+        const char *nl = (const char *)memchr(d, '\n', n);
+        const size_t end = nl ? (size_t)(nl - d) : n;
+        unsigned bad = 0;
+        for (size_t k = 0; k < end; k++) {
+            const unsigned char c = (unsigned char)d[k];
+            bad |= !(((unsigned)((c | 0x20u) - 'a') < 26u) | (STAR & (c == '*')));
         }
-        return done;
+        size_t take = end;  // up to the newline (or the end of the block): the state machine takes it from there
+        if (bad) {          // stop at the first character that is not sequence data
+            take = 0;
+            while (is_alpha((unsigned char)d[take]) || (STAR && d[take] == '*')) take++;
+        }
+        residues.append(d, take);
+        return take;
     }
     void error(const std::string &what) {
         n_errors++;
