@@ -573,10 +573,10 @@ static int prepare_regions(ckm_ctx *c, uint32_t n, uint64_t total, uint32_t max_
     {
         // by mean length: a group step covers 4*G start positions
         const uint64_t mean = n ? total / n : 0;
-        plan->probe_group = (n >= 64 && mean <= 48) ? 8u : (n >= 64 && mean <= 96) ? 16u : 32u;
+        plan->probe_group = n < 64 ? 32u : mean <= 24 ? 4u : mean <= 48 ? 8u : mean <= 96 ? 16u : 32u;
         if (const char *pg = getenv("CKM_PROBE_GROUP")) {
             const int g = atoi(pg);
-            if (g == 8 || g == 16 || g == 32) plan->probe_group = (uint32_t)g;
+            if (g == 4 || g == 8 || g == 16 || g == 32) plan->probe_group = (uint32_t)g;
         }
     }
     plan->general = plan->want_scan && (c->prm.order_constraint != 0 || max_len == 0 || max_len > kHitCap + CKM_KMER_SIZE);
@@ -633,7 +633,9 @@ static int launch_range(ckm_ctx *c, cudaStream_t stream, const uint8_t *d_res, c
             uint32_t *nh = (uint32_t *)c->n_hits.p + i0;
             unsigned long long *tot = (unsigned long long *)c->totals.p;
             const bool packed = c->slot_bytes == kPackedSlotBytes;
-            if (packed && group == 8u) probe_group_kernel<true, 8><<<gb, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
+            if (packed && group == 4u) probe_group_kernel<true, 4><<<gb, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
+            else if (group == 4u) probe_group_kernel<false, 4><<<gb, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
+            else if (packed && group == 8u) probe_group_kernel<true, 8><<<gb, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
             else if (packed) probe_group_kernel<true, 16><<<gb, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
             else if (group == 8u) probe_group_kernel<false, 8><<<gb, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
             else probe_group_kernel<false, 16><<<gb, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);

@@ -1,5 +1,5 @@
 // K1 for batches of SHORT sequences (fastq fragments, peptides): the same encode + probe + ordered compaction as
-// probe_kernel (ckm_probe.cuh), with a group of G lanes (8 or 16) per sequence instead of the whole warp, so that a warp
+// probe_kernel (ckm_probe.cuh), with a group of G lanes (4, 8 or 16) per sequence instead of the whole warp, so that a warp
 // works on 32/G sequences side by side.  A 50-residue fragment has 42 probed windows: one warp step of probe_kernel offers
 // 128 window slots for them, a group of 8 lanes offers 32 per step.  Every warp-wide primitive becomes segment-wide
 // (shuffles of width G, prefix sums within the group); the groups of a warp iterate in lock step until the longest of
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kProbeThreads)
 probe_group_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64_t *__restrict__ offsets, uint32_t n,
                    HitRec *__restrict__ hits, uint64_t *__restrict__ hit_keys, uint16_t *__restrict__ hit_avg,
                    uint32_t *__restrict__ n_hits, unsigned long long *__restrict__ totals) {
-    static_assert(G == 8 || G == 16, "group size");
+    static_assert(G == 4 || G == 8 || G == 16, "group size");
     constexpr uint32_t kPerWarp = 32u / G, T = 4u * G;
     __shared__ uint8_t lut[256];
     fill_aa_lut(lut);

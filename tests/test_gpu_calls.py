@@ -51,9 +51,9 @@ def test_call_batch_bit_exact(checkers, world, prm):
     assert len(want["calls"]) > 100
 
 
-@pytest.mark.parametrize("group", ["8", "16"])
+@pytest.mark.parametrize("group", ["4", "8", "16"])
 def test_group_probe_kernel_bit_exact(checkers, world, group):
-    """probe_group_kernel (8 / 16 lanes per sequence, chosen for batches of short sequences) against the oracle: forced on
+    """probe_group_kernel (4 / 8 / 16 lanes per sequence, chosen for batches of short sequences) against the oracle: forced on
     the mixed edge + protein batch, with and without the occupancy bitmap, and picked by itself on short peptides."""
     protos, sig, img, orc, guts, guts_raw = world
     batch = wl.concat_batches(wl.edge_batch(protos), synth.make_proteins(4, protos, 3000))
