@@ -41,6 +41,7 @@
 #include "../../include/ckm_server.h"
 #include "http.h"
 #include "lookup.h"
+#include "seq_parser.h"
 
 namespace {
 
@@ -56,7 +57,7 @@ struct Options {
     bool have_kmer_version = false, have_families_version = false, no_listen = false, daemonize = false, debug_http = false, help = false;
     int n_load_threads = 1, n_kmer_threads = 4;
     std::vector<int> devices;
-    size_t batch_bytes = 32u << 20;
+    size_t batch_bytes = 16u << 20;
 };
 
 const char *USAGE =
@@ -79,7 +80,7 @@ const char *USAGE =
     "  --pid-file arg                 write the process id to this file\n"
     "  --debug-http                   debug HTTP protocol\n"
     "  --device arg (=0)              CUDA device(s), comma separated: one engine per device\n"
-    "  --batch-mb arg (=32)           residues handed to the GPU per batch\n"
+    "  --batch-mb arg (=16)           residues handed to the GPU per batch\n"
     "accepted and ignored (CPU scheduling of the reference): --n-family-file-threads --n-inserter-threads\n"
     "  --peg-kmer-data --reserve-mapping --no-populate-mmap; not supported: --family-reps --kmer-family-distribution-file\n"
     "If the kmer data directory contains files families.dat and a\n"
@@ -594,6 +595,47 @@ struct Inflater {  // a gzip body on /fq_lookup (fq_process_request.cc:66-97, zl
     }
 };
 
+// One parsed batch on its way from the connection thread (socket + parser) to the request's worker (GPU + text + send).
+struct Job {
+    std::vector<std::string> ids;
+    std::string residues;
+    std::vector<uint64_t> offsets;
+};
+
+struct JobQueue {  // depth 2: the connection thread parses batch k+1 while batch k is computed, formatted and sent
+    std::mutex m;
+    std::condition_variable cv;
+    std::vector<std::unique_ptr<Job>> q;
+    bool closed = false, failed = false;
+    bool push(std::unique_ptr<Job> j) {
+        std::unique_lock<std::mutex> l(m);
+        cv.wait(l, [&] { return q.size() < 2 || failed; });
+        if (failed) return false;
+        q.push_back(std::move(j));
+        cv.notify_all();
+        return true;
+    }
+    std::unique_ptr<Job> pop() {
+        std::unique_lock<std::mutex> l(m);
+        cv.wait(l, [&] { return !q.empty() || closed; });
+        if (q.empty()) return nullptr;
+        std::unique_ptr<Job> j = std::move(q.front());
+        q.erase(q.begin());
+        cv.notify_all();
+        return j;
+    }
+    void close() {
+        std::lock_guard<std::mutex> l(m);
+        closed = true;
+        cv.notify_all();
+    }
+    void fail() {
+        std::lock_guard<std::mutex> l(m);
+        failed = true;
+        cv.notify_all();
+    }
+};
+
 void handle_post(Server &s, Conn &c, const Request &r, const Decision &d) {
     const std::string &action = d.action;
     const bool is_fq = action == "/fq_lookup", is_matrix = action == "/matrix", is_add = action == "/add", is_lookup = action == "/lookup";
@@ -620,6 +662,64 @@ void handle_post(Server &s, Conn &c, const Request &r, const Decision &d) {
     memset(&lopt, 0, sizeof lopt);
     if (is_lookup) lopt = ckm_lookup::options_from(r, s.fams, s.family_mode);
 
+    // ---- worker: one batch at a time, in arrival order ----
+    JobQueue jobs;
+    auto work = [&]() {
+        while (std::unique_ptr<Job> j = jobs.pop()) {
+            std::vector<const char *> idp;
+            idp.reserve(j->ids.size());
+            for (const auto &id : j->ids) idp.push_back(id.c_str());
+            const uint32_t n = (uint32_t)j->ids.size();
+            std::string out;
+            if (!header_written && !is_matrix) {
+                out = header_text(r, 200, "OK") + "\n";
+                header_written = true;
+            }
+            char *text = nullptr;
+            int rc = 0;
+            {
+                std::unique_lock<std::mutex> lock;
+                Engine &e = s.lease(lock, is_add || is_matrix || (is_lookup && !s.family_mode));
+                if (!is_fq) rc = apply_parameters(e.ctx, r);  // fq_process_request.cc never calls set_parameters
+                if (rc) {
+                } else if (action == "/query") {
+                    rc = ckm_query_text(e.ctx, idp.data(), j->residues.data(), j->offsets.data(), n, int_param(r, "details"),
+                                        int_param(r, "find_best_call"), &text);
+                } else if (is_add) {
+                    rc = ckm_postings_select(e.ctx, mapping.post_key);
+                    if (!rc) rc = ckm_add_text(e.ctx, mapping.ids, idp.data(), j->residues.data(), j->offsets.data(), n, silent, &text);
+                } else if (is_matrix) {
+                    rc = ckm_postings_select(e.ctx, mapping.post_key);
+                    if (!rc) rc = ckm_matrix_text(e.ctx, mapping.ids, idp.data(), j->residues.data(), j->offsets.data(), n, &text);
+                    out = "HTTP/1.1 200 OK\nContent-type: text/plain\n\n";  // matrix_request.cc:168-170
+                } else if (is_fq) {
+                    rc = ckm_fq_text(e.ctx, idp.data(), j->residues.data(), j->offsets.data(), n, &text);
+                } else {
+                    if (!s.family_mode) rc = ckm_postings_select(e.ctx, mapping.post_key);
+                    if (!rc)
+                        rc = ckm_lookup_text(e.ctx, mapping.ids, s.fams.flat.data(), (uint32_t)s.fams.flat.size(), &lopt, idp.data(),
+                                             j->residues.data(), j->offsets.data(), n, &text);
+                }
+            }
+            bool ok = true;
+            if (rc) {
+                std::cerr << "ERROR in " << action << ": " << ckm_last_error() << "\n";
+                if (!header_written || is_matrix) respond(c, r, 500, "Failed", std::string("Caught exception ") + ckm_last_error() + "\n");
+                ok = false;
+            } else {
+                if (text) out += text;
+                ok = c.write_all(out);
+            }
+            ckm_free_text(text);
+            if (!ok) {
+                jobs.fail();
+                return;
+            }
+        }
+    };
+    std::thread worker(work);
+
+    // ---- this thread: socket -> (inflate) -> parser -> batches ----
     ckm_seq_parser *parser = ckm_seq_parser_new(is_fq ? CKM_FORMAT_FASTQ : CKM_FORMAT_FASTA);
     Inflater gz;
     size_t remaining = d.content_length;
@@ -643,48 +743,12 @@ void handle_post(Server &s, Conn &c, const Request &r, const Decision &d) {
         }
         if (finished) ckm_seq_parser_complete(parser);
         if (!finished && (is_matrix || ckm_seq_parser_pending(parser) < s.opt.batch_bytes)) continue;
-        ckm_seq_batch_t b;
-        ckm_seq_parser_take(parser, &b);
-        std::string out;
-        if (!header_written && !is_matrix) {
-            out = header_text(r, 200, "OK") + "\n";
-            header_written = true;
-        }
-        char *text = nullptr;
-        int rc = 0;
-        {
-            std::unique_lock<std::mutex> lock;
-            Engine &e = s.lease(lock, is_add || is_matrix || (is_lookup && !s.family_mode));
-            if (!is_fq) rc = apply_parameters(e.ctx, r);  // fq_process_request.cc never calls set_parameters
-            if (rc) {
-            } else if (action == "/query") {
-                rc = ckm_query_text(e.ctx, b.ids, b.residues, b.offsets, b.n, int_param(r, "details"), int_param(r, "find_best_call"), &text);
-            } else if (is_add) {
-                rc = ckm_postings_select(e.ctx, mapping.post_key);
-                if (!rc) rc = ckm_add_text(e.ctx, mapping.ids, b.ids, b.residues, b.offsets, b.n, silent, &text);
-            } else if (is_matrix) {
-                rc = ckm_postings_select(e.ctx, mapping.post_key);
-                if (!rc) rc = ckm_matrix_text(e.ctx, mapping.ids, b.ids, b.residues, b.offsets, b.n, &text);
-                out = "HTTP/1.1 200 OK\nContent-type: text/plain\n\n";  // matrix_request.cc:168-170
-            } else if (is_fq) {
-                rc = ckm_fq_text(e.ctx, b.ids, b.residues, b.offsets, b.n, &text);
-            } else {
-                if (!s.family_mode) rc = ckm_postings_select(e.ctx, mapping.post_key);
-                if (!rc)
-                    rc = ckm_lookup_text(e.ctx, mapping.ids, s.fams.flat.data(), (uint32_t)s.fams.flat.size(), &lopt, b.ids, b.residues,
-                                         b.offsets, b.n, &text);
-            }
-        }
-        if (rc) {
-            std::cerr << "ERROR in " << action << ": " << ckm_last_error() << "\n";
-            if (!header_written || is_matrix) respond(c, r, 500, "Failed", std::string("Caught exception ") + ckm_last_error() + "\n");
-            ok = false;
-        } else {
-            if (text) out += text;
-            ok = c.write_all(out);
-        }
-        ckm_free_text(text);
+        std::unique_ptr<Job> j(new Job());
+        parser->take_owned(j->ids, j->residues, j->offsets);
+        ok = jobs.push(std::move(j));
     }
+    jobs.close();
+    worker.join();
     ckm_seq_parser_free(parser);
 }
 
