@@ -707,8 +707,7 @@ void handle_post(Server &s, Conn &c, const Request &r, const Decision &d) {
                 if (!header_written || is_matrix) respond(c, r, 500, "Failed", std::string("Caught exception ") + ckm_last_error() + "\n");
                 ok = false;
             } else {
-                if (text) out += text;
-                ok = c.write_all(out);
+                ok = c.write_all(out) && (!text || c.write_all(text, strlen(text)));  // no second copy of a large response
             }
             ckm_free_text(text);
             if (!ok) {
@@ -766,6 +765,9 @@ void handle_connection(Server *sp, int fd) {
             if (cr != std::string::npos) shown.erase(cr);
             if (s.opt.debug_http) std::cerr << "Request: " << shown << "\n";
             if (!r.parse_request_line(line)) {
+                for (char &ch : shown)  // stringPurifier (krequest2.cc:76-85; defined there, never called): keep the log printable
+                    if ((unsigned char)ch < 32 || (unsigned char)ch > 127) ch = ' ';
+                if (shown.size() > 200) shown = shown.substr(0, 200) + "...";
                 std::cerr << "Invalid request '" << shown << "'\n";
                 break;
             }

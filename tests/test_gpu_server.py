@@ -318,6 +318,57 @@ def test_server_query(world, server):
     assert post(port, "/query", b"") == OK_HEADER + ref.query_text([""], synth.batch_from_strings([b""]), 0, 0)
 
 
+def test_server_survives_bad_clients(world, server):
+    """Truncated bodies, oversized request lines, clients that hang up: the server answers what it can and keeps serving."""
+    protos = world[0]
+    port, ref = server[0], server[1]
+    batch = clean_batch(protos, 63, 50)
+    ids = [f"t{i}" for i in range(batch.n)]
+    body = fasta(ids, batch)
+    # body shorter than Content-Length, then the client stops sending: handled like eof (parse_complete on what arrived)
+    s = socket.create_connection(("127.0.0.1", port), timeout=60)
+    s.sendall(b"POST /query HTTP/1.1\r\nContent-Length: %d\r\n\r\n" % (len(body) + 1000) + body)
+    s.shutdown(socket.SHUT_WR)
+    got = b""
+    while True:
+        b = s.recv(1 << 20)
+        if not b:
+            break
+        got += b
+    s.close()
+    assert got.decode() == OK_HEADER + ref.query_text(ids, batch, 0, 0)
+    # a request line that never ends, a client that connects and leaves, binary junk
+    for junk in (b"GET /" + b"a" * (3 << 20), b"", b"\x00\xff\x16\x03\x01" * 100 + b"\n\n"):
+        s = socket.create_connection(("127.0.0.1", port), timeout=60)
+        try:
+            s.sendall(junk)
+        except OSError:
+            pass
+        s.close()
+    # a client that posts and hangs up without reading the answer
+    big = clean_batch(protos, 64, 3000)
+    s = socket.create_connection(("127.0.0.1", port), timeout=60)
+    bb = fasta([f"h{i}" for i in range(big.n)], big)
+    s.sendall(b"POST /query?details=1 HTTP/1.1\r\nContent-Length: %d\r\n\r\n" % len(bb) + bb[: len(bb) // 2])
+    s.close()
+    # concurrent requests of different kinds
+    out = [None] * 6
+    def one(k):
+        if k % 3 == 0:
+            out[k] = post(port, "/query", body)
+        elif k % 3 == 1:
+            out[k] = post(port, f"/mapping/stress{k}/add?silent=1", body)
+        else:
+            out[k] = http(port, b"GET /version HTTP/1.1\r\n\r\n")
+    ts = [threading.Thread(target=one, args=(k,)) for k in range(6)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    want = OK_HEADER + ref.query_text(ids, batch, 0, 0)
+    assert out[0] == want and out[3] == want
+    assert out[1] == OK_HEADER and out[4] == OK_HEADER  # silent /add: header only
+    assert out[2].startswith("HTTP/1.1 200 OK\n") and "family-mode\t1" in out[5]
+
+
 def fastq(ids, batch, crlf=False):
     out = []
     for i, sid in enumerate(ids):
@@ -439,5 +490,5 @@ def test_server_quit(server):
     port, _, proc, log = server
     assert http(port, b"GET /quit HTTP/1.1\r\n\r\n") == "HTTP/1.1 200 OK\nContent-type: text/plain\nContent-length: 13\n\nOK, quitting\n"
     assert proc.wait(timeout=60) == 0
-    text = open(log).read()
+    text = open(log, errors="replace").read()
     assert "Listening on 0.0.0.0:" in text and "NO FAM FOR id='fig|2500.peg.2'" in text
