@@ -364,6 +364,23 @@ def main():
     probe_ms, scan_ms, nb_prof = guts.profile_read()
     guts.profile_enable(False)
     n_probes, n_hits, n_calls = guts.read_totals()
+    chain = guts.chain_info
+    plain_probe_ms = None
+    if chain["entries"]:
+        # A/B, outside the timed region: the same steps with plain hash probing (probe_kernel) instead of
+        # probe_chain_kernel -- identical results, every hit its own DRAM transaction
+        guts.set_tuning(32)
+        step_resident()
+        guts.synchronize()
+        guts.profile_enable(True)
+        guts.profile_read()
+        for _ in range(min(K, 5)):
+            step_resident()
+        guts.synchronize()
+        pm, _, nbp = guts.profile_read()
+        guts.profile_enable(False)
+        plain_probe_ms = pm / max(nbp, 1)
+        guts.set_tuning(0)
 
     # ---- end to end through the C ABI with HOST buffers (H2D + kernels + D2H in the timed region)
     for _ in range(2):
@@ -397,20 +414,22 @@ def main():
         achieved = alg_bytes / (probe_ms_avg * 1e-3) / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(
+                args.workload + ("_chain" if chain["entries"] else ""))
         except (OSError, ValueError):
             pass
         # independent random 16 B reads over the resident table: best of a few occupancies
         cal_rate = max(guts.calibrate_gather(16, u, 64, b)[0] for u, b in ((1, 8), (4, 4), (4, 8)))
         value = prot_all * K / (ms_total * 1e-3)
+        probe_name = "probe_chain_kernel" if chain["entries"] else "probe_kernel"
         line = {
             "metric": "proteins/sec", "value": value, "unit": "proteins/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64 keys / f32 scores", "data": "synthetic", "config": config,
             "probes_per_s": probes_all * K / (ms_total * 1e-3),
             "per_step": {"proteins": n, "residues": total, "probes": n_probes, "hits": n_hits, "calls": n_calls},
-            "kernels_ms": {"probe_kernel": probe_ms_avg, "scan_kernel": scan_ms / max(nb_prof, 1)},
-            "roofline": {"bound": "hbm", "kernel": "probe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "kernels_ms": {probe_name: probe_ms_avg, "scan_kernel": scan_ms / max(nb_prof, 1)},
+            "roofline": {"bound": "hbm", "kernel": probe_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "algorithmic_bytes_per_launch": alg_bytes,
@@ -423,7 +442,10 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "table": {"buckets": guts.num_sigs, "slot_bytes": guts.slot_bytes, "l2_fetch_granularity": guts.l2_fetch_granularity,
-                      "occupancy_bitmap": guts.has_occupancy_bitmap},
+                      "occupancy_bitmap": guts.has_occupancy_bitmap,
+                      "neighbour_copy": {"entries": chain["entries"], "chains": chain["chains"], "build_ms": chain["build_ms"],
+                                         "hits_answered_from_copy": chain["hits_from_copy"],
+                                         "plain_hash_probe_kernel_ms": plain_probe_ms}},
         }
         if not args.no_cpu_baseline and world == 1:
             with stdout_to_stderr():

@@ -89,6 +89,7 @@ def lib() -> C.CDLL:
     L.ckm_l2_fetch_granularity.argtypes = [C.c_void_p]
     L.ckm_has_occupancy_bitmap.argtypes = [C.c_void_p]
     L.ckm_set_tuning.argtypes = [C.c_void_p, C.c_uint32]
+    L.ckm_chain_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.ckm_set_default_params.argtypes = [C.c_void_p]
     L.ckm_set_params.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     L.ckm_get_params.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
@@ -448,6 +449,13 @@ class KmerGuts:
     @property
     def has_occupancy_bitmap(self) -> bool:
         return bool(lib().ckm_has_occupancy_bitmap(self._h))
+
+    @property
+    def chain_info(self) -> dict:
+        """Neighbour-ordered copy of the table (ckm_chain.cuh): entries, chains, build time, hits it answered last batch."""
+        info = (C.c_uint64 * 4)()
+        _check(lib().ckm_chain_info(self._h, info))
+        return {"entries": int(info[0]), "chains": int(info[1]), "build_ms": info[2] / 1000.0, "hits_from_copy": int(info[3])}
 
     @property
     def stream(self) -> int:

@@ -24,6 +24,7 @@
 #include "ckm_ctx.h"
 #include "ckm_probe.cuh"
 #include "ckm_probe_group.cuh"
+#include "ckm_chain.cuh"
 #include "ckm_scan.cuh"
 #include "ckm_util.cuh"
 
@@ -166,6 +167,8 @@ static int select_device(int device) {
 }
 
 static int install_table(ckm_ctx *c, DevBuf raw, uint64_t n);
+static int build_chain(ckm_ctx *c);
+static int prefix_sum(ckm_ctx *c, const uint32_t *d_in, uint64_t n, uint64_t *d_out /* n+1 */);
 
 static int upload_table(ckm_ctx *c, const ckm_image_header_t *hdr) {
     const uint64_t n = hdr->num_sigs;
@@ -248,7 +251,102 @@ static int install_table(ckm_ctx *c, DevBuf raw, uint64_t n) {
             }
         }
     }
+    // neighbour-ordered copy (ckm_chain.cuh): like the bitmap, only pays when hits are DRAM transactions
+    c->chain.release();
+    c->cpos.release();
+    c->n_chain = 0;
+    const char *ch = getenv("CKM_CHAIN");  // "0" disables, "1" forces
+    const bool want_chain = ch ? ch[0] == '1' : false;  // opt-in while probe_chain_kernel is slower than probe_kernel
+    if (want_chain && c->slot_bytes == kPackedSlotBytes && n < 0xFFFFFFF0ull) {
+        // an optimisation only: without the memory for it (~32 B per bucket while building) the table works as before
+        if (build_chain(c)) {
+            if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess)
+                return ckm_fail(CKM_ECUDA, "building the neighbour copy failed: %s", ckm_last_error());
+            fprintf(stderr, "libckm: neighbour copy of the table not built (%s); plain hash probing\n", ckm_last_error());
+        }
+    }
     return 0;
+}
+
+// Build chain[] / cpos[] from the packed table on the device (steps 1-3 of ckm_chain.cuh).
+static int build_chain(ckm_ctx *c) {
+    const uint64_t n = c->num_sigs;
+    TableView tv;
+    memset(&tv, 0, sizeof tv);
+    tv.slots = c->table.p;
+    tv.num_sigs = n;
+    tv.magic = c->magic;
+    tv.occupied = (const uint32_t *)c->occupied.p;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, c->stream));
+    DevBuf pd, succ, claim, len, start, flag;
+    int rc = 0;
+    auto body = [&]() -> int {
+        RC(pd.ensure(n * 8));
+        RC(succ.ensure(n * 4));
+        RC(claim.ensure(n * 8));
+        RC(len.ensure(n * 4 + 64));
+        RC(start.ensure((n + 1) * 8));
+        RC(flag.ensure(64));
+        RC(c->cpos.ensure(n * 4 + 64));
+        const unsigned blocks = (unsigned)((n + 255) / 256);
+        CU(cudaMemsetAsync(claim.p, 0xFF, n * 8, c->stream));
+        CU(cudaMemsetAsync(len.p, 0, n * 4, c->stream));
+        CU(cudaMemsetAsync(flag.p, 0, 64, c->stream));
+        chain_propose_kernel<<<blocks, 256, 0, c->stream>>>(tv, (uint64_t *)pd.p, (uint32_t *)succ.p, (unsigned long long *)claim.p);
+        chain_link_kernel<<<blocks, 256, 0, c->stream>>>(n, (const uint32_t *)succ.p, (const unsigned long long *)claim.p, (uint64_t *)pd.p);
+        c->launches += 2;
+        unsigned int changed = 1;
+        for (int round = 0; round < 26 && changed; round++) {
+            CU(cudaMemsetAsync(flag.p, 0, 4, c->stream));
+            chain_jump_kernel<<<blocks, 256, 0, c->stream>>>(n, (volatile uint64_t *)pd.p, (unsigned int *)flag.p);
+            c->launches++;
+            CU(cudaMemcpyAsync(&changed, flag.p, 4, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+        }
+        c->chain_cycles = changed ? 1 : 0;
+        if (changed) {  // cycles: their members become chains of one (succ[] is free by now and holds the marks)
+            chain_cycle_mark_kernel<<<blocks, 256, 0, c->stream>>>(n, (const uint64_t *)pd.p, (uint32_t *)succ.p);
+            chain_cycle_cut_kernel<<<blocks, 256, 0, c->stream>>>(n, (const uint32_t *)succ.p, (uint64_t *)pd.p);
+            c->launches += 2;
+        }
+        chain_length_kernel<<<blocks, 256, 0, c->stream>>>(n, (const uint64_t *)pd.p, (uint32_t *)len.p);
+        c->launches++;
+        RC(prefix_sum(c, (const uint32_t *)len.p, n, (uint64_t *)start.p));
+        uint64_t total = 0;
+        CU(cudaMemcpyAsync(&total, (const uint64_t *)start.p + n, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (total >= 0xFFFFFFF0ull) return ckm_fail(CKM_ESTATE, "chain copy: %llu entries do not fit 32-bit indices", (unsigned long long)total);
+        RC(c->chain.ensure((total + 8) * sizeof(uint4)));
+        CU(cudaMemsetAsync(c->chain.p, 0xFF, (total + 8) * sizeof(uint4), c->stream));
+        chain_place_kernel<<<blocks, 256, 0, c->stream>>>(tv, (const uint64_t *)pd.p, (const uint64_t *)start.p, (uint4 *)c->chain.p,
+                                                          (uint32_t *)c->cpos.p, (unsigned long long *)flag.p + 1);
+        c->launches++;
+        unsigned long long roots = 0;
+        CU(cudaMemcpyAsync(&roots, (const unsigned long long *)flag.p + 1, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaEventRecord(e1, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaGetLastError());
+        c->n_chain = (uint32_t)total;
+        c->n_chains = roots;
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        c->chain_build_ms = ms;
+        return 0;
+    };
+    rc = body();
+    DevBuf *tmp[] = {&pd, &succ, &claim, &len, &start, &flag};
+    for (auto b : tmp) b->release();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc) {
+        c->chain.release();
+        c->cpos.release();
+        c->n_chain = 0;
+    }
+    return rc;
 }
 
 // T2: kmer_image.cc:87-105
@@ -384,6 +482,10 @@ extern "C" int ckm_clone(ckm_ctx *parent, ckm_ctx **out) {
     c->shares_tables = true;
     c->table = parent->table;
     c->occupied = parent->occupied;
+    c->chain = parent->chain;
+    c->cpos = parent->cpos;
+    c->n_chain = parent->n_chain;
+    c->n_chains = parent->n_chains;
     c->num_sigs = parent->num_sigs;
     c->magic = parent->magic;
     c->slot_bytes = parent->slot_bytes;
@@ -447,6 +549,18 @@ extern "C" int ckm_table_slot_bytes(const ckm_ctx *c) { return c->slot_bytes; }
 extern "C" int ckm_l2_fetch_granularity(const ckm_ctx *c) { return c->l2_fetch; }
 extern "C" void ckm_set_tuning(ckm_ctx *c, uint32_t bits) { c->tuning = bits; }
 extern "C" int ckm_has_occupancy_bitmap(const ckm_ctx *c) { return c->occupied.p != nullptr; }
+extern "C" int ckm_chain_info(ckm_ctx *c, uint64_t info[4]) {
+    if (!c || !info) return ckm_fail(CKM_EINVAL, "NULL argument");
+    info[0] = c->n_chain;
+    info[1] = c->n_chains;
+    info[2] = (uint64_t)(c->chain_build_ms * 1000.0);
+    info[3] = 0;
+    if (c->totals.p && c->n_chain) {
+        CU(cudaMemcpyAsync(&info[3], (const uint64_t *)c->totals.p + 4, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
 extern "C" void *ckm_stream(ckm_ctx *c) { return (void *)c->stream; }
 extern "C" uint64_t ckm_launch_count(const ckm_ctx *c) { return c->launches; }
 extern "C" int ckm_synchronize(ckm_ctx *c) {
@@ -614,6 +728,9 @@ static int launch_range(ckm_ctx *c, cudaStream_t stream, const uint8_t *d_res, c
     tv.magic = c->magic;
     tv.occupied = (const uint32_t *)c->occupied.p;
     tv.tuning = c->tuning;
+    tv.chain = (const uint4 *)c->chain.p;
+    tv.cpos = (const uint32_t *)c->cpos.p;
+    tv.n_chain = c->n_chain;
     {
         const uint32_t warps_per_block = kProbeThreads / 32;
         uint64_t blocks = ((uint64_t)cnt + warps_per_block - 1) / warps_per_block;
@@ -639,7 +756,17 @@ static int launch_range(ckm_ctx *c, cudaStream_t stream, const uint8_t *d_res, c
             else if (packed) probe_group_kernel<true, 16><<<gb, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
             else if (group == 8u) probe_group_kernel<false, 8><<<gb, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
             else probe_group_kernel<false, 16><<<gb, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
-        } else if (c->slot_bytes == kPackedSlotBytes)
+        } else if (c->slot_bytes == kPackedSlotBytes && c->n_chain && !(c->tuning & 32u)) {
+            if (c->tuning & 64u)
+                probe_chain_kernel<2><<<(unsigned)blocks, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, (HitRec *)c->hits.p, keys, avg,
+                                                                                      (uint32_t *)c->n_hits.p + i0,
+                                                                                      (unsigned long long *)c->totals.p);
+            else
+                probe_chain_kernel<3><<<(unsigned)blocks, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, (HitRec *)c->hits.p, keys, avg,
+                                                                                      (uint32_t *)c->n_hits.p + i0,
+                                                                                      (unsigned long long *)c->totals.p);
+        }
+        else if (c->slot_bytes == kPackedSlotBytes)
             probe_kernel<true><<<(unsigned)blocks, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, (HitRec *)c->hits.p, keys, avg,
                                                                                (uint32_t *)c->n_hits.p + i0,
                                                                                (unsigned long long *)c->totals.p);

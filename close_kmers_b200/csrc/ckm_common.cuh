@@ -39,8 +39,13 @@ struct TableView {
     // what bounds this kernel.  NULL when the table itself fits L2.
     const uint32_t *occupied;
     // cache-policy experiments (ckm_set_tuning): bit0 table loads evict_first, bit1 bitmap loads evict_last,
-    // bit2 hit-record stores evict_first, bit4 table loads with a 64-byte L2 fetch (instead of bit0)
+    // bit2 hit-record stores evict_first, bit4 table loads with a 64-byte L2 fetch (instead of bit0),
+    // bit5 plain hash probing even when the neighbour copy exists (A/B measurements)
     uint32_t tuning;
+    // Neighbour-ordered copy of the occupied slots and each slot's index in it (ckm_chain.cuh); NULL when not built.
+    const uint4 *chain;
+    const uint32_t *cpos;
+    uint32_t n_chain;
 };
 
 // One table hit as the ordered scoring scan consumes it (KmerHit, kguts.h:154-163, minus the key).

@@ -38,6 +38,10 @@ struct ckm_ctx {
     // signature table in HBM
     bool shares_tables = false;  // a ckm_clone: table / occupied / family tables belong to the parent
     DevBuf table, occupied;  // occupied: 1 bit per slot, only for tables larger than L2
+    DevBuf chain, cpos;      // neighbour-ordered copy of the occupied slots + slot -> index in it (ckm_chain.cuh)
+    uint32_t n_chain = 0;
+    uint64_t n_chains = 0, chain_cycles = 0;
+    double chain_build_ms = 0.0;
     int l2_bytes = 0;
     bool has_l2_window = false;
     cudaAccessPolicyWindow l2_window;  // persisting window over `occupied`
@@ -118,10 +122,12 @@ struct ckm_ctx {
         if (shares_tables) {  // drop the borrowed handles before the common release below
             table = DevBuf();
             occupied = DevBuf();
+            chain = DevBuf();
+            cpos = DevBuf();
             DevBuf *borrowed[] = {&fam.table, &fam.ids, &fam.fam_func, &fam.fam_pgf, &fam.func_sid};
             for (auto b : borrowed) *b = DevBuf();
         }
-        DevBuf *d[] = {&table, &occupied, &in_res, &in_off, &totals, &hits, &hit_keys, &hit_avg, &n_hits, &stored_idx, &calls, &calls_work,
+        DevBuf *d[] = {&table, &occupied, &chain, &cpos, &in_res, &in_off, &totals, &hits, &hit_keys, &hit_avg, &n_hits, &stored_idx, &calls, &calls_work,
                        &n_calls, &otus, &n_otus, &best, &ps_blocks, &hit_off, &call_off, &otu_off, &hits_out, &calls_out,
                        &otus_out};
         for (auto b : d) b->release();

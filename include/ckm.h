@@ -155,8 +155,12 @@ int ckm_table_slot_bytes(const ckm_ctx *ctx);
 int ckm_l2_fetch_granularity(const ckm_ctx *ctx);
 /* 1 when the L2-resident slot-occupancy bitmap is in use (tables larger than L2; CKM_OCCUPANCY_BITMAP=0/1 overrides) */
 int ckm_has_occupancy_bitmap(const ckm_ctx *ctx);
+/* Neighbour-ordered copy of the table (built at load for tables larger than L2; CKM_CHAIN=0/1 overrides; results are
+ * identical with and without it).  info[0] = entries (0 = not built), info[1] = chains, info[2] = build time in
+ * microseconds, info[3] = hits of the last batch that were answered from the copy instead of a hash probe. */
+int ckm_chain_info(ckm_ctx *ctx, uint64_t info[4]);
 /* L2 cache-policy switches of the probe kernel (results unaffected): bit0 table loads evict_first, bit1 bitmap
- * loads evict_last, bit2 hit-record stores evict_first */
+ * loads evict_last, bit2 hit-record stores evict_first, bit5 plain hash probing although the neighbour copy exists */
 void ckm_set_tuning(ckm_ctx *ctx, uint32_t bits);
 
 /* ---- parameters (KmerGuts::set_default_parameters / set_parameters, kguts.cc:236-268) -------------- */
