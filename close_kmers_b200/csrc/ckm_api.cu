@@ -25,6 +25,7 @@
 #include "ckm_probe.cuh"
 #include "ckm_probe_group.cuh"
 #include "ckm_chain.cuh"
+#include "ckm_hint.cuh"
 #include "ckm_scan.cuh"
 #include "ckm_util.cuh"
 
@@ -276,6 +277,7 @@ static int build_chain(ckm_ctx *c) {
     tv.slots = c->table.p;
     tv.num_sigs = n;
     tv.magic = c->magic;
+    tv.m35 = magic35(n);
     tv.occupied = (const uint32_t *)c->occupied.p;
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
@@ -319,8 +321,8 @@ static int build_chain(ckm_ctx *c) {
         CU(cudaMemcpyAsync(&total, (const uint64_t *)start.p + n, 8, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         if (total >= 0xFFFFFFF0ull) return ckm_fail(CKM_ESTATE, "chain copy: %llu entries do not fit 32-bit indices", (unsigned long long)total);
-        RC(c->chain.ensure((total + 8) * sizeof(uint4)));
-        CU(cudaMemsetAsync(c->chain.p, 0xFF, (total + 8) * sizeof(uint4), c->stream));
+        RC(c->chain.ensure((total + 32) * sizeof(uint4)));
+        CU(cudaMemsetAsync(c->chain.p, 0xFF, (total + 32) * sizeof(uint4), c->stream));
         chain_place_kernel<<<blocks, 256, 0, c->stream>>>(tv, (const uint64_t *)pd.p, (const uint64_t *)start.p, (uint4 *)c->chain.p,
                                                           (uint32_t *)c->cpos.p, (unsigned long long *)flag.p + 1);
         c->launches++;
@@ -700,6 +702,7 @@ static int prepare_regions(ckm_ctx *c, uint32_t n, uint64_t total, uint32_t max_
     RC(c->totals.ensure(64));
     RC(c->hits.ensure((total + 1) * sizeof(HitRec)));
     RC(c->n_hits.ensure(((size_t)n + 1) * 4));
+    if (c->n_chain && plan->probe_group >= 32u) RC(c->hints.ensure(((total >> kHintShift) + n + 2) * 4));
     if (plan->want_keys) RC(c->hit_keys.ensure((total + 1) * 8));
     if (plan->want_avg) RC(c->hit_avg.ensure((total + 1) * 2));
     if (plan->want_scan) {
@@ -731,6 +734,7 @@ static int launch_range(ckm_ctx *c, cudaStream_t stream, const uint8_t *d_res, c
     tv.chain = (const uint4 *)c->chain.p;
     tv.cpos = (const uint32_t *)c->cpos.p;
     tv.n_chain = c->n_chain;
+    tv.m35 = magic35(c->num_sigs);
     {
         const uint32_t warps_per_block = kProbeThreads / 32;
         uint64_t blocks = ((uint64_t)cnt + warps_per_block - 1) / warps_per_block;
@@ -757,7 +761,20 @@ static int launch_range(ckm_ctx *c, cudaStream_t stream, const uint8_t *d_res, c
             else if (group == 8u) probe_group_kernel<false, 8><<<gb, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
             else probe_group_kernel<false, 16><<<gb, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
         } else if (c->slot_bytes == kPackedSlotBytes && c->n_chain && !(c->tuning & 32u)) {
-            if (c->tuning & 64u)
+            if (!(c->tuning & (64u | 128u))) {  // hints first (one sample window in 32), then the probe proper (ckm_hint.cuh)
+                const uint64_t per_block = 256 / kHintLanes;
+                const unsigned hb = (unsigned)std::min<uint64_t>(((uint64_t)cnt + per_block - 1) / per_block, (uint64_t)c->sm_count * 64);
+                hint_kernel<<<hb, 256, 0, stream>>>(tv, d_res, d_off + i0, cnt, i0, (uint32_t *)c->hints.p);
+                c->launches++;
+                if (c->tuning & 0x10000u)
+                    probe_hint_kernel<4><<<(unsigned)blocks, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, i0, (const uint32_t *)c->hints.p,
+                                                                                         (HitRec *)c->hits.p, keys, avg, (uint32_t *)c->n_hits.p + i0,
+                                                                                         (unsigned long long *)c->totals.p);
+                else
+                    probe_hint_kernel<3><<<(unsigned)blocks, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, i0, (const uint32_t *)c->hints.p,
+                                                                                         (HitRec *)c->hits.p, keys, avg, (uint32_t *)c->n_hits.p + i0,
+                                                                                         (unsigned long long *)c->totals.p);
+            } else if (c->tuning & 64u)
                 probe_chain_kernel<2><<<(unsigned)blocks, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, (HitRec *)c->hits.p, keys, avg,
                                                                                       (uint32_t *)c->n_hits.p + i0,
                                                                                       (unsigned long long *)c->totals.p);

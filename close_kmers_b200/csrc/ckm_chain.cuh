@@ -173,6 +173,8 @@ chain_place_kernel(TableView tv, const uint64_t *__restrict__ pd, const uint64_t
 // ---------------------------------------------------------------------------------------------------
 // K1 through the neighbour copy (packed slots only)
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 constexpr uint32_t kChainPasses = 3;  // anchor passes per warp step before everything left is hash-probed
 
 struct HitWords {  // words 1..3 of the packed slot behind a hit (word 0 is the low half of the key)

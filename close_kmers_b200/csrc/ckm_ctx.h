@@ -64,6 +64,7 @@ struct ckm_ctx {
 
     // device work buffers
     DevBuf in_res, in_off, totals, hits, hit_keys, hit_avg, n_hits, stored_idx, calls, calls_work, n_calls;
+    DevBuf hints;  // per 32-window segment: where the protein sits in chain[] (ckm_hint.cuh)
     DevBuf otus, n_otus, best, ps_blocks;
     DevBuf hit_off, call_off, otu_off, hits_out, calls_out, otus_out;
     // family voting (ckm_family.cuh)
@@ -127,7 +128,7 @@ struct ckm_ctx {
             DevBuf *borrowed[] = {&fam.table, &fam.ids, &fam.fam_func, &fam.fam_pgf, &fam.func_sid};
             for (auto b : borrowed) *b = DevBuf();
         }
-        DevBuf *d[] = {&table, &occupied, &chain, &cpos, &in_res, &in_off, &totals, &hits, &hit_keys, &hit_avg, &n_hits, &stored_idx, &calls, &calls_work,
+        DevBuf *d[] = {&table, &occupied, &chain, &cpos, &hints, &in_res, &in_off, &totals, &hits, &hit_keys, &hit_avg, &n_hits, &stored_idx, &calls, &calls_work,
                        &n_calls, &otus, &n_otus, &best, &ps_blocks, &hit_off, &call_off, &otu_off, &hits_out, &calls_out,
                        &otus_out};
         for (auto b : d) b->release();

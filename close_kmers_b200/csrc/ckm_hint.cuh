@@ -1,0 +1,277 @@
+// K1 through the neighbour copy with precomputed hints: two kernels, no dependency between the 128-window steps.
+//
+// probe_chain_kernel (ckm_chain.cuh) cuts the DRAM transactions per probe by a factor of three and is still no faster
+// than plain hash probing, because it learns where a protein sits in chain[] *while* walking it: every warp step waits
+// for the previous step's offset and then runs up to three anchor passes, each a chain of dependent DRAM round trips
+// (slot -> cpos -> chain entry).  A dozen serial round trips per protein with ~20 warps per SM is latency, not bandwidth.
+//
+// Here the dependency is taken out of the walk:
+//
+//   hint_kernel        one thread per *sample* window (one window in 32): plain lookup_hash_entry (kguts.cc:585-602); a hit
+//                      stores hint = cpos[slot] - position, "where window 0 of this protein would sit in chain[] if the
+//                      protein followed this chain".  All samples of a batch are independent: two or three round trips at
+//                      full occupancy, ~3 % of the probes.
+//   probe_hint_kernel  probe_kernel (ckm_probe.cuh) with one extra source: every window first compares its key with
+//                      chain[hint + position], the hint being that of its own 32-window segment or else of the nearest
+//                      segment that has one.  Those reads are issued together with the occupancy words, are coalesced (the
+//                      128 windows of a step read 2 KB = 16 lines of chain[] when they share a hint) and answer ~98 % of the
+//                      hits of a protein that is a homologue of a signature source.  What is left -- windows whose home slot
+//                      is occupied and whose chain entry did not match: misses that collide with another k-mer, hits off
+//                      the chain, windows without a hint -- is hash-probed exactly as probe_kernel does it.
+//
+// A hint only chooses where to look first; the key is compared in full and every unresolved window takes the reference's
+// probe sequence, so results are bit-identical to probe_kernel whatever the hints hold (tests/test_gpu_chain.py runs
+// garbage-free and hint-free worlds side by side with plain probing).
+#pragma once
+#include "ckm_chain.cuh"
+
+namespace ckm {
+
+constexpr uint32_t kHintShift = 5;                 // one sample per 32 windows
+constexpr uint32_t kHintSeg = 1u << kHintShift;
+constexpr uint32_t kNoHint = 0xFFFFFFFFu;
+constexpr uint32_t kHintLanes = 16;                // lanes per protein in hint_kernel
+
+// hints of protein i (global index gi) live at hints[(offsets[i] >> kHintShift) + gi ...): a protein of length L has at most
+// (L-1)/32 + 1 segments and consecutive regions start at least that far apart, so regions never overlap.
+__device__ __forceinline__ uint64_t hint_region(uint64_t seq_base, uint32_t gi) { return (seq_base >> kHintShift) + gi; }
+
+__global__ void __launch_bounds__(256)
+hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64_t *__restrict__ offsets, uint32_t n, uint32_t index_base,
+            uint32_t *__restrict__ hints) {
+    __shared__ uint8_t lut[256];
+    fill_aa_lut(lut);
+    __syncthreads();
+    const uint32_t sub = threadIdx.x & (kHintLanes - 1);
+    const uint32_t g0 = (blockIdx.x * blockDim.x + threadIdx.x) / kHintLanes;
+    const uint32_t n_groups = (gridDim.x * blockDim.x) / kHintLanes;
+    const uint4 *__restrict__ slots = reinterpret_cast<const uint4 *>(tv.slots);
+    const uint32_t nsig = (uint32_t)tv.num_sigs;
+    for (uint32_t i = g0; i < n; i += n_groups) {
+        const uint64_t seq_base = __ldg(offsets + i);
+        const uint32_t len = (uint32_t)(__ldg(offsets + i + 1) - seq_base);
+        if (len <= CKM_KMER_SIZE) continue;
+        const uint32_t nwin = len - CKM_KMER_SIZE;
+        const uint32_t nseg = (nwin + kHintSeg - 1) >> kHintShift;
+        uint32_t *out = hints + hint_region(seq_base, index_base + i);
+        for (uint32_t k = sub; k < nseg; k += kHintLanes) {
+            uint32_t p = (k << kHintShift) + kHintSeg / 2;  // middle of the segment, or its first window when it is short
+            if (p >= nwin) p = k << kHintShift;
+            const uint8_t *r = residues + seq_base + p;
+            uint64_t key = 0;
+            uint32_t bad = 0;
+#pragma unroll
+            for (int q = 0; q < CKM_KMER_SIZE; q++) {
+                const uint32_t code = lut[__ldg(r + q)];
+                bad |= code;
+                key = key * 20ull + (code & 0x1Fu);
+            }
+            uint32_t hint = kNoHint;
+            if (!(bad & kInvalidCode)) {
+                uint32_t h = tv.m35 ? fast_mod35(key, nsig, tv.m35) : (uint32_t)fast_mod(key, tv.num_sigs, tv.magic);
+                for (uint32_t steps = 0; steps < nsig; steps++) {
+                    if (tv.occupied && !((__ldg(tv.occupied + (h >> 5)) >> (h & 31u)) & 1u)) break;
+                    const uint4 v = __ldg(slots + h);
+                    if (packed_match(v, key)) {
+                        hint = __ldg(tv.cpos + h) - p;
+                        break;
+                    }
+                    if (v.y & 0x8u) break;
+                    h = (h + 1u == nsig) ? 0u : h + 1u;
+                }
+            }
+            out[k] = hint;
+        }
+    }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(kProbeThreads, MINB)
+probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64_t *__restrict__ offsets, uint32_t n, uint32_t index_base,
+                  const uint32_t *__restrict__ hints, HitRec *__restrict__ hits, uint64_t *__restrict__ hit_keys,
+                  uint16_t *__restrict__ hit_avg, uint32_t *__restrict__ n_hits, unsigned long long *__restrict__ totals) {
+    __shared__ uint8_t lut[256];
+    fill_aa_lut(lut);
+    __syncthreads();
+
+    constexpr uint32_t full = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint4 *__restrict__ slots = reinterpret_cast<const uint4 *>(tv.slots);
+    const uint32_t nsig = (uint32_t)tv.num_sigs;  // the neighbour copy is only built for tables below 2^32 buckets
+    uint32_t my_probes = 0, my_hits = 0, my_chain = 0;
+    const bool pf = !(tv.tuning & 0x20000u);
+    const uint32_t m35 = tv.m35;
+
+    for (uint32_t i = warp0; i < n; i += n_warps) {
+        const uint64_t seq_base = __ldg(offsets + i);
+        const uint32_t len = (uint32_t)(__ldg(offsets + i + 1) - seq_base);
+        uint32_t count = 0;
+        if (len > CKM_KMER_SIZE) {
+            uint32_t nwin = len - CKM_KMER_SIZE;  // the last window is never probed (kguts.cc:792, 798)
+            const uint32_t nseg = (nwin + kHintSeg - 1) >> kHintShift;
+            const uint32_t *hp = hints + hint_region(seq_base, index_base + i);
+            const uint8_t *p0 = residues + seq_base;
+            const uint32_t s = (uint32_t)(reinterpret_cast<uintptr_t>(p0) & 3u);
+            const uint32_t *wb = reinterpret_cast<const uint32_t *>(p0 - s);
+            const uint32_t nwords = (len + s + 3u) >> 2;
+            const uint32_t sh = 8u * s;
+            HitRec *out = hits + seq_base;
+            uint32_t hv = kNoHint;     // hint of segment (32 * round + lane), reloaded every 8 steps
+            uint32_t carry = kNoHint;  // last hint seen in front of the current segment (the first one there is, to begin with)
+
+            for (uint32_t t0 = 0; t0 < nwin; t0 += kTile) {
+                const uint32_t seg0 = t0 >> kHintShift;  // first of the four segments of this step
+                if ((seg0 & 31u) == 0u) {
+                    hv = (seg0 + lane < nseg) ? __ldg(hp + seg0 + lane) : kNoHint;
+                    if (carry == kNoHint) {
+                        const uint32_t m = __ballot_sync(full, hv != kNoHint);
+                        if (m) carry = __shfl_sync(full, hv, __ffs(m) - 1);
+                    }
+                }
+                const TileKeys tk = tile_keys(lut, wb, nwords, sh, t0, lane, len, nwin);
+                const uint32_t q0 = t0 + 4u * lane;
+                const uint32_t act = tk.act;
+                if (pf) {
+                    // pull into L2 what the next step (or, from the first step, the next protein of this warp) starts with
+                    if (lane < 2u && t0 + kTile + 128u * lane < len) prefetch_l2(p0 + t0 + kTile + 128u * lane);
+                    if (t0 == 0 && i + n_warps < n && lane >= 2u && lane < 5u) {
+                        const uint64_t nb = __ldg(offsets + i + n_warps);
+                        if (lane < 4u) prefetch_l2(residues + nb + 128u * (lane - 2u));
+                        else prefetch_l2(hints + hint_region(nb, index_base + i + n_warps));
+                    }
+                }
+                uint32_t h[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) h[j] = m35 ? fast_mod35(tk.key[j], nsig, m35) : (uint32_t)fast_mod(tk.key[j], tv.num_sigs, tv.magic);
+
+                // ---- this lane's hint: its segment's, else the nearest one in front, else the nearest one behind ----
+                uint32_t f[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    f[k] = __shfl_sync(full, hv, (seg0 & 31u) + k);
+                    if (f[k] == kNoHint) f[k] = carry;
+                    else carry = f[k];
+                }
+                const uint32_t q = lane >> 3;
+                const uint32_t mh = q == 0 ? f[0] : q == 1 ? f[1] : q == 2 ? f[2] : f[3];
+
+                // ---- one round trip: occupancy words (L2) and the chain entries the hint predicts (coalesced) ----
+                uint32_t bw[4];
+                if (tv.occupied) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (act & (1u << j)) bw[j] = __ldg(tv.occupied + (h[j] >> 5));
+                }
+                HitWords w[4];
+                uint32_t hm = 0;
+                if (mh != kNoHint) {
+                    if (pf && t0 + kTile < nwin && mh + q0 + kTile < tv.n_chain) prefetch_l2(tv.chain + (mh + q0 + kTile));
+                    uint4 cv[4];
+                    uint32_t ok = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t idx = mh + q0 + j;
+                        if ((act & (1u << j)) && idx < tv.n_chain) {
+                            cv[j] = __ldg(tv.chain + idx);
+                            ok |= 1u << j;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if ((ok & (1u << j)) && packed_match(cv[j], tk.key[j])) {
+                            w[j].y = cv[j].y;
+                            w[j].z = cv[j].z;
+                            w[j].w = cv[j].w;
+                            hm |= 1u << j;
+                        }
+                    }
+                }
+                my_chain += __popc(hm);
+                uint32_t need = act & ~hm;
+                if (tv.occupied) {  // a window whose home slot is empty is a miss
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if ((need & (1u << j)) && !((bw[j] >> (h[j] & 31u)) & 1u)) need &= ~(1u << j);
+                }
+
+                // ---- what is left: lookup_hash_entry (kguts.cc:585-602), independent loads first ----
+                if (__any_sync(full, need != 0u)) {
+                    uint4 v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (need & (1u << j)) v[j] = __ldg(slots + h[j]);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (need & (1u << j)) {
+                            uint32_t hh = h[j];
+                            bool found = false;
+                            for (;;) {
+                                if (packed_match(v[j], tk.key[j])) { found = true; break; }
+                                if (v[j].y & 0x8u) break;
+                                hh = (hh + 1u == nsig) ? 0u : hh + 1u;
+                                if (hh == h[j]) break;  // a table without an empty slot
+                                if (tv.occupied) {
+                                    const uint32_t ow = (hh >> 5) == (h[j] >> 5) ? bw[j] : __ldg(tv.occupied + (hh >> 5));
+                                    if (!((ow >> (hh & 31u)) & 1u)) break;
+                                }
+                                v[j] = __ldg(slots + hh);
+                            }
+                            if (found) {
+                                w[j].y = v[j].y;
+                                w[j].z = v[j].z;
+                                w[j].w = v[j].w;
+                                hm |= 1u << j;
+                            }
+                        }
+                    }
+                }
+                my_probes += __popc(act);
+
+                // ---- ordered compaction: exclusive prefix of per-lane hit counts ----
+                const uint32_t cnt = __popc(hm);
+                uint32_t incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(full, incl, d);
+                    if (lane >= (uint32_t)d) incl += t;
+                }
+                const uint32_t tile_hits = __shfl_sync(full, incl, 31);
+                uint32_t o = count + incl - cnt;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (hm & (1u << j)) {
+                        HitRec rec;
+                        rec.pos = q0 + j;
+                        rec.fI = w[j].w & (kPackedFieldLimit - 1);
+                        rec.wt = __uint_as_float(w[j].z);
+                        rec.oI = (int32_t)(((w[j].y >> 20) & 0xFFFu) | ((w[j].w >> 22) << 12)) - 1;
+                        out[o] = rec;
+                        if (hit_keys) hit_keys[seq_base + o] = tk.key[j];
+                        if (hit_avg) hit_avg[seq_base + o] = (uint16_t)((w[j].y >> 4) & 0xFFFFu);
+                        o++;
+                    }
+                }
+                count += tile_hits;
+            }
+        }
+        if (lane == 0) n_hits[i] = count;
+        if (lane == 0) my_hits += count;
+    }
+
+    // batch totals: one atomic per warp (totals[4] = hits answered from the neighbour copy)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        my_probes += __shfl_down_sync(full, my_probes, d);
+        my_hits += __shfl_down_sync(full, my_hits, d);
+        my_chain += __shfl_down_sync(full, my_chain, d);
+    }
+    if (lane == 0) {
+        atomicAdd(totals + 0, (unsigned long long)my_probes);
+        atomicAdd(totals + 1, (unsigned long long)my_hits);
+        atomicAdd(totals + 4, (unsigned long long)my_chain);
+    }
+}
+
+}  // namespace ckm

@@ -1,6 +1,6 @@
 """probe_chain_kernel vs probe_kernel on a C2-shaped workload (GPU box): builds the world once, then times K1 per setting.
 python tools/tune_chain.py [n_proteins] [n_sigs] [tuning values ...]
-tuning: 0 = probe_chain_kernel<3 blocks/SM>, 64 = <2 blocks/SM>, 32 = plain hash probing (probe_kernel)"""
+tuning: 0 = hint_kernel + probe_hint_kernel, 128 = probe_chain_kernel<3 blocks/SM>, 64 = <2 blocks/SM>, 32 = plain hash probing (probe_kernel)"""
 import json
 import os
 import sys
@@ -12,7 +12,7 @@ from close_kmers_b200 import api, synth
 
 n_prot = int(sys.argv[1]) if len(sys.argv) > 1 else 300_000
 n_sigs = int(sys.argv[2]) if len(sys.argv) > 2 else 20_000_000
-tunings = [int(x) for x in sys.argv[3:]] or [0, 64, 32]
+tunings = [int(x) for x in sys.argv[3:]] or [0, 128, 32]
 protos = synth.make_prototypes(12345, max(64, -(-n_sigs // 293) + 8), 300, 60.0)
 batch = synth.make_proteins_parallel(12346, protos, n_prot)
 sig = synth.make_signatures(protos, n_sigs, dedupe=n_sigs <= 2_000_000)
