@@ -91,11 +91,14 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
                   const uint32_t *__restrict__ hints, HitRec *__restrict__ hits, uint64_t *__restrict__ hit_keys,
                   uint16_t *__restrict__ hit_avg, uint32_t *__restrict__ n_hits, unsigned long long *__restrict__ totals) {
     __shared__ uint8_t lut[256];
+    __shared__ uint4 queues[kProbeThreads / 32][kTile];  // per warp: windows left for the hash probe, then their results
     fill_aa_lut(lut);
     __syncthreads();
+    uint4 *queue = queues[threadIdx.x >> 5];
 
     constexpr uint32_t full = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt = (1u << lane) - 1u;
     const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint4 *__restrict__ slots = reinterpret_cast<const uint4 *>(tv.slots);
@@ -120,6 +123,8 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
             HitRec *out = hits + seq_base;
             uint32_t hv = kNoHint;     // hint of segment (32 * round + lane), reloaded every 8 steps
             uint32_t carry = kNoHint;  // last hint seen in front of the current segment (the first one there is, to begin with)
+            uint32_t rw, rx;           // residue words of the step, fetched one step ahead
+            tile_words(wb, nwords, 0, lane, rw, rx);
 
             for (uint32_t t0 = 0; t0 < nwin; t0 += kTile) {
                 const uint32_t seg0 = t0 >> kHintShift;  // first of the four segments of this step
@@ -130,12 +135,13 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
                         if (m) carry = __shfl_sync(full, hv, __ffs(m) - 1);
                     }
                 }
-                const TileKeys tk = tile_keys(lut, wb, nwords, sh, t0, lane, len, nwin);
+                const TileKeys tk = tile_keys_from(lut, rw, rx, sh, t0, lane, len, nwin);
+                if (t0 + kTile < nwin) tile_words(wb, nwords, t0 + kTile, lane, rw, rx);
                 const uint32_t q0 = t0 + 4u * lane;
                 const uint32_t act = tk.act;
                 if (pf) {
                     // pull into L2 what the next step (or, from the first step, the next protein of this warp) starts with
-                    if (lane < 2u && t0 + kTile + 128u * lane < len) prefetch_l2(p0 + t0 + kTile + 128u * lane);
+                    if (lane < 2u && t0 + 2u * kTile + 128u * lane < len) prefetch_l2(p0 + t0 + 2u * kTile + 128u * lane);
                     if (t0 == 0 && i + n_warps < n && lane >= 2u && lane < 5u) {
                         const uint64_t nb = __ldg(offsets + i + n_warps);
                         if (lane < 4u) prefetch_l2(residues + nb + 128u * (lane - 2u));
@@ -158,7 +164,7 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
                 const uint32_t mh = q == 0 ? f[0] : q == 1 ? f[1] : q == 2 ? f[2] : f[3];
 
                 // ---- one round trip: occupancy words (L2) and the chain entries the hint predicts (coalesced) ----
-                uint32_t bw[4];
+                uint32_t bw[4] = {0u, 0u, 0u, 0u};
                 if (tv.occupied) {
 #pragma unroll
                     for (int j = 0; j < 4; j++)
@@ -196,36 +202,53 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
                         if ((need & (1u << j)) && !((bw[j] >> (h[j] & 31u)) & 1u)) need &= ~(1u << j);
                 }
 
-                // ---- what is left: lookup_hash_entry (kguts.cc:585-602), independent loads first ----
+                // ---- what is left: lookup_hash_entry (kguts.cc:585-602).  The windows left are few (a tenth) and scattered over
+                //      the lanes, so they are queued in shared memory and probed one per lane: one dense pass instead of four
+                //      sparse ones, and one slot in registers instead of four. ----
                 if (__any_sync(full, need != 0u)) {
-                    uint4 v[4];
+                    uint32_t qp[4], n_left = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t b = __ballot_sync(full, (need >> j) & 1u);
+                        qp[j] = n_left + __popc(b & lt);
+                        n_left += __popc(b);
+                    }
 #pragma unroll
                     for (int j = 0; j < 4; j++)
-                        if (need & (1u << j)) v[j] = __ldg(slots + h[j]);
+                        if (need & (1u << j)) queue[qp[j]] = make_uint4((uint32_t)tk.key[j], (uint32_t)(tk.key[j] >> 32), h[j], bw[j]);
+                    __syncwarp();
+                    for (uint32_t k = lane; k < n_left; k += 32u) {
+                        const uint4 it = queue[k];
+                        uint32_t hh = it.z;
+                        uint4 v = __ldg(slots + hh);
+                        uint32_t found = 0;
+                        for (;;) {
+                            if (v.x == it.x && (v.y & 0xFu) == it.y) { found = 1u; break; }
+                            if (v.y & 0x8u) break;
+                            hh = (hh + 1u == nsig) ? 0u : hh + 1u;
+                            if (hh == it.z) break;  // a table without an empty slot
+                            if (tv.occupied) {
+                                const uint32_t ow = (hh >> 5) == (it.z >> 5) ? it.w : __ldg(tv.occupied + (hh >> 5));
+                                if (!((ow >> (hh & 31u)) & 1u)) break;
+                            }
+                            v = __ldg(slots + hh);
+                        }
+                        queue[k] = make_uint4(found, v.y, v.z, v.w);
+                    }
+                    __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         if (need & (1u << j)) {
-                            uint32_t hh = h[j];
-                            bool found = false;
-                            for (;;) {
-                                if (packed_match(v[j], tk.key[j])) { found = true; break; }
-                                if (v[j].y & 0x8u) break;
-                                hh = (hh + 1u == nsig) ? 0u : hh + 1u;
-                                if (hh == h[j]) break;  // a table without an empty slot
-                                if (tv.occupied) {
-                                    const uint32_t ow = (hh >> 5) == (h[j] >> 5) ? bw[j] : __ldg(tv.occupied + (hh >> 5));
-                                    if (!((ow >> (hh & 31u)) & 1u)) break;
-                                }
-                                v[j] = __ldg(slots + hh);
-                            }
-                            if (found) {
-                                w[j].y = v[j].y;
-                                w[j].z = v[j].z;
-                                w[j].w = v[j].w;
+                            const uint4 r = queue[qp[j]];
+                            if (r.x) {
+                                w[j].y = r.y;
+                                w[j].z = r.z;
+                                w[j].w = r.w;
                                 hm |= 1u << j;
                             }
                         }
                     }
+                    __syncwarp();
                 }
                 my_probes += __popc(act);
 

@@ -89,12 +89,27 @@ struct TileKeys {
     uint32_t act;
 };
 
+// the residue words of one step: 32 words (one per lane) + 3 spill words (lanes 0-2)
+__device__ __forceinline__ void tile_words(const uint32_t *__restrict__ wb, uint32_t nwords, uint32_t t0, uint32_t lane, uint32_t &w,
+                                           uint32_t &x) {
+    const uint32_t wi = (t0 >> 2) + lane;
+    w = wi < nwords ? __ldg(wb + wi) : 0u;
+    x = (lane < 3u && wi + 32u < nwords) ? __ldg(wb + wi + 32u) : 0u;
+}
+
+__device__ __forceinline__ TileKeys tile_keys_from(const uint8_t *lut, uint32_t w, uint32_t x, uint32_t sh, uint32_t t0, uint32_t lane,
+                                                   uint32_t len, uint32_t &nwin);
+
 __device__ __forceinline__ TileKeys tile_keys(const uint8_t *lut, const uint32_t *__restrict__ wb, uint32_t nwords, uint32_t sh,
                                               uint32_t t0, uint32_t lane, uint32_t len, uint32_t &nwin) {
-    // ---- residues: 32 words + 3 spill words, re-aligned to the protein start ----
-    const uint32_t wi = (t0 >> 2) + lane;
-    uint32_t w = wi < nwords ? __ldg(wb + wi) : 0u;
-    uint32_t x = (lane < 3u && wi + 32u < nwords) ? __ldg(wb + wi + 32u) : 0u;
+    uint32_t w, x;
+    tile_words(wb, nwords, t0, lane, w, x);
+    return tile_keys_from(lut, w, x, sh, t0, lane, len, nwin);
+}
+
+__device__ __forceinline__ TileKeys tile_keys_from(const uint8_t *lut, uint32_t w, uint32_t x, uint32_t sh, uint32_t t0, uint32_t lane,
+                                                   uint32_t len, uint32_t &nwin) {
+    // ---- residues re-aligned to the protein start ----
     uint32_t w_next = __shfl_down_sync(0xffffffffu, w, 1);
     const uint32_t x0 = __shfl_sync(0xffffffffu, x, 0);
     if (lane == 31u) w_next = x0;
