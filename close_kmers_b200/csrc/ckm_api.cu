@@ -766,7 +766,18 @@ static int launch_range(ckm_ctx *c, cudaStream_t stream, const uint8_t *d_res, c
                 const unsigned hb = (unsigned)std::min<uint64_t>(((uint64_t)cnt + per_block - 1) / per_block, (uint64_t)c->sm_count * 64);
                 hint_kernel<<<hb, 256, 0, stream>>>(tv, d_res, d_off + i0, cnt, i0, (uint32_t *)c->hints.p);
                 c->launches++;
-                if (c->tuning & 0x10000u)
+                if (!(c->tuning & 0x40000u)) {  // two-stage pipeline per warp
+                    const uint64_t wpb = kHint2Threads / 32;
+                    const unsigned pb = (unsigned)std::min<uint64_t>(((uint64_t)cnt + wpb - 1) / wpb, (uint64_t)c->sm_count * 128);
+                    if (c->tuning & 0x10000u)
+                        probe_hint2_kernel<5><<<pb, kHint2Threads, 0, stream>>>(tv, d_res, d_off + i0, cnt, i0, (const uint32_t *)c->hints.p,
+                                                                               (HitRec *)c->hits.p, keys, avg, (uint32_t *)c->n_hits.p + i0,
+                                                                               (unsigned long long *)c->totals.p);
+                    else
+                        probe_hint2_kernel<6><<<pb, kHint2Threads, 0, stream>>>(tv, d_res, d_off + i0, cnt, i0, (const uint32_t *)c->hints.p,
+                                                                               (HitRec *)c->hits.p, keys, avg, (uint32_t *)c->n_hits.p + i0,
+                                                                               (unsigned long long *)c->totals.p);
+                } else if (c->tuning & 0x10000u)
                     probe_hint_kernel<4><<<(unsigned)blocks, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, i0, (const uint32_t *)c->hints.p,
                                                                                          (HitRec *)c->hits.p, keys, avg, (uint32_t *)c->n_hits.p + i0,
                                                                                          (unsigned long long *)c->totals.p);
