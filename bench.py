@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -71,9 +71,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([time.time()] + [x.strip() for x in line.split(",")])
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Statistics over the samples that arrived inside [t_begin, t_end] (the timed regions); the sampler itself is
+        started earlier so that nvidia-smi is already reporting when a short timed region begins."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -84,7 +86,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r[1:] for r in self.rows if t_begin is None or t_begin <= r[0] <= t_end + 0.05]
+        window = "timed regions"
+        if not rows:  # a timed region shorter than one nvidia-smi period: the samples of the same run around it
+            rows = [r[1:] for r in self.rows]
+            window = "whole run (no sample fell inside the timed regions)"
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -94,7 +101,7 @@ class ClockSampler:
                 if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def build_world(name, n_sigs, n_proteins, sd, rank, seed=12345):
@@ -327,6 +334,8 @@ def main():
     def step_e2e():
         return guts.call_batch_raw(hp_res.value, hp_off.value, n, flags)
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(W, 3)):
         step_resident()
     guts.synchronize()
@@ -347,10 +356,9 @@ def main():
     # ---- kernel-resident: K steps, device-timed on the ctx stream, max over ranks
     guts.profile_enable(True)
     guts.profile_read()
-    sampler = ClockSampler(local)
     launches0 = guts.launch_count
     barrier()
-    sampler.start()
+    t_clk0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(K):
@@ -358,7 +366,6 @@ def main():
     e1.record(stream)
     guts.synchronize()
     barrier()
-    clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
     launches = guts.launch_count - launches0
     probe_ms, scan_ms, nb_prof = guts.profile_read()
@@ -368,7 +375,7 @@ def main():
     plain_probe_ms = None
     if chain["entries"]:
         # A/B, outside the timed region: the same steps with plain hash probing (probe_kernel) instead of
-        # probe_chain_kernel -- identical results, every hit its own DRAM transaction
+        # hint_kernel + probe_hint_kernel -- identical results, every hit its own DRAM transaction
         guts.set_tuning(32)
         step_resident()
         guts.synchronize()
@@ -391,6 +398,7 @@ def main():
         out = step_e2e()
     t_e2e = time.perf_counter() - t0
     assert out.n_probes == n_probes, (out.n_probes, n_probes)
+    clocks = sampler.stop(t_clk0, time.time())  # both timed regions (device-resident steps, then end-to-end steps)
 
     ms_t = torch.tensor([ms_total, t_e2e * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -421,7 +429,7 @@ def main():
         # independent random 16 B reads over the resident table: best of a few occupancies
         cal_rate = max(guts.calibrate_gather(16, u, 64, b)[0] for u, b in ((1, 8), (4, 4), (4, 8)))
         value = prot_all * K / (ms_total * 1e-3)
-        probe_name = "probe_chain_kernel" if chain["entries"] else "probe_kernel"
+        probe_name = "hint_kernel+probe_hint_kernel" if chain["entries"] else "probe_kernel"
         line = {
             "metric": "proteins/sec", "value": value, "unit": "proteins/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -257,7 +257,7 @@ static int install_table(ckm_ctx *c, DevBuf raw, uint64_t n) {
     c->cpos.release();
     c->n_chain = 0;
     const char *ch = getenv("CKM_CHAIN");  // "0" disables, "1" forces
-    const bool want_chain = ch ? ch[0] == '1' : false;  // opt-in while probe_chain_kernel is slower than probe_kernel
+    const bool want_chain = ch ? ch[0] == '1' : table_bytes > (size_t)c->l2_bytes;
     if (want_chain && c->slot_bytes == kPackedSlotBytes && n < 0xFFFFFFF0ull) {
         // an optimisation only: without the memory for it (~32 B per bucket while building) the table works as before
         if (build_chain(c)) {
@@ -766,18 +766,7 @@ static int launch_range(ckm_ctx *c, cudaStream_t stream, const uint8_t *d_res, c
                 const unsigned hb = (unsigned)std::min<uint64_t>(((uint64_t)cnt + per_block - 1) / per_block, (uint64_t)c->sm_count * 64);
                 hint_kernel<<<hb, 256, 0, stream>>>(tv, d_res, d_off + i0, cnt, i0, (uint32_t *)c->hints.p);
                 c->launches++;
-                if (!(c->tuning & 0x40000u)) {  // two-stage pipeline per warp
-                    const uint64_t wpb = kHint2Threads / 32;
-                    const unsigned pb = (unsigned)std::min<uint64_t>(((uint64_t)cnt + wpb - 1) / wpb, (uint64_t)c->sm_count * 128);
-                    if (c->tuning & 0x10000u)
-                        probe_hint2_kernel<5><<<pb, kHint2Threads, 0, stream>>>(tv, d_res, d_off + i0, cnt, i0, (const uint32_t *)c->hints.p,
-                                                                               (HitRec *)c->hits.p, keys, avg, (uint32_t *)c->n_hits.p + i0,
-                                                                               (unsigned long long *)c->totals.p);
-                    else
-                        probe_hint2_kernel<6><<<pb, kHint2Threads, 0, stream>>>(tv, d_res, d_off + i0, cnt, i0, (const uint32_t *)c->hints.p,
-                                                                               (HitRec *)c->hits.p, keys, avg, (uint32_t *)c->n_hits.p + i0,
-                                                                               (unsigned long long *)c->totals.p);
-                } else if (c->tuning & 0x10000u)
+                if (c->tuning & 0x10000u)
                     probe_hint_kernel<4><<<(unsigned)blocks, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, i0, (const uint32_t *)c->hints.p,
                                                                                          (HitRec *)c->hits.p, keys, avg, (uint32_t *)c->n_hits.p + i0,
                                                                                          (unsigned long long *)c->totals.p);

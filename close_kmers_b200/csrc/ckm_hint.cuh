@@ -221,6 +221,15 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
                         const uint4 it = queue[k];
                         uint32_t hh = it.z;
                         uint4 v = __ldg(slots + hh);
+                        // a window gets here because its home slot is taken -- nearly always by another k-mer, so the probe
+                        // sequence goes on: when the same occupancy word says the next slot is taken too, fetch it now
+                        if ((hh & 31u) != 31u && hh + 1u < nsig && ((it.w >> ((hh & 31u) + 1u)) & 1u) && tv.occupied) {
+                            const uint4 v1 = __ldg(slots + hh + 1u);
+                            if (!(v.x == it.x && (v.y & 0xFu) == it.y) && !(v.y & 0x8u)) {
+                                v = v1;
+                                hh++;
+                            }
+                        }
                         uint32_t found = 0;
                         for (;;) {
                             if (v.x == it.x && (v.y & 0xFu) == it.y) { found = 1u; break; }
@@ -284,288 +293,6 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
     }
 
     // batch totals: one atomic per warp (totals[4] = hits answered from the neighbour copy)
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        my_probes += __shfl_down_sync(full, my_probes, d);
-        my_hits += __shfl_down_sync(full, my_hits, d);
-        my_chain += __shfl_down_sync(full, my_chain, d);
-    }
-    if (lane == 0) {
-        atomicAdd(totals + 0, (unsigned long long)my_probes);
-        atomicAdd(totals + 1, (unsigned long long)my_hits);
-        atomicAdd(totals + 4, (unsigned long long)my_chain);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// The same probe as a two-stage software pipeline per warp.
-//
-// What probe_hint_kernel still waits for is the one DRAM round trip of the windows left for the hash probe: their slots are
-// loaded and examined in the same step, and nothing else in the step can proceed without them (hits are appended in
-// position order).  Here a step's results are staged in shared memory instead of registers:
-//
-//   front(T)   keys, hints, occupancy words, chain compare; chain hits go to stage[T & 1][window] as whole 16-byte entries,
-//              windows left over to queue[T & 1] with an "unanswered" marker in their stage entry; the home slots of the
-//              first 32 queued windows are *requested* (one per lane) ...
-//   back(T-1)  ... and examined one step later, after front(T) has run: linear probing continues where needed, slots that
-//              match overwrite their stage entry, and the step's stage entries are compacted in position order and stored.
-//
-// so the round trip of step T-1 is covered by the front half of step T.  Per warp: 2 x (2 KB stage + 1 KB queue).
-// ---------------------------------------------------------------------------------------------------
-constexpr int kHint2Threads = 128;
-
-// stage[] index of a step's window e: 16-byte entries are written 32 consecutive ones at a time (one per lane) and read
-// four consecutive ones per lane; XOR-ing the low three bits with the next three keeps both patterns free of bank conflicts
-__device__ __forceinline__ uint32_t stage_at(uint32_t e) { return e ^ ((e >> 3) & 7u); }
-
-__device__ __forceinline__ uint32_t ldg_u32_na(const uint32_t *p) {  // read-once data: do not displace L1 lines
-    uint32_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ uint4 ldg_v4_na(const uint4 *p) {
-    uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
-}
-
-template <int MINB>
-__global__ void __launch_bounds__(kHint2Threads, MINB)
-probe_hint2_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64_t *__restrict__ offsets, uint32_t n, uint32_t index_base,
-                   const uint32_t *__restrict__ hints, HitRec *__restrict__ hits, uint64_t *__restrict__ hit_keys,
-                   uint16_t *__restrict__ hit_avg, uint32_t *__restrict__ n_hits, unsigned long long *__restrict__ totals) {
-    __shared__ uint8_t lut[256];
-    __shared__ uint4 stages[kHint2Threads / 32][2][kTile];  // per window of a step: the packed slot behind its hit, or y = 0x8 ("none")
-    __shared__ uint4 queues[kHint2Threads / 32][2][kTile];  // windows left for the hash probe: key, window << 8, home slot, occupancy word
-    fill_aa_lut(lut);
-    __syncthreads();
-
-    constexpr uint32_t full = 0xffffffffu;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t wid = threadIdx.x >> 5;
-    const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    const uint4 *__restrict__ slots = reinterpret_cast<const uint4 *>(tv.slots);
-    const uint32_t nsig = (uint32_t)tv.num_sigs;  // the neighbour copy is only built for tables below 2^32 buckets
-    const uint32_t m35 = tv.m35;
-    const bool na = !(tv.tuning & 0x80000u);
-    uint32_t my_probes = 0, my_hits = 0, my_chain = 0;
-
-    for (uint32_t i = warp0; i < n; i += n_warps) {
-        const uint64_t seq_base = __ldg(offsets + i);
-        const uint32_t len = (uint32_t)(__ldg(offsets + i + 1) - seq_base);
-        uint32_t count = 0;
-        if (len > CKM_KMER_SIZE) {
-            uint32_t nwin = len - CKM_KMER_SIZE;  // the last window is never probed (kguts.cc:792, 798)
-            const uint32_t nseg = (nwin + kHintSeg - 1) >> kHintShift;
-            const uint32_t *hp = hints + hint_region(seq_base, index_base + i);
-            const uint8_t *p0 = residues + seq_base;
-            const uint32_t s = (uint32_t)(reinterpret_cast<uintptr_t>(p0) & 3u);
-            const uint32_t *wb = reinterpret_cast<const uint32_t *>(p0 - s);
-            const uint32_t nwords = (len + s + 3u) >> 2;
-            const uint32_t sh = 8u * s;
-            HitRec *out = hits + seq_base;
-            uint32_t hv = kNoHint, carry = kNoHint;
-            uint32_t rw, rx;
-            tile_words(wb, nwords, 0, lane, rw, rx);
-            if (i + n_warps < n && lane < 3u) {  // the next protein of this warp: pull its first lines into L2
-                const uint64_t nb = __ldg(offsets + i + n_warps);
-                if (lane < 2u) prefetch_l2(residues + nb + 128u * lane);
-                else prefetch_l2(hints + hint_region(nb, index_base + i + n_warps));
-            }
-
-            // front half of the step at t0: everything up to requesting the home slots of the windows left over.
-            // Leaves: pm = windows of this lane that may hold a hit, nl = queued windows, (v, occ1, v1) = the slot requested by
-            // this lane, whether the slot after it is known to be occupied, and that slot (requested too).
-            auto front = [&](uint32_t t0, uint32_t par, uint32_t &pm, uint32_t &nl, uint4 &v, uint4 &v1, uint32_t &occ1) {
-                uint4 *stage = stages[wid][par];
-                uint4 *queue = queues[wid][par];
-                const uint32_t seg0 = t0 >> kHintShift;
-                if ((seg0 & 31u) == 0u) {
-                    hv = (seg0 + lane < nseg) ? __ldg(hp + seg0 + lane) : kNoHint;
-                    if (carry == kNoHint) {
-                        const uint32_t m = __ballot_sync(full, hv != kNoHint);
-                        if (m) carry = __shfl_sync(full, hv, __ffs(m) - 1);
-                    }
-                }
-                const TileKeys tk = tile_keys_from(lut, rw, rx, sh, t0, lane, len, nwin);
-                if (t0 + kTile < nwin) tile_words(wb, nwords, t0 + kTile, lane, rw, rx);
-                if (lane < 2u && t0 + 2u * kTile + 128u * lane < len) prefetch_l2(p0 + t0 + 2u * kTile + 128u * lane);
-                const uint32_t act = tk.act;
-                uint32_t h[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) h[j] = m35 ? fast_mod35(tk.key[j], nsig, m35) : (uint32_t)fast_mod(tk.key[j], tv.num_sigs, tv.magic);
-
-                uint32_t f[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    f[k] = __shfl_sync(full, hv, (seg0 & 31u) + k);
-                    if (f[k] == kNoHint) f[k] = carry;
-                    else carry = f[k];
-                }
-
-                // ---- one round trip: occupancy words (L2) and the chain entries the hints predict.  Load k covers segment k
-                //      of the step -- one hint, 32 consecutive entries, one per lane: 512 contiguous bytes -- and goes to
-                //      stage[] as it is; every lane then compares the keys of its own four windows there. ----
-                uint32_t bw[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-                if (tv.occupied) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        if (act & (1u << j)) bw[j] = na ? ldg_u32_na(tv.occupied + (h[j] >> 5)) : __ldg(tv.occupied + (h[j] >> 5));
-                }
-                {
-                    uint4 cv[4];
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const uint32_t p = t0 + 32u * k + lane;
-                        const uint32_t idx = f[k] + p;
-                        cv[k] = make_uint4(0u, 0x8u, 0u, 0u);
-                        if (f[k] != kNoHint && p < nwin && idx < tv.n_chain) {
-                            cv[k] = na ? ldg_v4_na(tv.chain + idx) : __ldg(tv.chain + idx);
-                            if (lane == 0 && p + kTile < nwin && idx + kTile < tv.n_chain) {
-                                prefetch_l2(tv.chain + idx + kTile);
-                                prefetch_l2(tv.chain + idx + kTile + 16u);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; k++) stage[stage_at(32u * k + lane)] = cv[k];
-                }
-                __syncwarp();
-                uint32_t hm = 0;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if (act & (1u << j)) {
-                        const uint2 e = *reinterpret_cast<const uint2 *>(&stage[stage_at(4u * lane + j)]);
-                        if (e.x == (uint32_t)tk.key[j] && (e.y & 0xFu) == (uint32_t)(tk.key[j] >> 32)) hm |= 1u << j;
-                    }
-                }
-                uint32_t need = act & ~hm;
-                if (tv.tuning & 0x100000u) need = 0;  // EXPERIMENT (wrong results): no hash probes
-#pragma unroll
-                for (int j = 0; j < 4; j++)  // a window whose home slot is empty is a miss
-                    if ((need & (1u << j)) && !((bw[j] >> (h[j] & 31u)) & 1u)) need &= ~(1u << j);
-                nl = 0;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t b = __ballot_sync(full, (need >> j) & 1u);
-                    if (need & (1u << j)) {
-                        stage[stage_at(4u * lane + j)].y = 0x8u;
-                        queue[nl + __popc(b & lt)] =
-                            make_uint4((uint32_t)tk.key[j], (uint32_t)(tk.key[j] >> 32) | ((4u * lane + j) << 8), h[j], bw[j]);
-                    }
-                    nl += __popc(b);
-                }
-                __syncwarp();
-                occ1 = 0;
-                if (lane < nl) {  // request the home slots of the first 32 queued windows; examined in the back half
-                    const uint4 it = queue[lane];
-                    v = na ? ldg_v4_na(slots + it.z) : __ldg(slots + it.z);
-                    // the slot after it, when the same occupancy word says it is taken (the probe sequence goes on there)
-                    if ((it.z & 31u) != 31u && it.z + 1u < nsig && ((it.w >> ((it.z & 31u) + 1u)) & 1u)) {
-                        occ1 = 1u;
-                        v1 = __ldg(slots + it.z + 1u);
-                    }
-                }
-                pm = hm | need;
-                my_probes += __popc(act);
-                my_chain += __popc(hm);
-            };
-
-            // back half of the step at t0: examine the requested slots, finish their probe sequences, compact and store
-            auto back = [&](uint32_t t0, uint32_t par, uint32_t pm, uint32_t nl, const uint4 &v0, const uint4 &v1, uint32_t occ1) {
-                uint4 *stage = stages[wid][par];
-                const uint4 *queue = queues[wid][par];
-                // ---- lookup_hash_entry (kguts.cc:585-602) for the queued windows ----
-                for (uint32_t k = lane; k < nl; k += 32u) {
-                    const uint4 it = queue[k];
-                    const uint32_t khi = it.y & 0xFFu;
-                    uint32_t hh = it.z;
-                    uint4 v;
-                    if (k < 32u) {
-                        v = v0;
-                        if (occ1 && !(v.x == it.x && (v.y & 0xFu) == khi) && !(v.y & 0x8u)) {  // second slot of the sequence, already here
-                            hh++;
-                            v = v1;
-                        }
-                    } else {
-                        v = __ldg(slots + hh);
-                    }
-                    for (uint32_t steps = 0;;) {
-                        if (v.x == it.x && (v.y & 0xFu) == khi) {
-                            stage[stage_at(it.y >> 8)] = v;
-                            break;
-                        }
-                        if (v.y & 0x8u) break;
-                        hh = (hh + 1u == nsig) ? 0u : hh + 1u;
-                        if (++steps >= nsig) break;  // a table without an empty slot
-                        if (tv.occupied) {
-                            const uint32_t ow = (hh >> 5) == (it.z >> 5) ? it.w : __ldg(tv.occupied + (hh >> 5));
-                            if (!((ow >> (hh & 31u)) & 1u)) break;
-                        }
-                        v = __ldg(slots + hh);
-                    }
-                }
-                __syncwarp();
-                // ---- ordered compaction: exclusive prefix of per-lane hit counts ----
-                uint32_t hit = 0;
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if ((pm & (1u << j)) && !(stage[stage_at(4u * lane + j)].y & 0x8u)) hit |= 1u << j;
-                const uint32_t cnt = __popc(hit);
-                uint32_t incl = cnt;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t t = __shfl_up_sync(full, incl, d);
-                    if (lane >= (uint32_t)d) incl += t;
-                }
-                const uint32_t tile_hits = __shfl_sync(full, incl, 31);
-                uint32_t o = count + incl - cnt;
-                const uint32_t q0 = t0 + 4u * lane;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if (hit & (1u << j)) {
-                        const uint4 r = stage[stage_at(4u * lane + j)];
-                        HitRec rec;
-                        rec.pos = q0 + j;
-                        rec.fI = r.w & (kPackedFieldLimit - 1);
-                        rec.wt = __uint_as_float(r.z);
-                        rec.oI = (int32_t)(((r.y >> 20) & 0xFFFu) | ((r.w >> 22) << 12)) - 1;
-                        if (!(tv.tuning & 0x200000u)) out[o] = rec;  // EXPERIMENT bit: no hit stores
-                        if (hit_keys) hit_keys[seq_base + o] = (uint64_t)r.x | ((uint64_t)(r.y & 0x7u) << 32);
-                        if (hit_avg) hit_avg[seq_base + o] = (uint16_t)((r.y >> 4) & 0xFFFFu);
-                        o++;
-                    }
-                }
-                count += tile_hits;
-                __syncwarp();
-            };
-
-            // the step whose back half is still to run
-            uint32_t pmP = 0, nlP = 0, occP = 0, par = 0;
-            uint4 vP = make_uint4(0u, 0x8u, 0u, 0u), wP = vP;
-            bool have_prev = false;
-            for (uint32_t t0 = 0;; t0 += kTile) {
-                const bool fr = t0 < nwin;
-                uint32_t pmN = 0, nlN = 0, occN = 0;
-                uint4 vN = make_uint4(0u, 0x8u, 0u, 0u), wN = vN;
-                if (fr) front(t0, par, pmN, nlN, vN, wN, occN);
-                if (have_prev) back(t0 - kTile, par ^ 1u, pmP, nlP, vP, wP, occP);
-                if (!fr) break;
-                pmP = pmN;
-                nlP = nlN;
-                occP = occN;
-                vP = vN;
-                wP = wN;
-                have_prev = true;
-                par ^= 1u;
-            }
-        }
-        if (lane == 0) n_hits[i] = count;
-        if (lane == 0) my_hits += count;
-    }
-
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         my_probes += __shfl_down_sync(full, my_probes, d);
