@@ -108,6 +108,10 @@ __device__ __forceinline__ uint32_t fast_mod35(uint64_t key, uint32_t d, uint32_
     const uint64_t r = key - (uint64_t)q * d;
     return r >= d ? (uint32_t)(r - d) : (uint32_t)r;
 }
+// home bucket of a valid 8-mer key
+__device__ __forceinline__ uint64_t table_home(const TableView &tv, uint64_t key) {
+    return tv.m35 ? (uint64_t)fast_mod35(key, (uint32_t)tv.num_sigs, tv.m35) : fast_mod(key, tv.num_sigs, tv.magic);
+}
 static inline uint32_t magic35(uint64_t num_sigs) {
     return (num_sigs >= 64 && num_sigs < 0xFFFFFFFFull) ? (uint32_t)((1ull << 35) / num_sigs) : 0u;
 }

@@ -85,13 +85,13 @@ hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64_t *
     }
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(kProbeThreads, MINB)
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64_t *__restrict__ offsets, uint32_t n, uint32_t index_base,
                   const uint32_t *__restrict__ hints, HitRec *__restrict__ hits, uint64_t *__restrict__ hit_keys,
                   uint16_t *__restrict__ hit_avg, uint32_t *__restrict__ n_hits, unsigned long long *__restrict__ totals) {
     __shared__ uint8_t lut[256];
-    __shared__ uint4 queues[kProbeThreads / 32][kTile];  // per warp: windows left for the hash probe, then their results
+    __shared__ uint4 queues[THREADS / 32][kTile];  // per warp: windows left for the hash probe, then their results
     fill_aa_lut(lut);
     __syncthreads();
     uint4 *queue = queues[threadIdx.x >> 5];

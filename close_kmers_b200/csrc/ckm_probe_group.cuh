@@ -114,7 +114,7 @@ probe_group_kernel(TableView tv, const uint8_t *__restrict__ residues, const uin
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 key[j] = tk.key[j];
-                h[j] = fast_mod(key[j], tv.num_sigs, tv.magic);
+                h[j] = table_home(tv, key[j]);
             }
             // ---- probe: occupancy bits from L2 first, then the sector loads that are still needed ----
             uint32_t need = act;

@@ -17,7 +17,7 @@ rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 cc.ensure_built()
 ALL = api.WANT_CALLS | api.WANT_HITS | api.WANT_OTU | api.WANT_BEST
 t_start = time.time()
-stats = dict(rounds=0, proteins=0, hits=0, calls=0, family_entries=0, reads=0)
+stats = dict(rounds=0, proteins=0, hits=0, calls=0, family_entries=0, reads=0, hits_from_copy=0)
 for rnd in range(rounds):
     rng = np.random.default_rng(1000 + rnd)
     mean_len = int(rng.choice([60, 150, 300, 600]))
@@ -39,6 +39,7 @@ for rnd in range(rounds):
                 continue
     os.environ["CKM_OCCUPANCY_BITMAP"] = str(rnd % 2)
     os.environ["CKM_FORCE_RAW_SLOTS"] = str((rnd // 2) % 2)
+    os.environ["CKM_CHAIN"] = str((rnd // 4) % 2)  # neighbour copy + hinted probe (packed slots only)
     g = api.KmerGuts(image=img, function_names=synth.function_names(sig.n_functions))
     g.family_load(fam.kmers, fam.fam_off, fam.fam_ids, fam.pgf, fam.plf, fam.function)
     orc = cc.Oracle().open_image(img)
@@ -54,6 +55,7 @@ for rnd in range(rounds):
     batch = wl.concat_batches(wl.edge_batch(protos), synth.batch_from_strings(pieces))
     want = orc.call_batch(batch, ALL)
     got = g.process_aa_seq_batch(batch.residues, batch.offsets, ALL)
+    from_copy = g.chain_info["hits_from_copy"]
     wl.assert_results_equal(got, want, f"round {rnd} calls {prm}")
     assert got["n_probes"] == want["n_probes"]
     sc, so = orc.family_scores(batch)
@@ -72,6 +74,7 @@ for rnd in range(rounds):
     stats["calls"] += len(want["calls"])
     stats["family_entries"] += len(sc)
     stats["reads"] += reads.n
+    stats["hits_from_copy"] += from_copy
     g.close()
     orc.close()
 stats["seconds"] = time.time() - t_start
