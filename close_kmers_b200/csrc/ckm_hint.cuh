@@ -104,7 +104,7 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
     const uint4 *__restrict__ slots = reinterpret_cast<const uint4 *>(tv.slots);
     const uint32_t nsig = (uint32_t)tv.num_sigs;  // the neighbour copy is only built for tables below 2^32 buckets
     uint32_t my_probes = 0, my_hits = 0, my_chain = 0;
-    const bool pf = !(tv.tuning & 0x20000u);
+    const bool pf = !(tv.tuning & 0x40000u);
     const uint32_t m35 = tv.m35;
 
     for (uint32_t i = warp0; i < n; i += n_warps) {

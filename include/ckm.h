@@ -159,8 +159,10 @@ int ckm_has_occupancy_bitmap(const ckm_ctx *ctx);
  * identical with and without it).  info[0] = entries (0 = not built), info[1] = chains, info[2] = build time in
  * microseconds, info[3] = hits of the last batch that were answered from the copy instead of a hash probe. */
 int ckm_chain_info(ckm_ctx *ctx, uint64_t info[4]);
-/* L2 cache-policy switches of the probe kernel (results unaffected): bit0 table loads evict_first, bit1 bitmap
- * loads evict_last, bit2 hit-record stores evict_first, bit5 plain hash probing although the neighbour copy exists */
+/* A/B switches of the probe kernels (results unaffected): bit0 table loads evict_first, bit1 bitmap loads evict_last,
+ * bit2 hit-record stores evict_first, bit5 (32) plain hash probing although the neighbour copy exists, bit7 (128) / bit6 (64)
+ * the walking probe_chain_kernel at 3 / 2 blocks per SM instead of hint_kernel + probe_hint_kernel, bits 16-17 block shape
+ * of probe_hint_kernel (1 = 4, 2 = 2 blocks per SM), bit18 (0x40000) without its L2 prefetches */
 void ckm_set_tuning(ckm_ctx *ctx, uint32_t bits);
 
 /* ---- parameters (KmerGuts::set_default_parameters / set_parameters, kguts.cc:236-268) -------------- */
