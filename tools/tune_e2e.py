@@ -25,7 +25,7 @@ C.memmove(hp_off.value, batch.offsets.ctypes.data, (batch.n + 1) * 8)
 import torch
 props = torch.cuda.get_device_properties(0)
 print(json.dumps(dict(l2=props.L2_cache_size)), flush=True)
-for chunk_kb, ramp, tail in ((98304, 6, 4), (98304, 24, 8), (98304, 12, 8), (65536, 16, 8), (131072, 32, 8), (98304, 24, 16)):
+for chunk_kb, ramp, tail in ((98304, 24, 16), (49152, 12, 8), (32768, 8, 8), (196608, 48, 16), (65536, 16, 16), (24576, 6, 8), (16384, 4, 4), (98304, 48, 16)):
     os.environ["CKM_PIPELINE_CHUNK_KB"] = str(chunk_kb)
     os.environ["CKM_PIPELINE_RAMP_DIV"] = str(ramp)
     os.environ["CKM_PIPELINE_TAIL_DIV"] = str(tail)
