@@ -766,14 +766,17 @@ static int launch_range(ckm_ctx *c, cudaStream_t stream, const uint8_t *d_res, c
                 const unsigned hb = (unsigned)std::min<uint64_t>(((uint64_t)cnt + per_block - 1) / per_block, (uint64_t)c->sm_count * 64);
                 hint_kernel<<<hb, 256, 0, stream>>>(tv, d_res, d_off + i0, cnt, i0, (uint32_t *)c->hints.p);
                 c->launches++;
-                const uint32_t variant = (c->tuning >> 16) & 3u;  // A/B: block shape / blocks per SM
-#define CKM_HINT_LAUNCH(T, B)                                                                                                         \
-    probe_hint_kernel<T, B><<<(unsigned)std::min<uint64_t>(((uint64_t)cnt + T / 32 - 1) / (T / 32), blocks * (kProbeThreads / T)), T, 0, \
+                const uint32_t variant = (c->tuning >> 16) & 7u;  // A/B: block shape, blocks per SM, hit payload staged in shared memory or registers
+#define CKM_HINT_LAUNCH(T, B, S)                                                                                                      \
+    probe_hint_kernel<T, B, S><<<(unsigned)std::min<uint64_t>(((uint64_t)cnt + T / 32 - 1) / (T / 32), blocks * (kProbeThreads / T)), T, 0, \
                               stream>>>(tv, d_res, d_off + i0, cnt, i0, (const uint32_t *)c->hints.p, (HitRec *)c->hits.p, keys, avg,  \
                                         (uint32_t *)c->n_hits.p + i0, (unsigned long long *)c->totals.p)
-                if (variant == 1u) CKM_HINT_LAUNCH(256, 4);
-                else if (variant == 2u) CKM_HINT_LAUNCH(256, 2);
-                else CKM_HINT_LAUNCH(256, 3);
+                if (variant == 1u) CKM_HINT_LAUNCH(256, 4, true);
+                else if (variant == 2u) CKM_HINT_LAUNCH(128, 8, true);
+                else if (variant == 3u) CKM_HINT_LAUNCH(128, 6, true);
+                else if (variant == 4u) CKM_HINT_LAUNCH(256, 3, false);
+                else if (variant == 5u) CKM_HINT_LAUNCH(256, 3, true);
+                else CKM_HINT_LAUNCH(128, 7, true);  // 72 registers, 28 warps per SM (profiles/r1/tune_hint_v13_1M.jsonl)
 #undef CKM_HINT_LAUNCH
             } else if (c->tuning & 64u)
                 probe_chain_kernel<2><<<(unsigned)blocks, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, (HitRec *)c->hits.p, keys, avg,

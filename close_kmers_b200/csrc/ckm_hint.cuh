@@ -72,8 +72,9 @@ hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64_t *
                 for (uint32_t steps = 0; steps < nsig; steps++) {
                     if (tv.occupied && !((__ldg(tv.occupied + (h >> 5)) >> (h & 31u)) & 1u)) break;
                     const uint4 v = __ldg(slots + h);
+                    const uint32_t cp = __ldg(tv.cpos + h);  // requested with the slot: one round trip instead of two on a hit
                     if (packed_match(v, key)) {
-                        hint = __ldg(tv.cpos + h) - p;
+                        hint = cp - p;
                         break;
                     }
                     if (v.y & 0x8u) break;
@@ -85,16 +86,24 @@ hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64_t *
     }
 }
 
-template <int THREADS, int MINB>
+// stage[] index of a step's window e (STAGE variant): 16-byte entries, four consecutive ones per lane; XOR-ing the low three
+// bits with the next three spreads a warp's accesses over all banks
+__device__ __forceinline__ uint32_t stage_at(uint32_t e) { return e ^ ((e >> 3) & 7u); }
+
+// STAGE: the slot behind every hit of a step waits in shared memory (one entry per window) instead of in twelve registers per
+// lane, which is what keeps the register variant at 80 registers / 24 warps per SM.
+template <int THREADS, int MINB, bool STAGE>
 __global__ void __launch_bounds__(THREADS, MINB)
 probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64_t *__restrict__ offsets, uint32_t n, uint32_t index_base,
                   const uint32_t *__restrict__ hints, HitRec *__restrict__ hits, uint64_t *__restrict__ hit_keys,
                   uint16_t *__restrict__ hit_avg, uint32_t *__restrict__ n_hits, unsigned long long *__restrict__ totals) {
     __shared__ uint8_t lut[256];
     __shared__ uint4 queues[THREADS / 32][kTile];  // per warp: windows left for the hash probe, then their results
+    __shared__ uint4 stages[STAGE ? THREADS / 32 : 1][kTile];
     fill_aa_lut(lut);
     __syncthreads();
     uint4 *queue = queues[threadIdx.x >> 5];
+    uint4 *stage = stages[STAGE ? threadIdx.x >> 5 : 0];
 
     constexpr uint32_t full = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
@@ -104,7 +113,7 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
     const uint4 *__restrict__ slots = reinterpret_cast<const uint4 *>(tv.slots);
     const uint32_t nsig = (uint32_t)tv.num_sigs;  // the neighbour copy is only built for tables below 2^32 buckets
     uint32_t my_probes = 0, my_hits = 0, my_chain = 0;
-    const bool pf = !(tv.tuning & 0x40000u);
+    const bool pf = !(tv.tuning & 0x80000u);
     const uint32_t m35 = tv.m35;
 
     for (uint32_t i = warp0; i < n; i += n_warps) {
@@ -135,9 +144,36 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
                         if (m) carry = __shfl_sync(full, hv, __ffs(m) - 1);
                     }
                 }
+                const uint32_t q0 = t0 + 4u * lane;
+
+                // ---- this lane's hint: its segment's, else the nearest one in front, else the first one of the protein ----
+                uint32_t f[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    f[k] = __shfl_sync(full, hv, (seg0 & 31u) + k);
+                    if (f[k] == kNoHint) f[k] = carry;
+                    else carry = f[k];
+                }
+                const uint32_t q = lane >> 3;
+                const uint32_t mh = q == 0 ? f[0] : q == 1 ? f[1] : q == 2 ? f[2] : f[3];
+                // the chain entries the hint predicts (coalesced) are requested before the keys are even built: their
+                // addresses depend on the position only
+                uint4 cv[4];
+                uint32_t ok = 0;
+                if (mh != kNoHint) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t idx = mh + q0 + j;
+                        if (q0 + j < nwin && idx < tv.n_chain) {
+                            cv[j] = __ldg(tv.chain + idx);
+                            ok |= 1u << j;
+                        }
+                    }
+                    if (pf && t0 + kTile < nwin && mh + q0 + kTile < tv.n_chain) prefetch_l2(tv.chain + (mh + q0 + kTile));
+                }
+
                 const TileKeys tk = tile_keys_from(lut, rw, rx, sh, t0, lane, len, nwin);
                 if (t0 + kTile < nwin) tile_words(wb, nwords, t0 + kTile, lane, rw, rx);
-                const uint32_t q0 = t0 + 4u * lane;
                 const uint32_t act = tk.act;
                 if (pf) {
                     // pull into L2 what the next step (or, from the first step, the next protein of this warp) starts with
@@ -152,18 +188,7 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
 #pragma unroll
                 for (int j = 0; j < 4; j++) h[j] = m35 ? fast_mod35(tk.key[j], nsig, m35) : (uint32_t)fast_mod(tk.key[j], tv.num_sigs, tv.magic);
 
-                // ---- this lane's hint: its segment's, else the nearest one in front, else the nearest one behind ----
-                uint32_t f[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    f[k] = __shfl_sync(full, hv, (seg0 & 31u) + k);
-                    if (f[k] == kNoHint) f[k] = carry;
-                    else carry = f[k];
-                }
-                const uint32_t q = lane >> 3;
-                const uint32_t mh = q == 0 ? f[0] : q == 1 ? f[1] : q == 2 ? f[2] : f[3];
-
-                // ---- one round trip: occupancy words (L2) and the chain entries the hint predicts (coalesced) ----
+                // ---- occupancy words (L2) ----
                 uint32_t bw[4] = {0u, 0u, 0u, 0u};
                 if (tv.occupied) {
 #pragma unroll
@@ -172,24 +197,17 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
                 }
                 HitWords w[4];
                 uint32_t hm = 0;
-                if (mh != kNoHint) {
-                    if (pf && t0 + kTile < nwin && mh + q0 + kTile < tv.n_chain) prefetch_l2(tv.chain + (mh + q0 + kTile));
-                    uint4 cv[4];
-                    uint32_t ok = 0;
+                {
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        const uint32_t idx = mh + q0 + j;
-                        if ((act & (1u << j)) && idx < tv.n_chain) {
-                            cv[j] = __ldg(tv.chain + idx);
-                            ok |= 1u << j;
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        if ((ok & (1u << j)) && packed_match(cv[j], tk.key[j])) {
-                            w[j].y = cv[j].y;
-                            w[j].z = cv[j].z;
-                            w[j].w = cv[j].w;
+                        if ((ok & act & (1u << j)) && packed_match(cv[j], tk.key[j])) {
+                            if (STAGE) {
+                                stage[stage_at(4u * lane + j)] = cv[j];
+                            } else {
+                                w[j].y = cv[j].y;
+                                w[j].z = cv[j].z;
+                                w[j].w = cv[j].w;
+                            }
                             hm |= 1u << j;
                         }
                     }
@@ -214,8 +232,12 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
                         n_left += __popc(b);
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        if (need & (1u << j)) queue[qp[j]] = make_uint4((uint32_t)tk.key[j], (uint32_t)(tk.key[j] >> 32), h[j], bw[j]);
+                    for (int j = 0; j < 4; j++) {
+                        if (need & (1u << j)) {
+                            queue[qp[j]] = make_uint4((uint32_t)tk.key[j], (uint32_t)(tk.key[j] >> 32) | ((4u * lane + j) << 8), h[j], bw[j]);
+                            if (STAGE) stage[stage_at(4u * lane + j)].y = 0x8u;  // "no hit" until the probe says otherwise
+                        }
+                    }
                     __syncwarp();
                     for (uint32_t k = lane; k < n_left; k += 32u) {
                         const uint4 it = queue[k];
@@ -225,14 +247,14 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
                         // sequence goes on: when the same occupancy word says the next slot is taken too, fetch it now
                         if ((hh & 31u) != 31u && hh + 1u < nsig && ((it.w >> ((hh & 31u) + 1u)) & 1u) && tv.occupied) {
                             const uint4 v1 = __ldg(slots + hh + 1u);
-                            if (!(v.x == it.x && (v.y & 0xFu) == it.y) && !(v.y & 0x8u)) {
+                            if (!(v.x == it.x && (v.y & 0xFu) == (it.y & 0xFFu)) && !(v.y & 0x8u)) {
                                 v = v1;
                                 hh++;
                             }
                         }
                         uint32_t found = 0;
                         for (;;) {
-                            if (v.x == it.x && (v.y & 0xFu) == it.y) { found = 1u; break; }
+                            if (v.x == it.x && (v.y & 0xFu) == (it.y & 0xFFu)) { found = 1u; break; }
                             if (v.y & 0x8u) break;
                             hh = (hh + 1u == nsig) ? 0u : hh + 1u;
                             if (hh == it.z) break;  // a table without an empty slot
@@ -242,18 +264,26 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
                             }
                             v = __ldg(slots + hh);
                         }
-                        queue[k] = make_uint4(found, v.y, v.z, v.w);
+                        if (STAGE) {
+                            if (found) stage[stage_at(it.y >> 8)] = v;
+                        } else {
+                            queue[k] = make_uint4(found, v.y, v.z, v.w);
+                        }
                     }
                     __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         if (need & (1u << j)) {
-                            const uint4 r = queue[qp[j]];
-                            if (r.x) {
-                                w[j].y = r.y;
-                                w[j].z = r.z;
-                                w[j].w = r.w;
-                                hm |= 1u << j;
+                            if (STAGE) {
+                                if (!(stage[stage_at(4u * lane + j)].y & 0x8u)) hm |= 1u << j;
+                            } else {
+                                const uint4 r = queue[qp[j]];
+                                if (r.x) {
+                                    w[j].y = r.y;
+                                    w[j].z = r.z;
+                                    w[j].w = r.w;
+                                    hm |= 1u << j;
+                                }
                             }
                         }
                     }
@@ -274,14 +304,26 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     if (hm & (1u << j)) {
+                        HitWords r;
+                        uint64_t key;
+                        if (STAGE) {
+                            const uint4 e = stage[stage_at(4u * lane + j)];
+                            r.y = e.y;
+                            r.z = e.z;
+                            r.w = e.w;
+                            key = (uint64_t)e.x | ((uint64_t)(e.y & 0x7u) << 32);
+                        } else {
+                            r = w[j];
+                            key = tk.key[j];
+                        }
                         HitRec rec;
                         rec.pos = q0 + j;
-                        rec.fI = w[j].w & (kPackedFieldLimit - 1);
-                        rec.wt = __uint_as_float(w[j].z);
-                        rec.oI = (int32_t)(((w[j].y >> 20) & 0xFFFu) | ((w[j].w >> 22) << 12)) - 1;
+                        rec.fI = r.w & (kPackedFieldLimit - 1);
+                        rec.wt = __uint_as_float(r.z);
+                        rec.oI = (int32_t)(((r.y >> 20) & 0xFFFu) | ((r.w >> 22) << 12)) - 1;
                         out[o] = rec;
-                        if (hit_keys) hit_keys[seq_base + o] = tk.key[j];
-                        if (hit_avg) hit_avg[seq_base + o] = (uint16_t)((w[j].y >> 4) & 0xFFFFu);
+                        if (hit_keys) hit_keys[seq_base + o] = key;
+                        if (hit_avg) hit_avg[seq_base + o] = (uint16_t)((r.y >> 4) & 0xFFFFu);
                         o++;
                     }
                 }

@@ -161,8 +161,9 @@ int ckm_has_occupancy_bitmap(const ckm_ctx *ctx);
 int ckm_chain_info(ckm_ctx *ctx, uint64_t info[4]);
 /* A/B switches of the probe kernels (results unaffected): bit0 table loads evict_first, bit1 bitmap loads evict_last,
  * bit2 hit-record stores evict_first, bit5 (32) plain hash probing although the neighbour copy exists, bit7 (128) / bit6 (64)
- * the walking probe_chain_kernel at 3 / 2 blocks per SM instead of hint_kernel + probe_hint_kernel, bits 16-17 block shape
- * of probe_hint_kernel (1 = 4, 2 = 2 blocks per SM), bit18 (0x40000) without its L2 prefetches */
+ * the walking probe_chain_kernel at 3 / 2 blocks per SM instead of hint_kernel + probe_hint_kernel, bits 16-18 variant of
+ * probe_hint_kernel (0 = 128 threads x 7 blocks per SM with the hit payload staged in shared memory, 1 = 256x4 staged,
+ * 2 = 128x8 staged, 3 = 128x6 staged, 4 = 256x3 payload in registers, 5 = 256x3 staged), bit19 (0x80000) without its L2 prefetches */
 void ckm_set_tuning(ckm_ctx *ctx, uint32_t bits);
 
 /* ---- parameters (KmerGuts::set_default_parameters / set_parameters, kguts.cc:236-268) -------------- */
