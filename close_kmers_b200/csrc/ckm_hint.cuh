@@ -114,6 +114,11 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
     const uint32_t nsig = (uint32_t)tv.num_sigs;  // the neighbour copy is only built for tables below 2^32 buckets
     uint32_t my_probes = 0, my_hits = 0, my_chain = 0;
     const bool pf = !(tv.tuning & 0x80000u);
+    // L2 policies: the read-once streams (chain entries, slots) are loaded evict_first, which keeps more of the occupancy bitmap
+    // in L2 (4.41 -> 4.22 ms on C2, profiles/r1/tune_hint_v15_c2.jsonl; tuning bit0 switches it off).  A/B only: bit1
+    // occupancy words evict_last, bit2 hit-record stores evict_first (no effect).
+    const bool t_tab = !(tv.tuning & 1u), t_bm = tv.tuning & 2u, t_st = tv.tuning & 4u;
+    const uint64_t pol_first = policy_evict_first(), pol_last = policy_evict_last();
     const uint32_t m35 = tv.m35;
 
     for (uint32_t i = warp0; i < n; i += n_warps) {
@@ -165,7 +170,7 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
                     for (int j = 0; j < 4; j++) {
                         const uint32_t idx = mh + q0 + j;
                         if (q0 + j < nwin && idx < tv.n_chain) {
-                            cv[j] = __ldg(tv.chain + idx);
+                            cv[j] = t_tab ? ldg_v4_hint(tv.chain + idx, pol_first) : __ldg(tv.chain + idx);
                             ok |= 1u << j;
                         }
                     }
@@ -193,7 +198,7 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
                 if (tv.occupied) {
 #pragma unroll
                     for (int j = 0; j < 4; j++)
-                        if (act & (1u << j)) bw[j] = __ldg(tv.occupied + (h[j] >> 5));
+                        if (act & (1u << j)) bw[j] = t_bm ? ldg_u32_hint(tv.occupied + (h[j] >> 5), pol_last) : __ldg(tv.occupied + (h[j] >> 5));
                 }
                 HitWords w[4];
                 uint32_t hm = 0;
@@ -242,7 +247,7 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
                     for (uint32_t k = lane; k < n_left; k += 32u) {
                         const uint4 it = queue[k];
                         uint32_t hh = it.z;
-                        uint4 v = __ldg(slots + hh);
+                        uint4 v = t_tab ? ldg_v4_hint(slots + hh, pol_first) : __ldg(slots + hh);
                         // a window gets here because its home slot is taken -- nearly always by another k-mer, so the probe
                         // sequence goes on: when the same occupancy word says the next slot is taken too, fetch it now
                         if ((hh & 31u) != 31u && hh + 1u < nsig && ((it.w >> ((hh & 31u) + 1u)) & 1u) && tv.occupied) {
@@ -321,7 +326,8 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
                         rec.fI = r.w & (kPackedFieldLimit - 1);
                         rec.wt = __uint_as_float(r.z);
                         rec.oI = (int32_t)(((r.y >> 20) & 0xFFFu) | ((r.w >> 22) << 12)) - 1;
-                        out[o] = rec;
+                        if (t_st) stg_v4_hint(reinterpret_cast<uint4 *>(out + o), *reinterpret_cast<const uint4 *>(&rec), pol_first);
+                        else out[o] = rec;
                         if (hit_keys) hit_keys[seq_base + o] = key;
                         if (hit_avg) hit_avg[seq_base + o] = (uint16_t)((r.y >> 4) & 0xFFFFu);
                         o++;

@@ -159,7 +159,8 @@ int ckm_has_occupancy_bitmap(const ckm_ctx *ctx);
  * identical with and without it).  info[0] = entries (0 = not built), info[1] = chains, info[2] = build time in
  * microseconds, info[3] = hits of the last batch that were answered from the copy instead of a hash probe. */
 int ckm_chain_info(ckm_ctx *ctx, uint64_t info[4]);
-/* A/B switches of the probe kernels (results unaffected): bit0 table loads evict_first, bit1 bitmap loads evict_last,
+/* A/B switches of the probe kernels (results unaffected): bit0 table loads evict_first (probe_kernel; in probe_hint_kernel
+ * evict_first is the default for chain and slot loads and bit0 switches it off), bit1 bitmap loads evict_last,
  * bit2 hit-record stores evict_first, bit5 (32) plain hash probing although the neighbour copy exists, bit7 (128) / bit6 (64)
  * the walking probe_chain_kernel at 3 / 2 blocks per SM instead of hint_kernel + probe_hint_kernel, bits 16-18 variant of
  * probe_hint_kernel (0 = 128 threads x 7 blocks per SM with the hit payload staged in shared memory, 1 = 256x4 staged,
