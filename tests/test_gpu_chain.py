@@ -100,6 +100,13 @@ def _compare(g, orc, batch, what, prms=(dict(), dict(order_constraint=1, min_hit
         wl.assert_results_equal(got, want, f"{what} chain {prm}")
         assert got["n_probes"] == want["n_probes"] and got["n_hits"] == len(want["hits"])
         from_copy = g.chain_info["hits_from_copy"]
+        # the other builds of probe_hint_kernel (block shape, hit payload in registers or shared memory; ckm_set_tuning
+        # bits 16-18), without the evict_first policy / L2 prefetches, and the walking probe_chain_kernel (bits 7, 6)
+        for tuning in (1 << 16, 2 << 16, 3 << 16, 4 << 16, 5 << 16, 1 | 0x80000, 128, 64):
+            g.set_tuning(tuning)
+            other = g.process_aa_seq_batch(batch.residues, batch.offsets, ALL)
+            wl.assert_results_equal(other, want, f"{what} tuning {tuning:#x} {prm}")
+            assert g.chain_info["hits_from_copy"] > 0 or from_copy == 0
         g.set_tuning(NO_CHAIN)
         plain = g.process_aa_seq_batch(batch.residues, batch.offsets, ALL)
         wl.assert_results_equal(plain, want, f"{what} plain {prm}")

@@ -1,6 +1,9 @@
 """probe_chain_kernel vs probe_kernel on a C2-shaped workload (GPU box): builds the world once, then times K1 per setting.
 python tools/tune_chain.py [n_proteins] [n_sigs] [tuning values ...]
-tuning: 0 = hint_kernel + probe_hint_kernel, 128 = probe_chain_kernel<3 blocks/SM>, 64 = <2 blocks/SM>, 32 = plain hash probing (probe_kernel)"""
+tuning (ckm_set_tuning, include/ckm.h): 0 = hint_kernel + probe_hint_kernel<128 threads, 7 blocks/SM, payload staged in shared
+memory>; n << 16 selects another build of it (1 = 256x4 staged, 2 = 128x8 staged, 3 = 128x6 staged, 4 = 256x3 registers,
+5 = 256x3 staged); 1 = without evict_first on chain/slot loads; 0x80000 = without L2 prefetches; 128 / 64 = the walking
+probe_chain_kernel at 3 / 2 blocks per SM; 32 = plain hash probing (probe_kernel)"""
 import json
 import os
 import sys
