@@ -25,7 +25,7 @@ C.memmove(hp_off.value, batch.offsets.ctypes.data, (batch.n + 1) * 8)
 import torch
 props = torch.cuda.get_device_properties(0)
 print(json.dumps(dict(l2=props.L2_cache_size)), flush=True)
-for chunk_kb, ramp, tail in ((98304, 24, 16), (49152, 12, 8), (32768, 8, 8), (196608, 48, 16), (65536, 16, 16), (24576, 6, 8), (16384, 4, 4), (98304, 48, 16)):
+for chunk_kb, ramp, tail in ((49152, 12, 8), (49152, 24, 8), (49152, 48, 16), (49152, 12, 16), (40960, 20, 10), (32768, 16, 8), (32768, 32, 16), (65536, 32, 16), (24576, 12, 8)):
     os.environ["CKM_PIPELINE_CHUNK_KB"] = str(chunk_kb)
     os.environ["CKM_PIPELINE_RAMP_DIV"] = str(ramp)
     os.environ["CKM_PIPELINE_TAIL_DIV"] = str(tail)
