@@ -216,3 +216,33 @@ def test_chain_copy_is_shared_by_clones_and_skipped_for_raw_slots(checkers):
         raw.close()
         g.close()
         orc.close()
+
+
+def test_chain_probe_long_proteins_reload_hints(checkers):
+    """Proteins longer than 32 hint segments (1024 windows): probe_hint_kernel reloads its hint registers every eight steps;
+    concatenated prototypes also change chain every few hundred windows."""
+    protos, sig, img = wl.small_world(seed=8, n_protos=150, n_sigs=40_000)
+    orc = checkers.Oracle().open_image(img)
+    g = _open(img, synth.function_names(sig.n_functions))
+    try:
+        rng = np.random.default_rng(17)
+        aa = synth.AA
+        seqs = []
+        for n_parts in (4, 5, 9, 17, 40, 3, 130):
+            parts = []
+            for _ in range(n_parts):
+                p = int(rng.integers(0, protos.n))
+                parts.append(aa[protos.codes[int(protos.offsets[p]):int(protos.offsets[p + 1])]])
+            s = np.concatenate(parts).copy()
+            sub = rng.random(len(s)) < 0.04
+            s[sub] = aa[rng.integers(0, 20, int(sub.sum()))]
+            seqs.append(s.tobytes())
+        seqs.append(seqs[2][:1031])  # 1023 windows: exactly one load of hints
+        seqs.append(seqs[3][:1033])  # 1025 windows: the first reload holds a single segment
+        batch = wl.concat_batches(synth.batch_from_strings(seqs), synth.make_proteins(6, protos, 300))
+        assert max(len(x) for x in seqs) > 30_000
+        from_copy, n_hits = _compare(g, orc, batch, "long proteins")
+        assert from_copy > 0.8 * n_hits, (from_copy, n_hits)
+    finally:
+        g.close()
+        orc.close()
