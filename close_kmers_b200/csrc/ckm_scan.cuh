@@ -198,7 +198,44 @@ struct ScanArgs {
 // stored hits are a strict subsequence of the hit list and their indices are kept in stored_idx.
 template <bool GENERAL>
 __global__ void __launch_bounds__(kScanThreads) scan_kernel(ScanArgs a) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    // A thread owns a protein and walks its hit list serially, so a warp lasts as long as its longest list.  The block's
+    // proteins are therefore dealt to its threads in order of hit count (counting sort on n_hits / 4 in shared memory): the
+    // 32 lanes of a warp then finish together.  Which thread takes which protein changes no result.
+    __shared__ uint32_t s_bins[256];
+    __shared__ uint16_t s_order[kScanThreads];
+    {
+        const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
+        const uint32_t nh0 = i0 < a.n ? a.n_hits[i0] : 0u;
+        const uint32_t bin = min(nh0 >> 2, 255u);
+        for (uint32_t t = threadIdx.x; t < 256u; t += blockDim.x) s_bins[t] = 0;
+        __syncthreads();
+        atomicAdd(&s_bins[bin], 1u);
+        __syncthreads();
+        if (threadIdx.x < 32u) {  // exclusive scan of the 256 bins by one warp, 8 bins per lane
+            uint32_t v[8], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                v[k] = s_bins[threadIdx.x * 8 + k];
+                sum += v[k];
+            }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (threadIdx.x >= (uint32_t)d) incl += t;
+            }
+            uint32_t ex = incl - sum;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                s_bins[threadIdx.x * 8 + k] = ex;
+                ex += v[k];
+            }
+        }
+        __syncthreads();
+        s_order[atomicAdd(&s_bins[bin], 1u)] = (uint16_t)threadIdx.x;
+        __syncthreads();
+    }
+    const uint32_t i = blockIdx.x * blockDim.x + s_order[threadIdx.x];
     if (i >= a.n) return;
     const uint64_t base = a.offsets[i];
     const HitRec *H = a.hits + base;
