@@ -258,7 +258,7 @@ static int install_table(ckm_ctx *c, DevBuf raw, uint64_t n) {
     c->n_chain = 0;
     const char *ch = getenv("CKM_CHAIN");  // "0" disables, "1" forces
     const bool want_chain = ch ? ch[0] == '1' : table_bytes > (size_t)c->l2_bytes;
-    if (want_chain && c->slot_bytes == kPackedSlotBytes && n < 0xFFFFFFF0ull) {
+    if (want_chain && c->slot_bytes == kPackedSlotBytes && n > 0 && n < 0xFFFFFFF0ull) {
         // an optimisation only: without the memory for it (~32 B per bucket while building) the table works as before
         if (build_chain(c)) {
             if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess)
