@@ -246,3 +246,25 @@ def test_chain_probe_long_proteins_reload_hints(checkers):
     finally:
         g.close()
         orc.close()
+
+
+def test_chain_forced_on_empty_and_tiny_tables(checkers):
+    """CKM_CHAIN=1 on a table without a k-mer (no copy is built) and on one with fewer than 64 buckets (fast_mod35 does
+    not apply: the kernels fall back to the 64-bit reduction)."""
+    protos, sig, _ = wl.small_world(seed=5, n_protos=20, n_sigs=2_000)
+    batch = synth.make_proteins(3, protos, 200)
+    z64, z32, z16, zf = np.zeros(0, np.uint64), np.zeros(0, np.int32), np.zeros(0, np.uint16), np.zeros(0, np.float32)
+    for nb, k in ((3769, 0), (61, 20)):
+        img = api.build_image(nb, sig.keys[:k] if k else z64, sig.fI[:k] if k else z32, sig.oI[:k] if k else z32,
+                              sig.avg[:k] if k else z16, sig.wt[:k] if k else zf)
+        orc = checkers.Oracle().open_image(img)
+        g = _open(img, synth.function_names(sig.n_functions))
+        try:
+            assert g.chain_info["entries"] == k
+            want = orc.call_batch(batch, ALL)
+            got = g.process_aa_seq_batch(batch.residues, batch.offsets, ALL)
+            wl.assert_results_equal(got, want, f"{k} k-mers in {nb} buckets")
+            assert got["n_probes"] == want["n_probes"]
+        finally:
+            g.close()
+            orc.close()
