@@ -761,7 +761,7 @@ static int launch_range(ckm_ctx *c, cudaStream_t stream, const uint8_t *d_res, c
             else if (group == 8u) probe_group_kernel<false, 8><<<gb, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
             else probe_group_kernel<false, 16><<<gb, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
         } else if (c->slot_bytes == kPackedSlotBytes && c->n_chain && !(c->tuning & 32u)) {
-            if (!(c->tuning & (64u | 128u))) {  // hints first (one sample window in 32), then the probe proper (ckm_hint.cuh)
+            if (!(c->tuning & (64u | 128u))) {  // hints first (one sample window in 64), then the probe proper (ckm_hint.cuh)
                 const uint64_t per_block = 256 / kHintLanes;
                 const unsigned hb = (unsigned)std::min<uint64_t>(((uint64_t)cnt + per_block - 1) / per_block, (uint64_t)c->sm_count * 64);
                 hint_kernel<<<hb, 256, 0, stream>>>(tv, d_res, d_off + i0, cnt, i0, (uint32_t *)c->hints.p);

@@ -7,12 +7,12 @@
 //
 // Here the dependency is taken out of the walk:
 //
-//   hint_kernel        one thread per *sample* window (one window in 32): plain lookup_hash_entry (kguts.cc:585-602); a hit
+//   hint_kernel        one thread per *sample* window (one window in 64): plain lookup_hash_entry (kguts.cc:585-602); a hit
 //                      stores hint = cpos[slot] - position, "where window 0 of this protein would sit in chain[] if the
 //                      protein followed this chain".  All samples of a batch are independent: two or three round trips at
-//                      full occupancy, ~3 % of the probes.
+//                      full occupancy, 1.6 % of the probes.
 //   probe_hint_kernel  probe_kernel (ckm_probe.cuh) with one extra source: every window first compares its key with
-//                      chain[hint + position], the hint being that of its own 32-window segment or else of the nearest
+//                      chain[hint + position], the hint being that of its own 64-window segment or else of the nearest
 //                      segment that has one.  Those reads are issued together with the occupancy words, are coalesced (the
 //                      128 windows of a step read 2 KB = 16 lines of chain[] when they share a hint) and answer ~98 % of the
 //                      hits of a protein that is a homologue of a signature source.  What is left -- windows whose home slot
@@ -33,13 +33,17 @@
 
 namespace ckm {
 
-constexpr uint32_t kHintShift = 5;                 // one sample per 32 windows
+#ifndef CKM_HINT_SHIFT
+#define CKM_HINT_SHIFT 6  // measured on C2: one sample per 32 / 64 / 128 windows -> K1 4.23 / 4.12 / 4.24 ms (tune_hint_v18_c2_*)
+#endif
+constexpr uint32_t kHintShift = CKM_HINT_SHIFT;    // one sample per 64 windows
+constexpr int kSegsPerTile = 128 >> kHintShift;    // hint segments per 128-window step
 constexpr uint32_t kHintSeg = 1u << kHintShift;
 constexpr uint32_t kNoHint = 0xFFFFFFFFu;
 constexpr uint32_t kHintLanes = 16;                // lanes per protein in hint_kernel
 
 // hints of protein i (global index gi) live at hints[(offsets[i] >> kHintShift) + gi ...): a protein of length L has at most
-// (L-1)/32 + 1 segments and consecutive regions start at least that far apart, so regions never overlap.
+// (L-1)/64 + 1 segments and consecutive regions start at least that far apart, so regions never overlap.
 __device__ __forceinline__ uint64_t hint_region(uint64_t seq_base, uint32_t gi) { return (seq_base >> kHintShift) + gi; }
 
 __global__ void __launch_bounds__(256)
@@ -141,13 +145,13 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
             const uint32_t nwords = (len + s + 3u) >> 2;
             const uint32_t sh = 8u * s;
             HitRec *out = hits + seq_base;
-            uint32_t hv = kNoHint;     // hint of segment (32 * round + lane), reloaded every 8 steps
+            uint32_t hv = kNoHint;     // hint of segment (32 * round + lane), reloaded every 32 segments
             uint32_t carry = kNoHint;  // last hint seen in front of the current segment (the first one there is, to begin with)
             uint32_t rw, rx;           // residue words of the step, fetched one step ahead
             tile_words(wb, nwords, 0, lane, rw, rx);
 
             for (uint32_t t0 = 0; t0 < nwin; t0 += kTile) {
-                const uint32_t seg0 = t0 >> kHintShift;  // first of the four segments of this step
+                const uint32_t seg0 = t0 >> kHintShift;  // first of the kSegsPerTile segments of this step
                 if ((seg0 & 31u) == 0u) {
                     hv = (seg0 + lane < nseg) ? __ldg(hp + seg0 + lane) : kNoHint;
                     if (carry == kNoHint) {
@@ -158,15 +162,14 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
                 const uint32_t q0 = t0 + 4u * lane;
 
                 // ---- this lane's hint: its segment's, else the nearest one in front, else the first one of the protein ----
-                uint32_t f[4];
+                uint32_t mh = kNoHint;
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    f[k] = __shfl_sync(full, hv, (seg0 & 31u) + k);
-                    if (f[k] == kNoHint) f[k] = carry;
-                    else carry = f[k];
+                for (int k = 0; k < kSegsPerTile; k++) {
+                    uint32_t fk = __shfl_sync(full, hv, (seg0 & 31u) + k);
+                    if (fk == kNoHint) fk = carry;
+                    else carry = fk;
+                    if ((int)(lane * kSegsPerTile >> 5) == k) mh = fk;
                 }
-                const uint32_t q = lane >> 3;
-                const uint32_t mh = q == 0 ? f[0] : q == 1 ? f[1] : q == 2 ? f[2] : f[3];
                 // the chain entries the hint predicts (coalesced) are requested before the keys are even built: their
                 // addresses depend on the position only
                 uint4 cv[4];

@@ -219,8 +219,8 @@ def test_chain_copy_is_shared_by_clones_and_skipped_for_raw_slots(checkers):
 
 
 def test_chain_probe_long_proteins_reload_hints(checkers):
-    """Proteins longer than 32 hint segments (1024 windows): probe_hint_kernel reloads its hint registers every eight steps;
-    concatenated prototypes also change chain every few hundred windows."""
+    """Proteins longer than 32 hint segments (2048 windows at one sample per 64): probe_hint_kernel reloads its hint
+    registers every 32 segments; concatenated prototypes also change chain every few hundred windows."""
     protos, sig, img = wl.small_world(seed=8, n_protos=150, n_sigs=40_000)
     orc = checkers.Oracle().open_image(img)
     g = _open(img, synth.function_names(sig.n_functions))
@@ -237,8 +237,8 @@ def test_chain_probe_long_proteins_reload_hints(checkers):
             sub = rng.random(len(s)) < 0.04
             s[sub] = aa[rng.integers(0, 20, int(sub.sum()))]
             seqs.append(s.tobytes())
-        seqs.append(seqs[2][:1031])  # 1023 windows: exactly one load of hints
-        seqs.append(seqs[3][:1033])  # 1025 windows: the first reload holds a single segment
+        for cut in (1031, 1033, 2055, 2057, 4103, 4105):  # one window short of / past a reload for 32-, 64- and 128-window segments
+            seqs.append(seqs[3][:cut])
         batch = wl.concat_batches(synth.batch_from_strings(seqs), synth.make_proteins(6, protos, 300))
         assert max(len(x) for x in seqs) > 30_000
         from_copy, n_hits = _compare(g, orc, batch, "long proteins")
