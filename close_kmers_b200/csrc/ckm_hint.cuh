@@ -40,7 +40,7 @@ constexpr uint32_t kHintShift = CKM_HINT_SHIFT;    // one sample per 64 windows
 constexpr int kSegsPerTile = 128 >> kHintShift;    // hint segments per 128-window step
 constexpr uint32_t kHintSeg = 1u << kHintShift;
 constexpr uint32_t kNoHint = 0xFFFFFFFFu;
-constexpr uint32_t kHintLanes = 16;                // lanes per protein in hint_kernel
+constexpr uint32_t kHintLanes = 8;                 // lanes per protein in hint_kernel (a 300-residue protein has 5 samples)
 
 // hints of protein i (global index gi) live at hints[(offsets[i] >> kHintShift) + gi ...): a protein of length L has at most
 // (L-1)/64 + 1 segments and consecutive regions start at least that far apart, so regions never overlap.
