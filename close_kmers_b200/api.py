@@ -15,6 +15,7 @@ import numpy as np
 from . import build as _build
 
 WANT_CALLS, WANT_HITS, WANT_OTU, WANT_BEST = 1, 2, 4, 8
+TUNE_PLAIN_PROBE, TUNE_UNFUSED, TUNE_NO_FALLBACK = 32, 0x100000, 0x200000  # ckm_set_tuning (include/ckm.h)
 BEST_HAS_CALLS, BEST_AMBIG = 1, 2
 MAX_ENCODED = 20**8
 
@@ -89,6 +90,7 @@ def lib() -> C.CDLL:
     L.ckm_l2_fetch_granularity.argtypes = [C.c_void_p]
     L.ckm_has_occupancy_bitmap.argtypes = [C.c_void_p]
     L.ckm_set_tuning.argtypes = [C.c_void_p, C.c_uint32]
+    L.ckm_last_batch_was_fused.argtypes = [C.c_void_p]
     L.ckm_chain_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.ckm_set_default_params.argtypes = [C.c_void_p]
     L.ckm_set_params.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -151,6 +153,11 @@ def lib() -> C.CDLL:
     L.ckm_host_free.argtypes = [C.c_void_p]
     _lib = L
     return L
+
+
+def experiments_enabled() -> bool:
+    """True when libckm.so was built with -DCKM_EXPERIMENTS (A/B kernels and cache-policy bits of ckm_set_tuning)."""
+    return bool(lib().ckm_experiments_enabled())
 
 
 def _check(rc: int) -> None:
@@ -479,6 +486,10 @@ class KmerGuts:
         r, ms = C.c_double(), C.c_double()
         _check(lib().ckm_calibrate_gather(self._h, nbytes, unroll, rounds, blocks_per_sm, C.byref(r), C.byref(ms)))
         return r.value, ms.value
+
+    @property
+    def last_batch_was_fused(self) -> bool:
+        return bool(lib().ckm_last_batch_was_fused(self._h))
 
     def set_tuning(self, bits: int):
         lib().ckm_set_tuning(self._h, bits)

@@ -27,6 +27,8 @@
 #include "ckm_chain.cuh"
 #include "ckm_hint.cuh"
 #include "ckm_scan.cuh"
+#include "ckm_warp_scan.cuh"
+#include "ckm_pc.cuh"
 #include "ckm_util.cuh"
 
 using namespace ckm;
@@ -377,6 +379,21 @@ static int ctx_create(int device, ckm_ctx **out) {
     if (const char *pm = getenv("CKM_PIPELINE_MIN_KB")) c->pipeline_min_bytes = (uint64_t)atol(pm) << 10;
     const char *fr = getenv("CKM_FORCE_RAW_SLOTS");
     c->force_raw = fr && fr[0] == '1';
+    if (const char *pg = getenv("CKM_PROBE_GROUP")) {
+        const int g = atoi(pg);
+        if (g == 4 || g == 8 || g == 16 || g == 32) c->probe_group_override = (uint32_t)g;
+    }
+    c->staged_upload = !getenv("CKM_NO_STAGED_UPLOAD");
+    if (const char *ps = getenv("CKM_PC_SHAPE")) c->pc_shape = atoi(ps);
+    if (const char *co = getenv("CKM_CARVEOUT"))  // experiment: shared-memory carve-out (percent) for the unfused hinted K1
+        cudaFuncSetAttribute(probe_hint_kernel<128, 7, true>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co));
+    if (cudaFuncSetAttribute(probe_pc_kernel<27, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pc_smem_bytes(27)) != cudaSuccess ||
+        cudaFuncSetAttribute(probe_pc_kernel<13, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pc_smem_bytes(13)) != cudaSuccess) {
+        const int rc = ckm_fail(CKM_ECUDA, "cudaFuncSetAttribute(probe_pc_kernel): %s", cudaGetErrorString(cudaGetLastError()));
+        cudaStreamDestroy(c->stream);
+        delete c;
+        return rc;
+    }
     if (check_cuda(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
         delete c;
         return CKM_ECUDA;
@@ -493,6 +510,9 @@ extern "C" int ckm_clone(ckm_ctx *parent, ckm_ctx **out) {
     c->slot_bytes = parent->slot_bytes;
     c->force_raw = parent->force_raw;
     c->tuning = parent->tuning;
+    c->probe_group_override = parent->probe_group_override;
+    c->staged_upload = parent->staged_upload;
+    c->pc_shape = parent->pc_shape;
     c->functions = parent->functions;
     c->otu_names = parent->otu_names;
     c->prm = parent->prm;
@@ -550,6 +570,14 @@ extern "C" uint64_t ckm_num_sigs(const ckm_ctx *c) { return c->num_sigs; }
 extern "C" int ckm_table_slot_bytes(const ckm_ctx *c) { return c->slot_bytes; }
 extern "C" int ckm_l2_fetch_granularity(const ckm_ctx *c) { return c->l2_fetch; }
 extern "C" void ckm_set_tuning(ckm_ctx *c, uint32_t bits) { c->tuning = bits; }
+extern "C" int ckm_last_batch_was_fused(const ckm_ctx *c) { return c->last_fused ? 1 : 0; }
+extern "C" int ckm_experiments_enabled(void) {
+#ifdef CKM_EXPERIMENTS
+    return 1;
+#else
+    return 0;
+#endif
+}
 extern "C" int ckm_has_occupancy_bitmap(const ckm_ctx *c) { return c->occupied.p != nullptr; }
 extern "C" int ckm_chain_info(ckm_ctx *c, uint64_t info[4]) {
     if (!c || !info) return ckm_fail(CKM_EINVAL, "NULL argument");
@@ -675,10 +703,19 @@ static int prefix_sum(ckm_ctx *c, const uint32_t *d_in, uint64_t n, uint64_t *d_
     return 0;
 }
 
+constexpr uint32_t kWorkSlots = 64;  // work counters of probe_pc_kernel launches in flight (two streams, a handful each)
+
 struct RunPlan {
     bool want_scan, general, want_keys, want_avg;
-    uint32_t probe_group;  // lanes per sequence in K1: 32 (probe_kernel) or 8 / 16 (probe_group_kernel, short sequences)
+    bool fused;            // the scoring scan runs inside K1 (ckm_warp_scan.cuh): no hit records, no scan_kernel
+    uint32_t probe_group;  // lanes per sequence in K1: 32 (probe_kernel) or 4 / 8 / 16 (probe_group_kernel, short sequences)
 };
+
+// the fused K1 serves requests for calls and / or the best call of proteins that cannot saturate the hit window
+static bool plan_fused(const ckm_ctx *c, const RunPlan &plan, uint32_t flags) {
+    return plan.want_scan && !plan.general && !(flags & (CKM_WANT_HITS | CKM_WANT_OTU)) && plan.probe_group >= 32u &&
+           c->slot_bytes == kPackedSlotBytes && c->num_sigs < 0xFFFFFFF0ull && !(c->tuning & CKM_TUNE_UNFUSED);
+}
 
 // size the per-batch regions (indexed by residue offset / sequence index, so chunked launches can share them)
 static int prepare_regions(ckm_ctx *c, uint32_t n, uint64_t total, uint32_t max_len, uint32_t flags, RunPlan *plan) {
@@ -690,17 +727,15 @@ static int prepare_regions(ckm_ctx *c, uint32_t n, uint64_t total, uint32_t max_
         // by mean length: a group step covers 4*G start positions
         const uint64_t mean = n ? total / n : 0;
         plan->probe_group = n < 64 ? 32u : mean <= 24 ? 4u : mean <= 48 ? 8u : mean <= 96 ? 16u : 32u;
-        if (const char *pg = getenv("CKM_PROBE_GROUP")) {
-            const int g = atoi(pg);
-            if (g == 4 || g == 8 || g == 16 || g == 32) plan->probe_group = (uint32_t)g;
-        }
+        if (c->probe_group_override) plan->probe_group = c->probe_group_override;
     }
     plan->general = plan->want_scan && (c->prm.order_constraint != 0 || max_len == 0 || max_len > kHitCap + CKM_KMER_SIZE);
     plan->want_keys = flags & CKM_WANT_HITS;
     plan->want_avg = (flags & CKM_WANT_HITS) || (plan->want_scan && c->prm.order_constraint != 0);
+    plan->fused = plan_fused(c, *plan, flags);
     const uint64_t ncall_slots = total / (uint64_t)std::max(1, c->prm.min_hits) + n + 1;
     RC(c->totals.ensure(64));
-    RC(c->hits.ensure((total + 1) * sizeof(HitRec)));
+    if (!plan->fused) RC(c->hits.ensure((total + 1) * sizeof(HitRec)));
     RC(c->n_hits.ensure(((size_t)n + 1) * 4));
     if (c->n_chain && plan->probe_group >= 32u) RC(c->hints.ensure(((total >> kHintShift) + n + 2) * 4));
     if (plan->want_keys) RC(c->hit_keys.ensure((total + 1) * 8));
@@ -721,10 +756,7 @@ static int prepare_regions(ckm_ctx *c, uint32_t n, uint64_t total, uint32_t max_
     return 0;
 }
 
-// K1 (+ K2) for sequences [i0, i0+cnt) of the batch on `stream`
-static int launch_range(ckm_ctx *c, cudaStream_t stream, const uint8_t *d_res, const uint64_t *d_off, uint32_t i0, uint32_t cnt,
-                        uint32_t flags, const RunPlan &plan, ckm_ctx::ProfEv *pe) {
-    if (cnt == 0) return 0;
+static TableView table_view(const ckm_ctx *c) {
     TableView tv;
     tv.slots = c->table.p;
     tv.num_sigs = c->num_sigs;
@@ -735,70 +767,122 @@ static int launch_range(ckm_ctx *c, cudaStream_t stream, const uint8_t *d_res, c
     tv.cpos = (const uint32_t *)c->cpos.p;
     tv.n_chain = c->n_chain;
     tv.m35 = magic35(c->num_sigs);
+    return tv;
+}
+
+// does K1 go through the neighbour copy (hint_kernel + probe_hint_kernel) for this ctx at present?
+static bool use_neighbour_copy(const ckm_ctx *c) {
+    return c->slot_bytes == kPackedSlotBytes && c->n_chain && !(c->tuning & CKM_TUNE_PLAIN_PROBE) && !c->copy_suspended;
+}
+
+// K1 (+ K2) for sequences [i0, i0+cnt) of the batch on `stream`
+static int launch_range(ckm_ctx *c, cudaStream_t stream, const uint8_t *d_res, const uint64_t *d_off, uint32_t i0, uint32_t cnt,
+                        uint32_t flags, const RunPlan &plan, ckm_ctx::ProfEv *pe) {
+    if (cnt == 0) return 0;
+    c->last_fused = plan.fused;
+    const TableView tv = table_view(c);
+    const bool packed = c->slot_bytes == kPackedSlotBytes;
+    FusedArgs fa;
+    memset(&fa, 0, sizeof fa);
+    if (plan.fused) {
+        fa.calls = (ckm_call_t *)c->calls.p;
+        fa.calls_work = (flags & CKM_WANT_BEST) ? (ckm_call_t *)c->calls_work.p : nullptr;
+        fa.n_calls = (uint32_t *)c->n_calls.p + i0;
+        fa.best = (flags & CKM_WANT_BEST) ? (ckm_best_t *)c->best.p + i0 : nullptr;
+        fa.prm = c->prm;
+        fa.call_magic = call_region_magic(c->prm.min_hits);
+    }
     {
         const uint32_t warps_per_block = kProbeThreads / 32;
         uint64_t blocks = ((uint64_t)cnt + warps_per_block - 1) / warps_per_block;
-        const uint32_t bps = (c->tuning >> 8) & 0xFu;  // blocks per SM override (0 = as many as fit)
         // 64 blocks per SM in the grid (3 are resident at 80 registers): a finer grid than the residency evens out the
         // tail between long and short proteins (measured: 7.5 -> 7.1 ms on C2, profiles/r1/tune3.jsonl)
-        const uint32_t gshift = (c->tuning >> 12) & 0xFu;
-        blocks = std::min<uint64_t>(blocks, ((uint64_t)c->sm_count * (bps ? bps : 8)) << (gshift ? gshift - 1 : 3));
+        uint32_t bps = 8, gshift = 3;
+#ifdef CKM_EXPERIMENTS
+        if ((c->tuning >> 8) & 0xFu) bps = (c->tuning >> 8) & 0xFu;
+        if ((c->tuning >> 12) & 0xFu) gshift = ((c->tuning >> 12) & 0xFu) - 1;
+#endif
+        blocks = std::min<uint64_t>(blocks, ((uint64_t)c->sm_count * bps) << gshift);
+        HitRec *hp = (HitRec *)c->hits.p;
         uint64_t *keys = plan.want_keys ? (uint64_t *)c->hit_keys.p : nullptr;
         uint16_t *avg = plan.want_avg ? (uint16_t *)c->hit_avg.p : nullptr;
-        // short sequences (fastq fragments, peptides): a group of 8 or 16 lanes per sequence instead of a warp
+        uint32_t *nh = (uint32_t *)c->n_hits.p + i0;
+        unsigned long long *tot = (unsigned long long *)c->totals.p;
+        // short sequences (fastq fragments, peptides): a group of 4, 8 or 16 lanes per sequence instead of a warp
         const uint32_t group = plan.probe_group;
         if (group < 32u) {
             const uint32_t per_block = warps_per_block * (32u / group);
             const unsigned gb = (unsigned)std::min<uint64_t>(((uint64_t)cnt + per_block - 1) / per_block, (uint64_t)c->sm_count * 64);
-            HitRec *hp = (HitRec *)c->hits.p;
-            uint32_t *nh = (uint32_t *)c->n_hits.p + i0;
-            unsigned long long *tot = (unsigned long long *)c->totals.p;
-            const bool packed = c->slot_bytes == kPackedSlotBytes;
             if (packed && group == 4u) probe_group_kernel<true, 4><<<gb, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
             else if (group == 4u) probe_group_kernel<false, 4><<<gb, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
             else if (packed && group == 8u) probe_group_kernel<true, 8><<<gb, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
             else if (packed) probe_group_kernel<true, 16><<<gb, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
             else if (group == 8u) probe_group_kernel<false, 8><<<gb, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
             else probe_group_kernel<false, 16><<<gb, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
-        } else if (c->slot_bytes == kPackedSlotBytes && c->n_chain && !(c->tuning & 32u)) {
-            if (!(c->tuning & (64u | 128u))) {  // hints first (one sample window in 64), then the probe proper (ckm_hint.cuh)
+        } else if (plan.fused) {
+            // probing warps + one scan warp per block (ckm_pc.cuh); through the neighbour copy when there is one
+            const uint32_t *hints = nullptr;
+            if (use_neighbour_copy(c)) {
                 const uint64_t per_block = 256 / kHintLanes;
                 const unsigned hb = (unsigned)std::min<uint64_t>(((uint64_t)cnt + per_block - 1) / per_block, (uint64_t)c->sm_count * 64);
                 hint_kernel<<<hb, 256, 0, stream>>>(tv, d_res, d_off + i0, cnt, i0, (uint32_t *)c->hints.p);
                 c->launches++;
-                const uint32_t variant = (c->tuning >> 16) & 7u;  // A/B: block shape, blocks per SM, hit payload staged in shared memory or registers
+                hints = (const uint32_t *)c->hints.p;
+            }
+            RC(c->work.ensure(kWorkSlots * 8));
+            unsigned long long *work = (unsigned long long *)c->work.p + (c->pc_seq++ % kWorkSlots);
+            CU(cudaMemsetAsync(work, 0, 8, stream));
+            if (c->pc_shape == 1) {
+                constexpr int P = 13;
+                const unsigned gb = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c->sm_count * 2, ((uint64_t)cnt + P * kPcChunk - 1) / (P * kPcChunk)));
+                probe_pc_kernel<P, 2><<<gb, (P + 1) * 32, pc_smem_bytes(P), stream>>>(tv, d_res, d_off + i0, cnt, i0, hints, nh, tot, fa, work);
+            } else {
+                constexpr int P = 27;
+                const unsigned gb = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c->sm_count, ((uint64_t)cnt + P * kPcChunk - 1) / (P * kPcChunk)));
+                probe_pc_kernel<P, 1><<<gb, (P + 1) * 32, pc_smem_bytes(P), stream>>>(tv, d_res, d_off + i0, cnt, i0, hints, nh, tot, fa, work);
+            }
+            if (fa.best) {  // find_best_call of the proteins with several calls
+                c->launches++;
+                best_fixup_kernel<<<(cnt + 255) / 256, 256, 0, stream>>>(d_off + i0, cnt, i0, fa);
+            }
+        } else if (use_neighbour_copy(c)) {
+            bool done = false;
+#ifdef CKM_EXPERIMENTS
+            if (c->tuning & (64u | 128u)) {  // the walking probe_chain_kernel at 2 / 3 blocks per SM
+                if (c->tuning & 64u) probe_chain_kernel<2><<<(unsigned)blocks, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
+                else probe_chain_kernel<3><<<(unsigned)blocks, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
+                done = true;
+            }
+#endif
+            if (!done) {  // hints first (one sample window in 64), then the probe proper (ckm_hint.cuh)
+                const uint64_t per_block = 256 / kHintLanes;
+                const unsigned hb = (unsigned)std::min<uint64_t>(((uint64_t)cnt + per_block - 1) / per_block, (uint64_t)c->sm_count * 64);
+                hint_kernel<<<hb, 256, 0, stream>>>(tv, d_res, d_off + i0, cnt, i0, (uint32_t *)c->hints.p);
+                c->launches++;
 #define CKM_HINT_LAUNCH(T, B, S)                                                                                                      \
     probe_hint_kernel<T, B, S><<<(unsigned)std::min<uint64_t>(((uint64_t)cnt + T / 32 - 1) / (T / 32), blocks * (kProbeThreads / T)), T, 0, \
-                              stream>>>(tv, d_res, d_off + i0, cnt, i0, (const uint32_t *)c->hints.p, (HitRec *)c->hits.p, keys, avg,  \
-                                        (uint32_t *)c->n_hits.p + i0, (unsigned long long *)c->totals.p)
+                              stream>>>(tv, d_res, d_off + i0, cnt, i0, (const uint32_t *)c->hints.p, hp, keys, avg, nh, tot)
+#ifdef CKM_EXPERIMENTS
+                const uint32_t variant = (c->tuning >> 16) & 7u;  // A/B: block shape, blocks per SM, hit payload staged or in registers
                 if (variant == 1u) CKM_HINT_LAUNCH(256, 4, true);
                 else if (variant == 2u) CKM_HINT_LAUNCH(128, 8, true);
                 else if (variant == 3u) CKM_HINT_LAUNCH(128, 6, true);
                 else if (variant == 4u) CKM_HINT_LAUNCH(256, 3, false);
                 else if (variant == 5u) CKM_HINT_LAUNCH(256, 3, true);
-                else CKM_HINT_LAUNCH(128, 7, true);  // 72 registers, 28 warps per SM (profiles/r1/tune_hint_v13_1M.jsonl)
+                else
+#endif
+                CKM_HINT_LAUNCH(128, 7, true);  // 72 registers, 28 warps per SM (profiles/r1/tune_hint_v13_1M.jsonl)
 #undef CKM_HINT_LAUNCH
-            } else if (c->tuning & 64u)
-                probe_chain_kernel<2><<<(unsigned)blocks, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, (HitRec *)c->hits.p, keys, avg,
-                                                                                      (uint32_t *)c->n_hits.p + i0,
-                                                                                      (unsigned long long *)c->totals.p);
-            else
-                probe_chain_kernel<3><<<(unsigned)blocks, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, (HitRec *)c->hits.p, keys, avg,
-                                                                                      (uint32_t *)c->n_hits.p + i0,
-                                                                                      (unsigned long long *)c->totals.p);
+            }
+        } else if (packed) {
+            probe_kernel<true><<<(unsigned)blocks, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
+        } else {
+            probe_kernel<false><<<(unsigned)blocks, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, hp, keys, avg, nh, tot);
         }
-        else if (c->slot_bytes == kPackedSlotBytes)
-            probe_kernel<true><<<(unsigned)blocks, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, (HitRec *)c->hits.p, keys, avg,
-                                                                               (uint32_t *)c->n_hits.p + i0,
-                                                                               (unsigned long long *)c->totals.p);
-        else
-            probe_kernel<false><<<(unsigned)blocks, kProbeThreads, 0, stream>>>(tv, d_res, d_off + i0, cnt, (HitRec *)c->hits.p, keys, avg,
-                                                                                (uint32_t *)c->n_hits.p + i0,
-                                                                                (unsigned long long *)c->totals.p);
         c->launches++;
     }
     if (pe) CU(cudaEventRecord(pe->e1, stream));
-    if (plan.want_scan) {
+    if (plan.want_scan && !plan.fused) {
         ScanArgs a;
         a.offsets = d_off + i0;
         a.hits = (const HitRec *)c->hits.p;
@@ -895,8 +979,13 @@ extern "C" int ckm_device_results(ckm_ctx *c, ckm_device_out_t *out) {
 extern "C" int ckm_read_totals(ckm_ctx *c, uint64_t totals[3]) {
     if (!c || !totals) return ckm_fail(CKM_EINVAL, "NULL argument");
     if (!c->totals.p) return ckm_fail(CKM_ESTATE, "no batch has been run on this ctx");
-    CU(cudaMemcpyAsync(totals, c->totals.p, 24, cudaMemcpyDeviceToHost, c->stream));
+    uint64_t t[8];
+    CU(cudaMemcpyAsync(t, c->totals.p, 64, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    if (t[7]) return ckm_fail(CKM_ECUDA, "probe_pc_kernel: a hand-off between probing and scan warps timed out");
+    totals[0] = t[0];
+    totals[1] = t[1];
+    totals[2] = t[2];
     return 0;
 }
 
@@ -968,7 +1057,7 @@ static int upload_batch(ckm_ctx *c, const char *residues, const uint64_t *offset
     const uint64_t total = offsets[n] - offsets[0];
     RC(c->in_res.ensure(total + 32));
     RC(c->in_off.ensure(((size_t)n + 1) * 8));
-    if (total >= (32u << 20) && !getenv("CKM_NO_STAGED_UPLOAD") && is_pageable(residues + offsets[0]))
+    if (total >= (32u << 20) && c->staged_upload && is_pageable(residues + offsets[0]))
         RC(staged_upload(c, c->in_res.p, residues + offsets[0], total));
     else if (total)
         CU(cudaMemcpyAsync(c->in_res.p, residues + offsets[0], total, cudaMemcpyHostToDevice, c->stream));
@@ -1049,11 +1138,17 @@ static int call_batch_pipelined(ckm_ctx *c, const char *residues, const uint64_t
         const uint64_t bytes = offsets[i1] - base0 - start;
         RunPlan cp = plan;
         cp.general = max_len > kHitCap + CKM_KMER_SIZE || c->prm.order_constraint != 0;
+        cp.fused = plan_fused(c, cp, CKM_WANT_BEST);
         if (cp.general) {
             if (c->stored_idx.cap < (total + 1) * 4) {  // first general chunk: nothing in flight uses this buffer yet
                 CU(cudaStreamSynchronize(c->stream));
                 CU(cudaStreamSynchronize(c->stream2));
                 RC(c->stored_idx.ensure((total + 1) * 4));
+            }
+            if (c->hits.cap < (total + 1) * sizeof(HitRec)) {  // the fused chunks before this one left no hit regions
+                CU(cudaStreamSynchronize(c->stream));
+                CU(cudaStreamSynchronize(c->stream2));
+                RC(c->hits.ensure((total + 1) * sizeof(HitRec)));
             }
             cp.want_avg = c->prm.order_constraint != 0;
             if (cp.want_avg && c->hit_avg.cap < (total + 1) * 2) {
@@ -1077,9 +1172,10 @@ static int call_batch_pipelined(ckm_ctx *c, const char *residues, const uint64_t
     CU(cudaEventRecord(c->ev_done2, c->stream2));
     CU(cudaStreamWaitEvent(c->stream, c->ev_done2, 0));
     uint64_t *ht = (uint64_t *)c->h_totals.p;
-    CU(cudaMemcpyAsync(ht, c->totals.p, 24, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(ht, c->totals.p, 64, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
+    if (ht[7]) return ckm_fail(CKM_ECUDA, "probe_pc_kernel: a hand-off between probing and scan warps timed out");
     out->n_probes = ht[0];
     out->n_hits = ht[1];
     out->best = (const ckm_best_t *)c->h_best.p;
@@ -1101,8 +1197,9 @@ extern "C" int ckm_call_batch(ckm_ctx *c, const char *residues, const uint64_t *
     // totals decide the size of the compacted outputs
     RC(c->h_totals.ensure(64));
     uint64_t *ht = (uint64_t *)c->h_totals.p;
-    CU(cudaMemcpyAsync(ht, c->totals.p, 24, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(ht, c->totals.p, 64, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    if (ht[7]) return ckm_fail(CKM_ECUDA, "probe_pc_kernel: a hand-off between probing and scan warps timed out");
     out->n_probes = ht[0];
     out->n_hits = ht[1];
     const uint64_t n_calls_total = ht[2];

@@ -181,6 +181,7 @@ struct HitWords {  // words 1..3 of the packed slot behind a hit (word 0 is the 
     uint32_t y, z, w;
 };
 
+#ifdef CKM_EXPERIMENTS  // the walking kernel: kept for A/B runs only (slower than plain probing)
 template <int MINB>
 __global__ void __launch_bounds__(kProbeThreads, MINB)
 probe_chain_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64_t *__restrict__ offsets, uint32_t n,
@@ -439,5 +440,7 @@ probe_chain_kernel(TableView tv, const uint8_t *__restrict__ residues, const uin
         atomicAdd(totals + 4, (unsigned long long)my_chain);
     }
 }
+
+#endif  // CKM_EXPERIMENTS
 
 }  // namespace ckm

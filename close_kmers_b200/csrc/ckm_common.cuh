@@ -38,9 +38,7 @@ struct TableView {
     // the reference's <= 1/3 load factor -- is answered from L2 and never becomes a DRAM transaction, which is
     // what bounds this kernel.  NULL when the table itself fits L2.
     const uint32_t *occupied;
-    // cache-policy experiments (ckm_set_tuning): bit0 table loads evict_first, bit1 bitmap loads evict_last,
-    // bit2 hit-record stores evict_first, bit4 table loads with a 64-byte L2 fetch (instead of bit0),
-    // bit5 plain hash probing even when the neighbour copy exists (A/B measurements)
+    // ckm_set_tuning bits (include/ckm.h); the kernels themselves read them only in CKM_EXPERIMENTS builds
     uint32_t tuning;
     // Neighbour-ordered copy of the occupied slots and each slot's index in it (ckm_chain.cuh); NULL when not built.
     const uint4 *chain;
@@ -56,6 +54,8 @@ struct __align__(16) HitRec {
     float wt;
     int32_t oI;
 };
+
+constexpr int kTile = 128;  // start positions per warp step of K1 (4 per lane)
 
 struct Params {  // kguts.h:290-293
     int order_constraint, min_hits, min_weighted_hits, max_gap;

@@ -33,6 +33,14 @@ struct ckm_ctx {
     uint32_t pipeline_ramp_div = 12, pipeline_tail_div = 8;   // first chunk = chunk/ramp_div (then doubling), last = chunk/tail_div
     bool force_raw = false;
     uint32_t tuning = 0;  // TableView::tuning
+    uint32_t probe_group_override = 0;  // CKM_PROBE_GROUP (read once at ctx creation)
+    bool staged_upload = true;          // CKM_NO_STAGED_UPLOAD=1 (read once) switches the threaded upload of pageable input off
+    // automatic fall-back of K1 from the neighbour copy to plain hash probing (see ckm_api.cu: adapt_probe_path)
+    int pc_shape = 0;     // probe_pc_kernel block shape: 0 = 27 producer warps + 1 scan warp x 1 block per SM, 1 = 13 + 1 x 2
+    bool last_fused = false;  // the last batch went through probe_pc_kernel
+    uint64_t pc_seq = 0;  // launches of probe_pc_kernel so far (picks the work counter)
+    bool copy_suspended = false;
+    uint32_t copy_retry_in = 0;
     int l2_fetch = 0;  // cudaLimitMaxL2FetchGranularity in effect
 
     // signature table in HBM
@@ -64,6 +72,7 @@ struct ckm_ctx {
 
     // device work buffers
     DevBuf in_res, in_off, totals, hits, hit_keys, hit_avg, n_hits, stored_idx, calls, calls_work, n_calls;
+    DevBuf work;   // work counters of probe_pc_kernel
     DevBuf hints;  // per 32-window segment: where the protein sits in chain[] (ckm_hint.cuh)
     DevBuf otus, n_otus, best, ps_blocks;
     DevBuf hit_off, call_off, otu_off, hits_out, calls_out, otus_out;
@@ -128,7 +137,7 @@ struct ckm_ctx {
             DevBuf *borrowed[] = {&fam.table, &fam.ids, &fam.fam_func, &fam.fam_pgf, &fam.func_sid};
             for (auto b : borrowed) *b = DevBuf();
         }
-        DevBuf *d[] = {&table, &occupied, &chain, &cpos, &hints, &in_res, &in_off, &totals, &hits, &hit_keys, &hit_avg, &n_hits, &stored_idx, &calls, &calls_work,
+        DevBuf *d[] = {&table, &occupied, &chain, &cpos, &hints, &work, &in_res, &in_off, &totals, &hits, &hit_keys, &hit_avg, &n_hits, &stored_idx, &calls, &calls_work,
                        &n_calls, &otus, &n_otus, &best, &ps_blocks, &hit_off, &call_off, &otu_off, &hits_out, &calls_out,
                        &otus_out};
         for (auto b : d) b->release();

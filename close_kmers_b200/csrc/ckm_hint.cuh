@@ -123,12 +123,18 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
     const uint4 *__restrict__ slots = reinterpret_cast<const uint4 *>(tv.slots);
     const uint32_t nsig = (uint32_t)tv.num_sigs;  // the neighbour copy is only built for tables below 2^32 buckets
     uint32_t my_probes = 0, my_hits = 0, my_chain = 0;
-    const bool pf = !(tv.tuning & 0x80000u);
     // L2 policies: the read-once streams (chain entries, slots) are loaded evict_first, which keeps more of the occupancy bitmap
-    // in L2 (4.41 -> 4.22 ms on C2, profiles/r1/tune_hint_v15_c2.jsonl; tuning bit0 switches it off).  A/B only: bit1
-    // occupancy words evict_last, bit2 hit-record stores evict_first (no effect).
+    // in L2 (4.41 -> 4.22 ms on C2, profiles/r1/tune_hint_v15_c2.jsonl).  CKM_EXPERIMENTS builds can switch that and the L2
+    // prefetches off, load the occupancy words evict_last or store hit records evict_first (measured: no effect).
+#ifdef CKM_EXPERIMENTS
+    const bool pf = !(tv.tuning & 0x80000u);
     const bool t_tab = !(tv.tuning & 1u), t_bm = tv.tuning & 2u, t_st = tv.tuning & 4u;
-    const uint64_t pol_first = policy_evict_first(), pol_last = policy_evict_last();
+    const uint64_t pol_last = policy_evict_last();
+#else
+    constexpr bool pf = true, t_tab = true, t_bm = false, t_st = false;
+    constexpr uint64_t pol_last = 0;
+#endif
+    const uint64_t pol_first = policy_evict_first();
     const uint32_t m35 = tv.m35;
 
     for (uint32_t i = warp0; i < n; i += n_warps) {

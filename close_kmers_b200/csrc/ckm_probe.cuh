@@ -79,7 +79,6 @@ struct SlotIO<false> {
     }
 };
 
-constexpr int kTile = 128;  // start positions per warp step (4 per lane)
 
 // The four 8-mer keys a lane owns in one 128-position warp step (positions t0 + 4*lane + j), with bit j of `act` set
 // when window j is probed: all eight residues valid (kguts.cc:273-339, 682-732) and j-th start < nwin.  `nwin` (= len-8:
@@ -182,8 +181,13 @@ probe_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64_t 
     const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     uint32_t my_probes = 0, my_hits = 0;
+#ifdef CKM_EXPERIMENTS  // cache-policy A/B (profiles/r1/tune1_cache_policy.jsonl: no effect or worse)
     const bool t_tab = tv.tuning & 17u, t_bm = tv.tuning & 2u, t_st = tv.tuning & 4u;
     const uint64_t pol_first = (tv.tuning & 16u) ? 0ull : policy_evict_first(), pol_last = policy_evict_last();
+#else
+    constexpr bool t_tab = false, t_bm = false, t_st = false;
+    constexpr uint64_t pol_first = 0, pol_last = 0;
+#endif
 
     for (uint32_t i = warp0; i < n; i += n_warps) {
         const uint64_t base = __ldg(offsets + i);

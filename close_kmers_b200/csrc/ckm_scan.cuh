@@ -104,8 +104,8 @@ __device__ __forceinline__ void best_from_top2(const Top2 &t, ckm_best_t &out) {
 }
 
 // find_best_call over calls[0..n) (kguts.cc:1008-1199); `work` is n call slots of scratch
-__device__ void find_best_call_dev(const ckm_call_t *__restrict__ calls, uint32_t n, ckm_call_t *__restrict__ work,
-                                   ckm_best_t &out) {
+// (no __restrict__: the caller may have written calls[] itself just before, and a non-coherent load must not be used)
+__device__ void find_best_call_dev(const ckm_call_t *calls, uint32_t n, ckm_call_t *work, ckm_best_t &out) {
     out.function_index = -1;
     out.ambig_a = out.ambig_b = -1;
     out.flags = 0;

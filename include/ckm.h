@@ -159,13 +159,18 @@ int ckm_has_occupancy_bitmap(const ckm_ctx *ctx);
  * identical with and without it).  info[0] = entries (0 = not built), info[1] = chains, info[2] = build time in
  * microseconds, info[3] = hits of the last batch that were answered from the copy instead of a hash probe. */
 int ckm_chain_info(ckm_ctx *ctx, uint64_t info[4]);
-/* A/B switches of the probe kernels (results unaffected): bit0 table loads evict_first (probe_kernel; in probe_hint_kernel
- * evict_first is the default for chain and slot loads and bit0 switches it off), bit1 bitmap loads evict_last,
- * bit2 hit-record stores evict_first, bit5 (32) plain hash probing although the neighbour copy exists, bit7 (128) / bit6 (64)
- * the walking probe_chain_kernel at 3 / 2 blocks per SM instead of hint_kernel + probe_hint_kernel, bits 16-18 variant of
- * probe_hint_kernel (0 = 128 threads x 7 blocks per SM with the hit payload staged in shared memory, 1 = 256x4 staged,
- * 2 = 128x8 staged, 3 = 128x6 staged, 4 = 256x3 payload in registers, 5 = 256x3 staged), bit19 (0x80000) without its L2 prefetches */
+/* A/B switches of K1 (results unaffected): CKM_TUNE_PLAIN_PROBE = plain hash probing (probe_kernel) although the neighbour
+ * copy exists; CKM_TUNE_UNFUSED = K1 writes hit records and scan_kernel runs even when the request could be served by the
+ * fused K1 (ckm_warp_scan.cuh); CKM_TUNE_NO_FALLBACK = never suspend the neighbour copy automatically.  A library built with
+ * -DCKM_EXPERIMENTS understands further bits (cache policies, block shapes, the walking probe_chain_kernel): see
+ * csrc/ckm_api.cu. */
+#define CKM_TUNE_PLAIN_PROBE 32u
+#define CKM_TUNE_UNFUSED 0x100000u
+#define CKM_TUNE_NO_FALLBACK 0x200000u
 void ckm_set_tuning(ckm_ctx *ctx, uint32_t bits);
+int ckm_experiments_enabled(void); /* 1 when built with -DCKM_EXPERIMENTS */
+/* 1 when the last batch of this ctx was served by probe_pc_kernel (scoring scan inside K1, no hit records in HBM) */
+int ckm_last_batch_was_fused(const ckm_ctx *ctx);
 
 /* ---- parameters (KmerGuts::set_default_parameters / set_parameters, kguts.cc:236-268) -------------- */
 void ckm_set_default_params(ckm_ctx *ctx); /* order_constraint 0, min_hits 5, min_weighted_hits 0, max_gap 200 */

@@ -12,7 +12,8 @@ from close_kmers_b200 import api, synth
 pytestmark = pytest.mark.gpu
 
 ALL = api.WANT_CALLS | api.WANT_HITS | api.WANT_OTU | api.WANT_BEST
-NO_CHAIN = 32  # ckm_set_tuning bit5
+NO_CHAIN = api.TUNE_PLAIN_PROBE | api.TUNE_NO_FALLBACK
+FUSED_FLAGS = api.WANT_CALLS | api.WANT_BEST
 
 
 def _open(img, names, bitmap="1", chain="1"):
@@ -95,14 +96,19 @@ def _compare(g, orc, batch, what, prms=(dict(), dict(order_constraint=1, min_hit
         orc.set_params(**prm)
         g.set_parameters(prm)
         want = orc.call_batch(batch, ALL)
-        g.set_tuning(0)
+        g.set_tuning(api.TUNE_NO_FALLBACK)
         got = g.process_aa_seq_batch(batch.residues, batch.offsets, ALL)
         wl.assert_results_equal(got, want, f"{what} chain {prm}")
         assert got["n_probes"] == want["n_probes"] and got["n_hits"] == len(want["hits"])
         from_copy = g.chain_info["hits_from_copy"]
-        # the other builds of probe_hint_kernel (block shape, hit payload in registers or shared memory; ckm_set_tuning
-        # bits 16-18), without the evict_first policy / L2 prefetches, and the walking probe_chain_kernel (bits 7, 6)
-        for tuning in (1 << 16, 2 << 16, 3 << 16, 4 << 16, 5 << 16, 1 | 0x80000, 128, 64):
+        # the same request served by the fused K1 (calls + best call without hit records, ckm_warp_scan.cuh)
+        fused = g.process_aa_seq_batch(batch.residues, batch.offsets, FUSED_FLAGS)
+        wl.assert_results_equal(fused, {k: want[k] for k in ("call_offsets", "calls", "best")}, f"{what} fused {prm}")
+        assert fused["n_probes"] == want["n_probes"] and fused["n_hits"] == len(want["hits"])
+        # CKM_EXPERIMENTS builds only: the other builds of probe_hint_kernel (block shape, hit payload in registers or shared
+        # memory; ckm_set_tuning bits 16-18), without the evict_first policy / L2 prefetches, and the walking
+        # probe_chain_kernel (bits 7, 6)
+        for tuning in ((1 << 16, 2 << 16, 3 << 16, 4 << 16, 5 << 16, 1 | 0x80000, 128, 64) if api.experiments_enabled() else ()):
             g.set_tuning(tuning)
             other = g.process_aa_seq_batch(batch.residues, batch.offsets, ALL)
             wl.assert_results_equal(other, want, f"{what} tuning {tuning:#x} {prm}")
@@ -111,6 +117,8 @@ def _compare(g, orc, batch, what, prms=(dict(), dict(order_constraint=1, min_hit
         plain = g.process_aa_seq_batch(batch.residues, batch.offsets, ALL)
         wl.assert_results_equal(plain, want, f"{what} plain {prm}")
         assert g.chain_info["hits_from_copy"] == 0
+        fused = g.process_aa_seq_batch(batch.residues, batch.offsets, FUSED_FLAGS)
+        wl.assert_results_equal(fused, {k: want[k] for k in ("call_offsets", "calls", "best")}, f"{what} plain fused {prm}")
         g.set_tuning(0)
     orc.set_params()
     g.set_default_parameters()
