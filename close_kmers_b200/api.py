@@ -71,7 +71,7 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build()
+    path = os.environ.get("CKM_LIB_PATH") or _build.build()  # CKM_LIB_PATH: a prebuilt variant of the library, for A/B runs
     L = C.CDLL(path)
     L.ckm_last_error.restype = C.c_char_p
     L.ckm_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]

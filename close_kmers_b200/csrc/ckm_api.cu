@@ -257,6 +257,8 @@ static int install_table(ckm_ctx *c, DevBuf raw, uint64_t n) {
     // neighbour-ordered copy (ckm_chain.cuh): like the bitmap, only pays when hits are DRAM transactions
     c->chain.release();
     c->cpos.release();
+    c->cres.release();
+    c->cpay.release();
     c->n_chain = 0;
     const char *ch = getenv("CKM_CHAIN");  // "0" disables, "1" forces
     const bool want_chain = ch ? ch[0] == '1' : table_bytes > (size_t)c->l2_bytes;
@@ -317,7 +319,8 @@ static int build_chain(ckm_ctx *c) {
             c->launches += 2;
         }
         chain_length_kernel<<<blocks, 256, 0, c->stream>>>(n, (const uint64_t *)pd.p, (uint32_t *)len.p);
-        c->launches++;
+        chain_pad_kernel<<<blocks, 256, 0, c->stream>>>(n, (uint32_t *)len.p);
+        c->launches += 2;
         RC(prefix_sum(c, (const uint32_t *)len.p, n, (uint64_t *)start.p));
         uint64_t total = 0;
         CU(cudaMemcpyAsync(&total, (const uint64_t *)start.p + n, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -327,7 +330,13 @@ static int build_chain(ckm_ctx *c) {
         CU(cudaMemsetAsync(c->chain.p, 0xFF, (total + 32) * sizeof(uint4), c->stream));
         chain_place_kernel<<<blocks, 256, 0, c->stream>>>(tv, (const uint64_t *)pd.p, (const uint64_t *)start.p, (uint4 *)c->chain.p,
                                                           (uint32_t *)c->cpos.p, (unsigned long long *)flag.p + 1);
-        c->launches++;
+        RC(c->cres.ensure(total + 256));
+        RC(c->cpay.ensure((total + 32) * sizeof(uint2)));
+        CU(cudaMemsetAsync(c->cres.p, kCresNone, total + 256, c->stream));
+        CU(cudaMemsetAsync(c->cpay.p, 0, (total + 32) * sizeof(uint2), c->stream));
+        chain_compact_kernel<<<blocks, 256, 0, c->stream>>>(tv, (const uint64_t *)pd.p, (const uint64_t *)start.p, (const uint32_t *)len.p,
+                                                            (uint8_t *)c->cres.p, (uint2 *)c->cpay.p);
+        c->launches += 2;
         unsigned long long roots = 0;
         CU(cudaMemcpyAsync(&roots, (const unsigned long long *)flag.p + 1, 8, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaEventRecord(e1, c->stream));
@@ -348,6 +357,8 @@ static int build_chain(ckm_ctx *c) {
     if (rc) {
         c->chain.release();
         c->cpos.release();
+        c->cres.release();
+        c->cpay.release();
         c->n_chain = 0;
     }
     return rc;
@@ -384,19 +395,11 @@ static int ctx_create(int device, ckm_ctx **out) {
         if (g == 4 || g == 8 || g == 16 || g == 32) c->probe_group_override = (uint32_t)g;
     }
     c->staged_upload = !getenv("CKM_NO_STAGED_UPLOAD");
-    if (const char *ps = getenv("CKM_PC_SHAPE")) c->pc_shape = atoi(ps);
-    if (const char *co = getenv("CKM_CARVEOUT"))  // experiment: shared-memory carve-out (percent) for the unfused hinted K1
-        cudaFuncSetAttribute(probe_hint_kernel<128, 7, true>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co));
-    if (cudaFuncSetAttribute(probe_pc_kernel<27, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pc_smem_bytes(27)) != cudaSuccess ||
-        cudaFuncSetAttribute(probe_pc_kernel<13, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pc_smem_bytes(13)) != cudaSuccess) {
+    if (cudaFuncSetAttribute(probe_pc_kernel<kPcProducers, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pc_smem_bytes(kPcProducers)) != cudaSuccess) {
         const int rc = ckm_fail(CKM_ECUDA, "cudaFuncSetAttribute(probe_pc_kernel): %s", cudaGetErrorString(cudaGetLastError()));
         cudaStreamDestroy(c->stream);
         delete c;
         return rc;
-    }
-    if (check_cuda(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
-        delete c;
-        return CKM_ECUDA;
     }
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
@@ -503,6 +506,8 @@ extern "C" int ckm_clone(ckm_ctx *parent, ckm_ctx **out) {
     c->occupied = parent->occupied;
     c->chain = parent->chain;
     c->cpos = parent->cpos;
+    c->cres = parent->cres;
+    c->cpay = parent->cpay;
     c->n_chain = parent->n_chain;
     c->n_chains = parent->n_chains;
     c->num_sigs = parent->num_sigs;
@@ -512,7 +517,6 @@ extern "C" int ckm_clone(ckm_ctx *parent, ckm_ctx **out) {
     c->tuning = parent->tuning;
     c->probe_group_override = parent->probe_group_override;
     c->staged_upload = parent->staged_upload;
-    c->pc_shape = parent->pc_shape;
     c->functions = parent->functions;
     c->otu_names = parent->otu_names;
     c->prm = parent->prm;
@@ -581,7 +585,7 @@ extern "C" int ckm_experiments_enabled(void) {
 extern "C" int ckm_has_occupancy_bitmap(const ckm_ctx *c) { return c->occupied.p != nullptr; }
 extern "C" int ckm_chain_info(ckm_ctx *c, uint64_t info[4]) {
     if (!c || !info) return ckm_fail(CKM_EINVAL, "NULL argument");
-    info[0] = c->n_chain;
+    info[0] = c->n_chain - (uint64_t)kChainPad * c->n_chains;  // k-mers in the copy (every chain is followed by kChainPad unused indices)
     info[1] = c->n_chains;
     info[2] = (uint64_t)(c->chain_build_ms * 1000.0);
     info[3] = 0;
@@ -765,6 +769,8 @@ static TableView table_view(const ckm_ctx *c) {
     tv.tuning = c->tuning;
     tv.chain = (const uint4 *)c->chain.p;
     tv.cpos = (const uint32_t *)c->cpos.p;
+    tv.cres = (const uint8_t *)c->cres.p;
+    tv.cpay = (const uint2 *)c->cpay.p;
     tv.n_chain = c->n_chain;
     tv.m35 = magic35(c->num_sigs);
     return tv;
@@ -832,12 +838,8 @@ static int launch_range(ckm_ctx *c, cudaStream_t stream, const uint8_t *d_res, c
             RC(c->work.ensure(kWorkSlots * 8));
             unsigned long long *work = (unsigned long long *)c->work.p + (c->pc_seq++ % kWorkSlots);
             CU(cudaMemsetAsync(work, 0, 8, stream));
-            if (c->pc_shape == 1) {
-                constexpr int P = 13;
-                const unsigned gb = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c->sm_count * 2, ((uint64_t)cnt + P * kPcChunk - 1) / (P * kPcChunk)));
-                probe_pc_kernel<P, 2><<<gb, (P + 1) * 32, pc_smem_bytes(P), stream>>>(tv, d_res, d_off + i0, cnt, i0, hints, nh, tot, fa, work);
-            } else {
-                constexpr int P = 27;
+            {
+                constexpr int P = kPcProducers;
                 const unsigned gb = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c->sm_count, ((uint64_t)cnt + P * kPcChunk - 1) / (P * kPcChunk)));
                 probe_pc_kernel<P, 1><<<gb, (P + 1) * 32, pc_smem_bytes(P), stream>>>(tv, d_res, d_off + i0, cnt, i0, hints, nh, tot, fa, work);
             }

@@ -150,6 +150,46 @@ chain_length_kernel(uint64_t num_sigs, const uint64_t *__restrict__ pd, uint32_t
     atomicMax(len + (uint32_t)x, (uint32_t)(x >> 32) + 1u);
 }
 
+// step 3a': every chain is followed by kChainPad unused indices, so that the residue string of the compact copy (below) can
+// carry the last k-mer's seven trailing residues
+constexpr uint32_t kChainPad = CKM_KMER_SIZE - 1;
+__global__ void __launch_bounds__(256) chain_pad_kernel(uint64_t num_sigs, uint32_t *__restrict__ len) {
+    const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h < num_sigs && len[h]) len[h] += kChainPad;
+}
+
+// step 3c: the compact form of the copy that probe_pc_kernel reads.  Consecutive members of a chain overlap by seven
+// residues (a successor is one of the twenty k-mers x2..x8+c, step 1), so a chain IS a residue string and its k-mers are the
+// string's windows: cres[i] = first residue of the k-mer at index i (bit 7 set: a k-mer starts here), followed after the
+// chain's last member by that k-mer's other seven residues; cpay[i] = (function_wt bits, word 3 of the packed slot).
+// "The query window equals the k-mer at index i" becomes an 8-byte string comparison against 1 + 8 bytes per window instead of
+// a key comparison against 16.
+constexpr uint8_t kCresNone = 0x7F;  // no residue (never equals a residue code)
+__global__ void __launch_bounds__(256)
+chain_compact_kernel(TableView tv, const uint64_t *__restrict__ pd, const uint64_t *__restrict__ start, const uint32_t *__restrict__ len,
+                     uint8_t *__restrict__ cres, uint2 *__restrict__ cpay) {
+    const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= tv.num_sigs) return;
+    const uint64_t x = pd[h];
+    if (x == kNoPd) return;
+    const uint32_t root = (uint32_t)x, d = (uint32_t)(x >> 32);
+    const uint64_t pos = start[root] + d;
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(tv.slots) + h);
+    uint64_t key = (uint64_t)v.x | ((uint64_t)(v.y & 0x7u) << 32);
+    uint8_t r[CKM_KMER_SIZE];
+#pragma unroll
+    for (int t = CKM_KMER_SIZE - 1; t >= 0; t--) {
+        r[t] = (uint8_t)(key % 20ull);
+        key /= 20ull;
+    }
+    cres[pos] = r[0] | 0x80u;
+    cpay[pos] = make_uint2(v.z, v.w);
+    if (d + 1u + kChainPad == len[root]) {
+#pragma unroll
+        for (int t = 1; t < CKM_KMER_SIZE; t++) cres[pos + t] = r[t];
+    }
+}
+
 // step 3b: copy every member to chain[start[root] + distance]
 __global__ void __launch_bounds__(256)
 chain_place_kernel(TableView tv, const uint64_t *__restrict__ pd, const uint64_t *__restrict__ start, uint4 *__restrict__ chain,

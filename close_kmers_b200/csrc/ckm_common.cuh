@@ -43,6 +43,9 @@ struct TableView {
     // Neighbour-ordered copy of the occupied slots and each slot's index in it (ckm_chain.cuh); NULL when not built.
     const uint4 *chain;
     const uint32_t *cpos;
+    // the compact form of the copy (chain_compact_kernel): residue string and (weight, function word) per index
+    const uint8_t *cres;
+    const uint2 *cpay;
     uint32_t n_chain;
     uint32_t m35;  // floor(2^35 / num_sigs) when 64 <= num_sigs < 2^32 (fast_mod35), else 0
 };
@@ -91,6 +94,18 @@ __device__ __forceinline__ void stg_v4_hint(uint4 *p, const uint4 &v, uint64_t p
     asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy)
                  : "memory");
 }
+
+// asynchronous global -> shared copies (LDGSTS): no registers are held while the data is in flight
+__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gsrc, uint64_t policy) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void *smem_dst, const void *gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // key % d with d = num_sigs: q = mulhi(key, floor(2^64/d)) is floor(key/d) or one less.
 __device__ __forceinline__ uint64_t fast_mod(uint64_t key, uint64_t d, uint64_t magic) {

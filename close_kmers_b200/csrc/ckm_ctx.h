@@ -36,7 +36,6 @@ struct ckm_ctx {
     uint32_t probe_group_override = 0;  // CKM_PROBE_GROUP (read once at ctx creation)
     bool staged_upload = true;          // CKM_NO_STAGED_UPLOAD=1 (read once) switches the threaded upload of pageable input off
     // automatic fall-back of K1 from the neighbour copy to plain hash probing (see ckm_api.cu: adapt_probe_path)
-    int pc_shape = 0;     // probe_pc_kernel block shape: 0 = 27 producer warps + 1 scan warp x 1 block per SM, 1 = 13 + 1 x 2
     bool last_fused = false;  // the last batch went through probe_pc_kernel
     uint64_t pc_seq = 0;  // launches of probe_pc_kernel so far (picks the work counter)
     bool copy_suspended = false;
@@ -46,6 +45,7 @@ struct ckm_ctx {
     // signature table in HBM
     bool shares_tables = false;  // a ckm_clone: table / occupied / family tables belong to the parent
     DevBuf table, occupied;  // occupied: 1 bit per slot, only for tables larger than L2
+    DevBuf cres, cpay;       // compact form of the copy: residue string + (weight, function word) per index (probe_pc_kernel)
     DevBuf chain, cpos;      // neighbour-ordered copy of the occupied slots + slot -> index in it (ckm_chain.cuh)
     uint32_t n_chain = 0;
     uint64_t n_chains = 0, chain_cycles = 0;
@@ -134,10 +134,12 @@ struct ckm_ctx {
             occupied = DevBuf();
             chain = DevBuf();
             cpos = DevBuf();
+            cres = DevBuf();
+            cpay = DevBuf();
             DevBuf *borrowed[] = {&fam.table, &fam.ids, &fam.fam_func, &fam.fam_pgf, &fam.func_sid};
             for (auto b : borrowed) *b = DevBuf();
         }
-        DevBuf *d[] = {&table, &occupied, &chain, &cpos, &hints, &work, &in_res, &in_off, &totals, &hits, &hit_keys, &hit_avg, &n_hits, &stored_idx, &calls, &calls_work,
+        DevBuf *d[] = {&table, &occupied, &chain, &cpos, &cres, &cpay, &hints, &work, &in_res, &in_off, &totals, &hits, &hit_keys, &hit_avg, &n_hits, &stored_idx, &calls, &calls_work,
                        &n_calls, &otus, &n_otus, &best, &ps_blocks, &hit_off, &call_off, &otu_off, &hits_out, &calls_out,
                        &otus_out};
         for (auto b : d) b->release();

@@ -35,6 +35,7 @@ namespace ckm {
 constexpr uint32_t kPcEnd = 1u;     // the protein ends with this record
 constexpr uint32_t kPcFin = 2u;     // the producer has no more work
 constexpr uint32_t kPcOneRun = 4u;  // all hits of the step share one function index
+constexpr int kPcProducers = 31;    // probing warps per block: 31 + 1 scan warp = 1 024 threads x 64 registers fill an SM
 constexpr uint32_t kPcChunk = 4u;   // sequences claimed per atomic
 constexpr uint32_t kPcDepth = 2u;   // published steps a producer may be ahead of its scan lane
 constexpr uint32_t kPcSpinLimit = 1u << 21;  // polls (a few tenths of a second) before a hand-off is declared stuck
@@ -59,11 +60,14 @@ static_assert(sizeof(PcRecord) == 64 && sizeof(PcSync) == 32, "shared-memory lay
 
 // Dynamic shared memory of a block with P producers:
 //   residue LUT | sync[P] | records[P][D] | queue[P][128] (8 B: key, window) | stage[P][128] (8 B: weight, function word) | W[P][D][128] | FI[P][D][128]
+//   | land[P][2][20] (residue string of the neighbour copy behind the step)
 // 4.2 KB per producer, as much as probe_hint_kernel uses per warp -- on purpose: what shared memory takes, the L1 loses, and
 // this kernel lives on its L1 (with the carve-out at its maximum probe_hint_kernel itself takes 7.1 ms per C2 step instead
 // of 4.0; profiles/r2/carveout_ab.jsonl).
+constexpr uint32_t kPcWSlot = kTile + 4;  // weights of a step + zero padding (the scan lane adds them four at a time)
+constexpr uint32_t kPcLandWords = 20;  // residue bytes of the neighbour copy behind one 64-window half of a step: 64 + 7 (+3 of alignment)
 constexpr size_t kPcPerProducer = sizeof(PcSync) + kPcDepth * sizeof(PcRecord) + kTile * sizeof(uint2) + kTile * sizeof(uint2) +
-                                  2 * kPcDepth * kTile * 4;
+                                  kPcDepth * (kPcWSlot + kTile) * 4 + 2 * kPcLandWords * 4;
 constexpr size_t pc_smem_bytes(int P) { return 256 + (size_t)P * kPcPerProducer; }
 
 // floor(off / max(1, min_hits)) by a multiply: exact for off < 2^64 / min_hits (call_region_base, ckm_scan.cuh)
@@ -71,6 +75,10 @@ static inline uint64_t call_region_magic(int min_hits) { return min_hits > 1 ? ~
 __device__ __forceinline__ uint64_t call_region_base_fast(uint64_t off, uint32_t i, uint64_t magic) {
     return (magic ? __umul64hi(off, magic) : off) + i;
 }
+
+// stage[] index of a step's window e: 8-byte entries, read four consecutive ones per lane (publish) and written 32 consecutive
+// ones per instruction (the asynchronous copy); XOR-ing the low four bits with the next three keeps both conflict-free
+__device__ __forceinline__ uint32_t stage8_at(uint32_t e) { return e ^ ((e >> 4) & 15u); }
 
 // 128-bit window masks of a step
 struct M128 {
@@ -103,16 +111,20 @@ __device__ __forceinline__ void m_drop_last(M128 &m) {
 // last position -- applied in bulk, the weights added in order.  (With max_gap < 127 a gap can fall between two hits of one
 // step, and every hit takes rs_hit.)  find_best_call of a protein with a single call is made here from registers; proteins
 // with several calls (a tenth of C2's) are left to best_fixup_kernel so that their long, divergent walk does not hold up
-// the other lanes.
-template <int P>
+// the other lanes.  What counts here is the length of the longest path through one iteration, not the work per record: the lanes
+// run in lockstep and a producer waits for its lane once it is two steps ahead (a separate shorter path for one-run
+// records made the iteration longer -- both paths are walked whenever one lane needs the general one -- and K1 8 % slower;
+// more scan warps cost probing warps, 1.6 % each: profiles/r2/k1_experiments.md).
+// first / count: the producers this scan warp serves
 __device__ __forceinline__ void pc_consume(PcSync *syncs, const PcRecord *recs, const float *wts, const uint32_t *fis, uint32_t lane,
-                                           uint32_t index_base, const FusedArgs &fa, unsigned long long *totals) {
+                                           uint32_t first, uint32_t count, uint32_t index_base, const FusedArgs &fa,
+                                           unsigned long long *totals) {
     constexpr uint32_t full = 0xffffffffu;
-    const bool mine = lane < (uint32_t)P;
-    const uint32_t w = mine ? lane : 0u;
+    const bool mine = lane < count;
+    const uint32_t w = first + (mine ? lane : 0u);
     PcSync *sy = syncs + w;
     const PcRecord *recD = recs + kPcDepth * w;
-    const float *wtsD = wts + (size_t)w * kPcDepth * kTile;
+    const float *wtsD = wts + (size_t)w * kPcDepth * kPcWSlot;
     const uint32_t *fisD = fis + (size_t)w * kPcDepth * kTile;
     const float *W = wtsD;
     const uint32_t *FI = fisD;
@@ -140,7 +152,7 @@ __device__ __forceinline__ void pc_consume(PcSync *syncs, const PcRecord *recs, 
             index = q.z;
             n = q.w;
             k = 0;
-            W = wtsD + slot * kTile;
+            W = wtsD + slot * kPcWSlot;
             FI = fisD + slot * kTile;
             if (flags & kPcFin) {
                 fin = true;
@@ -266,11 +278,11 @@ best_fixup_kernel(const uint64_t *__restrict__ offsets, uint32_t n, uint32_t ind
     fa.best[i] = b;
 }
 
-// P producer warps + 1 scan warp per block; dynamic shared memory pc_smem_bytes(P).  `work` is the next unclaimed sequence of
+// P producer warps + C scan warps per block; dynamic shared memory pc_smem_bytes(P).  `work` is the next unclaimed sequence of
 // this launch (zero at launch).  totals: [0] += probes, [1] += hits, [2] += calls, [4] += hits answered from the neighbour
 // copy, [7] = hand-off failure.
-template <int P, int MINB>
-__global__ void __launch_bounds__((P + 1) * 32, MINB)
+template <int P, int C>
+__global__ void __launch_bounds__((P + C) * 32, 1)
 probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64_t *__restrict__ offsets, uint32_t n, uint32_t index_base,
                 const uint32_t *__restrict__ hints, uint32_t *__restrict__ n_hits, unsigned long long *__restrict__ totals, FusedArgs fa,
                 unsigned long long *__restrict__ work) {
@@ -281,7 +293,8 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
     uint2 *queues = reinterpret_cast<uint2 *>(recs + kPcDepth * P);
     uint2 *stages = queues + P * kTile;
     float *wts = reinterpret_cast<float *>(stages + P * kTile);
-    uint32_t *fis = reinterpret_cast<uint32_t *>(wts + (size_t)P * kPcDepth * kTile);
+    uint32_t *fis = reinterpret_cast<uint32_t *>(wts + (size_t)P * kPcDepth * kPcWSlot);
+    uint32_t *lands = fis + (size_t)P * kPcDepth * kTile;
     fill_aa_lut(lut);
     if (threadIdx.x < P) {
         syncs[threadIdx.x].pub = 0;
@@ -292,8 +305,10 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
 
     constexpr uint32_t full = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    if (warp == (uint32_t)P) {
-        pc_consume<P>(syncs, recs, wts, fis, lane, index_base, fa, totals);
+    if (warp >= (uint32_t)P) {  // scan warp c serves producers [c * per, (c + 1) * per)
+        constexpr uint32_t per = (P + C - 1) / C;
+        const uint32_t first = (warp - P) * per;
+        pc_consume(syncs, recs, wts, fis, lane, first, first < (uint32_t)P ? min(per, (uint32_t)P - first) : 0u, index_base, fa, totals);
         return;
     }
 
@@ -301,8 +316,9 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
     PcRecord *recD = recs + kPcDepth * warp;
     uint2 *queue = queues + warp * kTile;  // left-over windows of the step: (key low word, key high bits | window << 8)
     uint2 *stage = stages + warp * kTile;  // (weight bits, word 3 of the packed slot) behind each window of the step that hit
-    float *wtsD = wts + (size_t)warp * kPcDepth * kTile;
+    float *wtsD = wts + (size_t)warp * kPcDepth * kPcWSlot;
     uint32_t *fisD = fis + (size_t)warp * kPcDepth * kTile;
+    uint32_t *land = lands + (size_t)warp * 2 * kPcLandWords;
     uint32_t pubc = 0;  // records this warp has published
     const uint32_t lt = (1u << lane) - 1u;
     const uint4 *__restrict__ slots = reinterpret_cast<const uint4 *>(tv.slots);
@@ -310,10 +326,9 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
     uint32_t my_probes = 0, my_hits = 0, my_chain = 0;
     const uint64_t pol_first = policy_evict_first();
     const uint32_t m35 = tv.m35;
-    const bool hw_fence = !(tv.tuning & 0x400000u);
 
     // hm: this lane's windows that hit (their slots are in `stage`).  Publishes the step -- hit mask, run starts, weights and
-    // function indices in position order -- into slot (pubc % kPcDepth) once the scan lane has released it.  Returns the
+    // function indices in position order -- into slot (pubc & (kPcDepth - 1u)) once the scan lane has released it.  Returns the
     // step's hit count.
     auto publish = [&](uint32_t hm, uint32_t t0, uint32_t flags, uint32_t index, uint64_t seq_base) -> uint32_t {
         if (pubc >= kPcDepth) {  // record pubc - kPcDepth consumed?
@@ -326,11 +341,11 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
                 }
                 __nanosleep(200);
             }
-            if (hw_fence) __threadfence_block();
+            __threadfence_block();
         }
         const uint32_t slot = pubc & (kPcDepth - 1u);
         PcRecord *r = recD + slot;
-        float *W = wtsD + slot * kTile;
+        float *W = wtsD + slot * kPcWSlot;
         uint32_t *FI = fisD + slot * kTile;
         uint32_t n_step = 0, rs = 0, n_runs = 0;
         const uint32_t anyb = __ballot_sync(full, hm != 0u);
@@ -339,7 +354,7 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 if (hm & (1u << j)) {
-                    const uint2 zw = stage[stage_at(4u * lane + j)];
+                    const uint2 zw = stage[stage8_at(4u * lane + j)];
                     wz[j] = zw.x;
                     fi[j] = zw.y & (kPackedFieldLimit - 1);
                     lastf = fi[j];
@@ -373,6 +388,7 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
                     FI[o] = fi[j];
                     o++;
                 }
+            if (lane < 4u) W[n_step + lane] = 0.0f;  // x + (+0) == x: the scan lane adds the weights four at a time
         }
         const uint32_t sh4 = 4u * (lane & 7u), gm = 0xFFu << (lane & 24u);
         const uint32_t hw = __reduce_or_sync(gm, hm << sh4), sw = __reduce_or_sync(gm, rs << sh4);
@@ -387,7 +403,7 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
         __syncwarp();
         pubc++;
         if (lane == 0) {
-            if (hw_fence) __threadfence_block();
+            __threadfence_block();
             sy->pub = pubc;
         }
         return n_step;
@@ -425,7 +441,6 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
                 tile_words(wb, nwords, 0, lane, rw, rx);
 
                 for (uint32_t t0 = 0; t0 < nwin; t0 += kTile) {
-                    const uint32_t q0 = t0 + 4u * lane;
                     uint32_t mh = kNoHint;
                     if (hp) {
                         const uint32_t seg0 = t0 >> kHintShift;  // first of the kSegsPerTile segments of this step
@@ -445,19 +460,35 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
                             if ((int)(lane * kSegsPerTile >> 5) == k) mh = fk;
                         }
                     }
-                    // the chain entries the hint predicts (coalesced) are requested before the keys are even built
-                    uint4 cv[4];
-                    uint32_t ok = 0;
-                    if (mh != kNoHint) {
+                    // The part of the neighbour copy the hints predict for this step is copied into shared memory asynchronously,
+                    // before the keys are even built (the addresses depend on the position only): (weight, function word) of the
+                    // 128 indices straight into the stage -- a window that matches is then already where a hit has to be -- and
+                    // the residue string behind each 64-window half.  No register holds any of it while it is in flight.
+                    static_assert(kSegsPerTile == 2, "one hint per 64-window half of a step");
+                    const uint32_t mh0 = __shfl_sync(full, mh, 0), mh1 = __shfl_sync(full, mh, 16);
+                    const bool hinted = mh0 != kNoHint || mh1 != kNoHint;
+                    if (hinted) {
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const uint32_t idx = mh + q0 + j;
-                            if (q0 + j < nwin && idx < tv.n_chain) {
-                                cv[j] = ldg_v4_hint(tv.chain + idx, pol_first);
-                                ok |= 1u << j;
+                        for (int j = 0; j < 4; j++) {  // payload of window e = 32 j + lane
+                            const uint32_t e = 32u * j + lane, mhe = j < 2 ? mh0 : mh1, idx = mhe + t0 + e;
+                            if (mhe != kNoHint && t0 + e < nwin && idx < tv.n_chain) cp_async_8(stage + stage8_at(e), tv.cpay + idx, pol_first);
+                        }
+#pragma unroll
+                        for (int hf = 0; hf < 2; hf++) {  // residues [mh + t0 + 64 hf, + 71) as aligned words; what is not there is poisoned
+                            const uint32_t mhe = hf ? mh1 : mh0, wb = ((mhe + t0 + 64u * hf) & ~3u) + 4u * lane;
+                            if (lane < kPcLandWords) {
+                                if (mhe != kNoHint && wb < tv.n_chain) cp_async_4(land + hf * kPcLandWords + lane, tv.cres + wb);
+                                else land[hf * kPcLandWords + lane] = 0x7F7F7F7Fu;
                             }
                         }
-                        if (t0 + kTile < nwin && mh + q0 + kTile < tv.n_chain) prefetch_l2(tv.chain + (mh + q0 + kTile));
+                        cp_async_commit();
+                        if (t0 + kTile < nwin) {  // the next step's part of the copy into L2
+                            const uint32_t nb = mh1 + t0 + kTile;
+                            if (mh1 != kNoHint && nb < tv.n_chain) {
+                                if (lane < 8u) prefetch_l2(tv.cpay + nb + 16u * lane);
+                                else if (lane == 8u) prefetch_l2(tv.cres + nb);
+                            }
+                        }
                     }
 
                     const TileKeys tk = tile_keys_from(lut, rw, rx, sh, t0, lane, len, nwin);
@@ -479,12 +510,26 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
                             if (act & (1u << j)) bw[j] = __ldg(tv.occupied + (h[j] >> 5));
                     }
                     uint32_t hm = 0;
+                    if (hinted) {
+                        cp_async_wait_all();
+                        __syncwarp();
+                        // the residues of the copy behind this lane's four windows, against the query's: window j matches when a
+                        // k-mer starts at its index (bit 7) and the eight residues from there on are equal
+                        const uint32_t hf = lane >> 4, l16 = lane & 15u, mhe = hf ? mh1 : mh0;
+                        const uint32_t *lw = land + hf * kPcLandWords + l16;
+                        const uint32_t s8 = 8u * ((mhe + t0) & 3u);
+                        const uint32_t w0 = lw[0], w1 = lw[1], w2 = lw[2], w3 = lw[3];
+                        const uint32_t ra = __funnelshift_r(w0, w1, s8), rb = __funnelshift_r(w1, w2, s8), rc = __funnelshift_r(w2, w3, s8);
+                        const uint32_t e0 = __vcmpeq4(ra & 0x7F7F7F7Fu, tk.c0), e1 = __vcmpeq4(rb & 0x7F7F7F7Fu, tk.c1),
+                                       e2 = __vcmpeq4(rc & 0x7F7F7F7Fu, tk.c2);
+                        const uint32_t eq = (e0 & 1u) | ((e0 >> 7) & 2u) | ((e0 >> 14) & 4u) | ((e0 >> 21) & 8u) | ((e1 << 4) & 16u) |
+                                            ((e1 >> 3) & 32u) | ((e1 >> 10) & 64u) | ((e1 >> 17) & 128u) | ((e2 << 8) & 256u) |
+                                            ((e2 << 1) & 512u) | ((e2 >> 6) & 1024u);
+                        const uint32_t sig = ((ra >> 7) & 1u) | ((ra >> 14) & 2u) | ((ra >> 21) & 4u) | ((ra >> 28) & 8u);
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        if ((ok & act & (1u << j)) && packed_match(cv[j], tk.key[j])) {
-                            stage[stage_at(4u * lane + j)] = make_uint2(cv[j].z, cv[j].w);
-                            hm |= 1u << j;
-                        }
+                        for (int j = 0; j < 4; j++)
+                            if (((eq >> j) & 0xFFu) == 0xFFu) hm |= 1u << j;
+                        hm &= sig & act;
                     }
                     my_chain += __popc(hm);
                     uint32_t need = act & ~hm;
@@ -539,7 +584,7 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
                             }
                             if (found) {
                                 const uint32_t e = it.y >> 8;
-                                stage[stage_at(e)] = make_uint2(v.z, v.w);
+                                stage[stage8_at(e)] = make_uint2(v.z, v.w);
                                 atomicOr(&sy->found[e >> 5], 1u << (e & 31u));
                             }
                         }

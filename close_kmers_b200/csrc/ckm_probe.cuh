@@ -86,6 +86,7 @@ struct SlotIO<false> {
 struct TileKeys {
     uint64_t key[4];
     uint32_t act;
+    uint32_t c0, c1, c2;  // the lane's residue codes t0 + 4*lane .. +10 (one per byte, invalid = 0x80; the top byte of c2 is unused)
 };
 
 // the residue words of one step: 32 words (one per lane) + 3 spill words (lanes 0-2)
@@ -157,6 +158,9 @@ __device__ __forceinline__ TileKeys tile_keys_from(const uint8_t *lut, uint32_t 
     const uint32_t q0 = t0 + 4u * lane;
     TileKeys tk;
     tk.act = 0;
+    tk.c0 = c0;
+    tk.c1 = c1;
+    tk.c2 = c2;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const bool ok = (((inv >> j) & 0xFFu) == 0u) && (q0 + j < nwin);
