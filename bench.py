@@ -2,18 +2,23 @@
 """Benchmark of the signature-k-mer calling path (BASELINE.json metric: proteins/s and k-mer probes/s per
 B200, % of the HBM gather roofline), with the reference's CPU path timed beside it.
 
-    python bench.py --gpus N --steps K --warmup W [--workload c1|c2|c3] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload c1|c2|c3] [--impl reference] [--skip c3,fq,matrix]
 
 A step = one pass of the hot path (encode -> probe -> ordered scoring scan -> find_best_call) over one batch
 of synthetic proteins against a synthetic signature image in the reference's file format.  Default workload
 is BASELINE.json configs[1] ("c2": 1M proteins, mean 300 aa, vs a 100M-k-mer image = 508,000,037 buckets).
 
-Keys of the JSON line: see DESIGN.md "Measurement".  `value` is kernel-resident (inputs already in HBM),
-`e2e` goes through ckm_call_batch with pinned HOST buffers (H2D + kernels + D2H inside the timed region).
+Keys of the JSON line: see DESIGN.md "Measurement".  `value` is kernel-resident (inputs already in HBM); `e2e` goes
+through the C ABI with pinned HOST buffers (H2D + kernels + D2H inside the timed region) -- ckm_call_batch_packed, the
+entry point a parser feeds (5 bits per residue), with `e2e_ascii` (ckm_call_batch, the reference's char* strings) beside it.
+Sub-records of the same line: `c3_stream` (BASELINE configs[2]: 100M proteins streamed against an 80M-k-mer image, strong-scaled
+over the ranks), `fq` (configs[3]: reads -> 6 frames -> calling -> family voting -> best frame) and `matrix` (configs[4]: 50k
+proteins, row blocks over the ranks, NCCL tile gather).
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import shutil
@@ -104,24 +109,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
-def build_world(name, n_sigs, n_proteins, sd, rank, seed=12345):
-    """Seeded synthetic world: prototypes -> signature k-mers -> (image bytes), plus this rank's proteins."""
+def build_world(n_sigs, n_proteins, sd, rank, seed=12345, what="bench"):
+    """Seeded synthetic world: prototypes -> (signature k-mers), plus this rank's proteins."""
     t0 = time.time()
     n_protos = max(64, -(-n_sigs // 293) + 8)
     protos = synth.make_prototypes(seed, n_protos, 300, sd)
     batch = synth.make_proteins_parallel(seed + 1 + rank, protos, n_proteins)
-    log(f"[bench r{rank}] prototypes+proteins: {time.time() - t0:.1f}s  ({batch.n} proteins, {batch.residues.nbytes / 1e6:.0f} MB)")
+    log(f"[{what} r{rank}] prototypes+proteins: {time.time() - t0:.1f}s  ({batch.n} proteins, {batch.residues.nbytes / 1e6:.0f} MB)")
     return protos, batch
 
 
-def build_image(protos, n_sigs, rank):
-    from close_kmers_b200 import api
-    t0 = time.time()
+def signatures_of(protos, n_sigs):
     sig = synth.make_signatures(protos, n_sigs, dedupe=n_sigs <= 2_000_000)
-    nb = synth.bucket_count(len(sig.keys))
-    img = api.build_image(nb, sig.keys, sig.fI, sig.oI, sig.avg, sig.wt)
-    log(f"[bench r{rank}] image: {len(sig.keys)} k-mers, {nb} buckets, {img.nbytes / 1e9:.2f} GB in {time.time() - t0:.1f}s")
-    return sig, nb, img
+    return sig, synth.bucket_count(len(sig.keys))
 
 
 def image_dir(tag, need_bytes):
@@ -134,6 +134,25 @@ def image_dir(tag, need_bytes):
         except OSError:
             pass
     return None
+
+
+def write_image_dir(kdir, protos, n_sigs, rank, with_reference_builder):
+    """<kdir>/kmer.table.mem_map + function.index + otu.index in the reference's format.  The reference arm builds the file
+    with the reference's own builder (KmerGuts(dir, nbuckets) + insert_kmer + save_kmer_hash_table, oracle/_ref); our arm
+    with the library's host builder (byte-identical, tests/test_oracle_vs_ref.py)."""
+    t0 = time.time()
+    sig, nb = signatures_of(protos, n_sigs)
+    if with_reference_builder:
+        import cpu_checkers as cc
+        with stdout_to_stderr():
+            cc.Ref().build_image(kdir, nb, sig)
+    else:
+        from close_kmers_b200 import api
+        api.build_image(nb, sig.keys, sig.fI, sig.oI, sig.avg, sig.wt).tofile(os.path.join(kdir, "kmer.table.mem_map"))
+    synth.write_index_files(kdir, sig.n_functions, 0)
+    log(f"[bench r{rank}] image: {len(sig.keys)} k-mers, {nb} buckets, {24 * nb / 1e9:.2f} GB in {kdir} in {time.time() - t0:.1f}s"
+        f" ({'reference builder' if with_reference_builder else 'ckm_image_build'})")
+    return sig, nb
 
 
 def cpu_threads():
@@ -158,36 +177,38 @@ class stdout_to_stderr:
         os.close(self.saved)
 
 
+def sub_batch(batch, n):
+    n = min(n, batch.n)
+    return synth.Batch(batch.residues[: int(batch.offsets[n])], batch.offsets[: n + 1])
+
+
 class CpuEngine:
     """The reference's CPU path for this workload: oracle/_ref (the reference's own object code, one KmerGuts
     per thread sharing one mmapped image, like threadpool.cc:18-45) when present, else the plain-C port."""
 
-    def __init__(self, kdir, img, threads):
+    def __init__(self, kdir, threads):
         import cpu_checkers as cc
         cc.ensure_built()
         self.threads = threads
-        self.kind = "reference" if (os.path.exists(cc.REF_SO) and kdir is not None) else "port"
+        self.kind = "reference" if os.path.exists(cc.REF_SO) else "port"
         if self.kind == "reference":
             self.eng = cc.Ref().open(kdir, threads)
             self.eng.set_params()
             self.run = lambda b: self.eng.bench_calls(b, True)
         else:
             self.eng = cc.Oracle()
-            self.eng.open_image(img) if img is not None else self.eng.open(kdir)
+            self.eng.open(kdir)
             self.run = lambda b: self.eng.bench_calls(b, threads, True)
         self.rate = None
 
     def sample(self, batch, target_s):
         """One bounded sample sized for ~target_s of wall time on all threads; returns the cpu_baseline dict."""
-        def sub(n):
-            n = min(n, batch.n)
-            return synth.Batch(batch.residues[: int(batch.offsets[n])], batch.offsets[: n + 1])
         if self.rate is None:  # calibrate once on a small slice
-            self.run(sub(min(batch.n, 50 * self.threads)))
+            self.run(sub_batch(batch, 50 * self.threads))
             cal_n = min(batch.n, 500 * self.threads)
-            self.rate = cal_n / max(self.run(sub(cal_n)), 1e-6)
+            self.rate = cal_n / max(self.run(sub_batch(batch, cal_n)), 1e-6)
         n = int(max(min(batch.n, 500 * self.threads), min(batch.n, self.rate * target_s)))
-        b = sub(n)
+        b = sub_batch(batch, n)
         t = self.run(b)
         probes = synth.n_probes_expected(b) if n <= 200_000 else None
         return {"value": n / t, "unit": "proteins/s", "cores": self.threads, "kind": self.kind,
@@ -217,6 +238,280 @@ def emit(line: dict):
     os.write(_JSON_FD if _JSON_FD is not None else 1, data)
 
 
+class Pinned:
+    """A batch in page-locked host memory: ASCII residues + offsets, and the 5-bit packed form + word offsets."""
+
+    def __init__(self, api, batch, packed=True):
+        self.api, self.L = api, api.lib()
+        self.n, self.total = batch.n, int(batch.offsets[-1])
+        self.bufs = []
+        self.res = self._copy(batch.residues, self.total + 64)
+        self.off = self._copy(batch.offsets.astype(np.uint64), (self.n + 1) * 8)
+        self.pk = self.woff = None
+        if packed:
+            pk, woff = api.pack_residues(batch.residues, batch.offsets)
+            self.words = int(woff[-1])
+            self.pk = self._copy(pk, (self.words + 2) * 4)
+            self.woff = self._copy(woff, (self.n + 1) * 8)
+
+    def _copy(self, arr, nbytes):
+        p = C.c_void_p()
+        self.api._check(self.L.ckm_host_alloc(C.byref(p), max(nbytes, 64)))
+        a = np.ascontiguousarray(arr)
+        C.memmove(p.value, a.ctypes.data, a.nbytes)
+        self.bufs.append(p)
+        return p.value
+
+    def free(self):
+        for p in self.bufs:
+            self.L.ckm_host_free(p)
+        self.bufs = []
+
+
+def timed_host_calls(fn, reps, barrier):
+    for _ in range(2):
+        fn()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = fn()
+    return time.perf_counter() - t0, out
+
+
+def allreduce(vals, op, world, torch, dist):
+    t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
+    return [float(x) for x in t]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# C3: a 100M-protein stream against the ~6 GB image, strong-scaled over the ranks, end to end through the C ABI
+# ----------------------------------------------------------------------------------------------------------------------
+def run_c3_stream(api, torch, dist, rank, world, local, barrier, peak, args, tag):
+    n_sigs, _, sd, _ = WORKLOADS["c3"]
+    n_sigs = args.c3_sigs or n_sigs
+    total_proteins = args.c3_proteins
+    pool_n = min(args.c3_pool, max(1, total_proteins // world))
+    protos, pool = build_world(n_sigs, pool_n, sd, rank, seed=54321, what="c3")
+    kdir = image_dir(tag + "_c3", 24 * synth.bucket_count(n_sigs))
+    if rank == 0:
+        write_image_dir(kdir, protos, n_sigs, rank, False)
+    barrier()
+    guts = api.KmerGuts(kmer_dir=kdir, device=local)
+    guts.set_default_parameters()
+    pin = Pinned(api, pool)
+    mine = total_proteins // world + (1 if rank < total_proteins % world else 0)  # this rank's share of the stream
+    passes, rem = divmod(mine, pool_n)
+
+    def one_pass(n=pool_n):
+        return guts.call_batch_packed_raw(pin.pk, pin.woff, n, api.WANT_BEST)
+
+    for _ in range(2):
+        out = one_pass()
+    probes_pool = int(out.n_probes)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(passes):
+        one_pass()
+    probes_rem = 0
+    if rem:
+        probes_rem = int(one_pass(rem).n_probes)
+    barrier()
+    wall = time.perf_counter() - t0
+    wall_max, = allreduce([wall], "MAX", world, torch, dist)
+    probes_all, prot_all, bytes_all = allreduce([passes * probes_pool + probes_rem, mine,
+                                                 passes * (pin.words * 4 + (pool_n + 1) * 8)], "SUM", world, torch, dist)
+    rec = None
+    if rank == 0:
+        alg = 32.0 * probes_all + prot_all * 300.0
+        rec = {"workload": f"c3: {total_proteins} proteins (a {pool_n}-protein pool per rank, cycled) vs {n_sigs}-k-mer image "
+                           f"({guts.num_sigs} buckets), strong-scaled: every rank streams 1/{world} of the proteins",
+               "entry": "ckm_call_batch_packed, pinned host buffers, WANT_BEST (H2D + unpack + K1 + D2H of 28-byte best calls in the timed region)",
+               "value": prot_all / wall_max, "unit": "proteins/s", "probes_per_s": probes_all / wall_max, "wall_s": wall_max,
+               "proteins": prot_all, "scaling": "strong", "timing": "wall clock, barrier on both sides, max over ranks",
+               "h2d_GBps_whole_job": bytes_all / wall_max / 1e9,
+               "roofline": {"bound": "hbm", "achieved": alg / wall_max / 1e9 / world, "peak": peak, "unit": "GB/s per GPU",
+                            "frac": alg / wall_max / 1e9 / world / peak,
+                            "note": "end-to-end wall time (PCIe included), not kernel time: a lower bound of the kernel's fraction"}}
+        if not args.no_cpu_baseline:
+            with stdout_to_stderr():
+                eng = CpuEngine(kdir, cpu_threads())
+                cb = eng.sample(pool, target_s=5.0)
+                eng.close()
+            rec["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    barrier()
+    guts.close()
+    pin.free()
+    if rank == 0 and kdir:
+        shutil.rmtree(kdir, ignore_errors=True)
+    return rec
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# C4: fastq reads -> six frames -> fragments -> calling + family voting -> best frame (FqProcessRequest::on_parsed_seq)
+# ----------------------------------------------------------------------------------------------------------------------
+def run_fq(api, torch, dist, rank, world, local, barrier, peak, args):
+    n_sigs, pool_n, reads_total = args.fq_sigs, args.fq_pool, args.fq_reads
+    t0 = time.time()
+    protos = synth.make_prototypes(4242, -(-n_sigs // 293) + 8, 300, 60.0)
+    sig = synth.make_signatures(protos, n_sigs, dedupe=True)  # family tables are keyed by k-mer: keys must be distinct
+    from close_kmers_b200 import api as _api
+    img = _api.build_image(synth.bucket_count(len(sig.keys)), sig.keys, sig.fI, sig.oI, sig.avg, sig.wt)
+    fam = synth.make_families(7, sig)
+    chunk = 250_000
+    parts = [synth.make_reads(100 + 7919 * rank + k, protos, min(chunk, pool_n - k * chunk)) for k in range(-(-pool_n // chunk))]
+    reads = synth.Batch(np.concatenate([p.residues for p in parts]), np.arange(pool_n + 1, dtype=np.uint64) * np.uint64(150))
+    log(f"[fq r{rank}] world ({len(sig.keys)} k-mers, {fam.n_fams} families, {pool_n} reads) in {time.time() - t0:.1f}s")
+    g = api.KmerGuts(image=img, device=local, function_names=synth.function_names(sig.n_functions))
+    g.family_load(fam.kmers, fam.fam_off, fam.fam_ids, fam.pgf, fam.plf, fam.function)
+    pin = Pinned(api, reads, packed=False)
+    o = api.FqOutC()
+    L = api.lib()
+
+    def one_pass():
+        api._check(L.ckm_fq_batch(g._h, pin.res, pin.off, pool_n, C.byref(o)))
+
+    passes = max(1, reads_total // world // pool_n)
+    for _ in range(2):
+        one_pass()
+    n_frag, n_probes = int(o.n_fragments), int(o.n_probes)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(passes):
+        one_pass()
+    barrier()
+    wall = time.perf_counter() - t0
+    wall_max, = allreduce([wall], "MAX", world, torch, dist)
+    reads_all, probes_all = allreduce([passes * pool_n, passes * n_probes], "SUM", world, torch, dist)
+    rec = None
+    if rank == 0:
+        res = g.fq_batch(reads.residues[: 150 * 20_000], reads.offsets[: 20_001])
+        fan_out = float(np.mean(np.diff(fam.fam_off.astype(np.int64))))
+        alg = reads_all * 150.0 + 32.0 * probes_all  # SURVEY 8d (the 4 B x fan-out per hit of the family lists is not counted)
+        rec = {"workload": f"c4: {int(reads_all)} reads of 150 bp ({passes} passes over a {pool_n}-read pool per rank) vs a {len(sig.keys)}-k-mer "
+                           f"image ({g.num_sigs} buckets, larger than L2) + family tables ({fam.n_fams} families, mean list {fan_out:.2f}); "
+                           f"BASELINE names 50M reads: the path is linear in reads (every read is independent), x{50e6 / max(reads_all, 1):.0f}",
+               "entry": "ckm_fq_batch, pinned host buffers (H2D of the bases, 6-frame translation, calling, family voting, best frame, D2H of the matches)",
+               "value": reads_all / wall_max, "unit": "reads/s", "probes_per_s": probes_all / wall_max, "wall_s": wall_max,
+               "fragments_per_read": n_frag / pool_n, "probes_per_read": n_probes / pool_n, "scaling": "weak",
+               "reads_with_output_in_sample": int((res["best_frame"] != 0).sum()),
+               "roofline": {"bound": "hbm", "achieved": alg / wall_max / 1e9 / world, "peak": peak, "unit": "GB/s per GPU",
+                            "frac": alg / wall_max / 1e9 / world / peak,
+                            "note": "150 B + 32 B x probes per read over end-to-end wall time"}}
+        if not args.no_cpu_baseline:
+            import cpu_checkers as cc
+            cc.ensure_built()
+            m = 4000
+            sub = synth.Batch(reads.residues[: 150 * m], reads.offsets[: m + 1])
+            if os.path.exists(cc.REF_SO):
+                d = image_dir(f"fq_{os.getpid()}", img.nbytes)
+                img.tofile(os.path.join(d, "kmer.table.mem_map"))
+                synth.write_index_files(d, sig.n_functions, 0)
+                with stdout_to_stderr():
+                    ref = cc.Ref().open(d, 1)
+                    ref.family_load(fam.kmers, fam.fam_off, fam.fam_ids, fam.pgf, fam.plf, fam.function)
+                    ref.fq_batch(synth.Batch(sub.residues[: 150 * 200], sub.offsets[:201]))
+                    t0 = time.perf_counter()
+                    want = ref.fq_batch(sub)
+                    dt = time.perf_counter() - t0
+                    ref.close()
+                shutil.rmtree(d, ignore_errors=True)
+                got = g.fq_batch(sub.residues, sub.offsets)
+                same = all(int(got["best_frame"][i]) == want[i][0] and float(got["best_score"][i]) == want[i][1] for i in range(m))
+                kind = "reference"
+                how = "the reference's DNASequence / TranslationTable / FamilyMapper / KmerGuts object code under the restated on_parsed_seq loop"
+            else:
+                orc = cc.Oracle().open_image(img)
+                orc.family_load(fam)
+                t0 = time.perf_counter()
+                want = orc.fq_batch(sub)
+                dt = time.perf_counter() - t0
+                got = g.fq_batch(sub.residues, sub.offsets)
+                same = bool(np.array_equal(got["best_frame"], want["best_frame"]) and np.array_equal(got["best_score"], want["best_score"]))
+                kind, how = "port", "the plain-C oracle"
+            rec["cpu_baseline"] = {"value": m / dt, "unit": "reads/s", "cores": 1, "kind": kind,
+                                   "sample": f"first {m} reads of the pool, {dt:.2f}s on one thread ({how}; the handler serves one request per worker thread)"}
+            rec["parity_on_sample"] = bool(same)
+    barrier()
+    g.close()
+    pin.free()
+    return rec
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# C5: /add + /matrix for 50k proteins, row blocks over the ranks, tiles gathered with NCCL
+# ----------------------------------------------------------------------------------------------------------------------
+def run_matrix(api, torch, dist, rank, world, local, barrier, peak, args):
+    from close_kmers_b200 import parallel
+    n = args.matrix_proteins
+    t0 = time.time()
+    protos = synth.make_prototypes(777, max(n // 10, 8), 300, 60.0)
+    sig = synth.make_signatures(protos, min(1_000_000, int(protos.offsets[-1]) - 8 * protos.n), dedupe=True)
+    img = api.build_image(synth.bucket_count(len(sig.keys)), sig.keys, sig.fI, sig.oI, sig.avg, sig.wt)
+    batch = synth.make_proteins_parallel(778, protos, n, mix=(0.9, 0.1, 0.0, 0.0))
+    eids = np.arange(batch.n, dtype=np.uint32)
+    log(f"[matrix r{rank}] world in {time.time() - t0:.1f}s")
+    g = api.KmerGuts(image=img, device=local)
+    job = parallel.MatrixJob(g, eids, batch, rank, world, device=torch.device("cuda", local) if world > 1 else None)
+    times = []
+    for rep in range(1 + max(2, min(args.steps, 5))):  # first pass grows every buffer
+        barrier()
+        t0 = time.perf_counter()
+        merged, stats = job.run()
+        torch.cuda.synchronize()
+        barrier()
+        times.append(time.perf_counter() - t0)
+    wall, = allreduce([min(times[1:])], "MAX", world, torch, dist)
+    rec = None
+    if rank == 0:
+        rec = {"workload": f"c5: /add of {n} proteins ({n // 10} prototypes x 10 mutated copies) + one /matrix request over all of them, "
+                           f"{len(sig.keys)}-k-mer image",
+               "entry": "ckm_postings_add_block + ckm_postings_import (NCCL all-gather of the postings) + ckm_matrix_rows per row block + "
+                        "all-gather of the COO tiles + merge",
+               "value": n / wall, "unit": "proteins/s", "wall_s": wall, "pairs": int(len(merged)), "postings": int(stats["postings"]),
+               "postings_walked": int(stats["walked"]), "scaling": "strong",
+               "row_blocks": stats["row_blocks"], "phase_ms": stats["phase_ms"],
+               "roofline": {"bound": "hbm", "achieved": 4.0 * stats["walked"] / wall / 1e9 / world, "peak": peak, "unit": "GB/s per GPU",
+                            "frac": 4.0 * stats["walked"] / wall / 1e9 / world / peak,
+                            "note": "4 B per posting walked (SURVEY 8d) over the whole request's wall time; the path is bound by "
+                                    "shared-memory atomics and launch latency at this size, not by HBM"}}
+        if not args.no_cpu_baseline:
+            import cpu_checkers as cc
+            cc.ensure_built()
+            m = min(n, 4000)
+            sub = sub_batch(batch, m)
+            ids = [f"fig|{i}.peg" for i in range(m)]
+            if os.path.exists(cc.REF_SO):
+                d = image_dir(f"mx_{os.getpid()}", img.nbytes)
+                img.tofile(os.path.join(d, "kmer.table.mem_map"))
+                synth.write_index_files(d, sig.n_functions, 0)
+                with stdout_to_stderr():
+                    ref = cc.Ref().open(d, 1)
+                    ref.mapping_new()
+                    t0 = time.perf_counter()
+                    ref.add_text(ids, sub, silent=1)
+                    want = ref.matrix_text(ids, sub)
+                    dt = time.perf_counter() - t0
+                    ref.close()
+                shutil.rmtree(d, ignore_errors=True)
+                g2 = api.KmerGuts(image=img, device=local)
+                mp = api.KmerPegMapping()
+                g2.add_text(mp, ids, sub.residues, sub.offsets, silent=1)
+                got = g2.matrix_text(mp, ids, sub.residues, sub.offsets)
+                g2.close()
+                rec["cpu_baseline"] = {"value": m / dt, "unit": "proteins/s", "cores": 1, "kind": "reference",
+                                       "sample": f"/add + /matrix of the first {m} proteins, {dt:.2f}s on one thread (the reference's KmerGuts "
+                                                 f"object code under the restated AddRequest / MatrixRequest loops; cost grows with n^2 / prototypes)"}
+                rec["equals_reference_text_on_sample"] = bool(got == want)
+            whole = api.merge_pairs(g.matrix_rows(eids, batch.residues, batch.offsets)) if world > 1 else merged
+            rec["equals_single_gpu"] = bool(whole.tobytes() == merged.tobytes())
+    barrier()
+    job.close()
+    g.close()
+    return rec
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -228,7 +523,16 @@ def main():
     ap.add_argument("--sigs", type=int, default=0, help="override signature k-mer count")
     ap.add_argument("--proteins", type=int, default=0, help="override proteins per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip", default="", help="comma-separated sub-records to leave out: c3,fq,matrix,plain")
+    ap.add_argument("--c3-proteins", type=int, default=100_000_000)
+    ap.add_argument("--c3-pool", type=int, default=2_000_000, help="proteins in the host pool each rank cycles through")
+    ap.add_argument("--c3-sigs", type=int, default=0)
+    ap.add_argument("--fq-reads", type=int, default=10_000_000)
+    ap.add_argument("--fq-pool", type=int, default=2_000_000)
+    ap.add_argument("--fq-sigs", type=int, default=20_000_000)
+    ap.add_argument("--matrix-proteins", type=int, default=50_000)
     args = ap.parse_args()
+    skip = set(x for x in args.skip.split(",") if x)
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     n_sigs, n_prot, sd, desc = WORKLOADS[args.workload]
@@ -238,23 +542,25 @@ def main():
     tag = os.environ.get("MASTER_PORT", str(os.getpid())) + f"_{args.workload}_{n_sigs}"
     config = {"workload": f"{args.workload}: {desc}", "signature_kmers": n_sigs, "proteins_per_gpu_per_step": n_prot,
               "flags": "WANT_BEST (process_aa_seq + find_best_call)", "params": "defaults (min_hits 5, max_gap 200)",
-              "l2": "inputs larger than L2 (table, residues and hit regions each exceed 126 MB)" if args.workload != "c1"
+              "l2": "inputs larger than L2 (table, residues and the neighbour copy each exceed 126 MB)" if args.workload != "c1"
                     else "table fits L2 (96 MB); parity config, not an HBM test", "seed": 12345}
 
-    # ------------------------------------------------------------------ reference arm (CPU only)
+    # ------------------------------------------------------------------ reference arm (CPU only; libckm.so is never loaded)
     if args.impl == "reference":
         if rank != 0:
             return 0
-        protos, batch = build_world(args.workload, n_sigs, n_prot, sd, 0)
-        sig, nb, img = build_image(protos, n_sigs, 0)
-        kdir = image_dir(tag + "_ref", img.nbytes)
-        if kdir:
-            img.tofile(os.path.join(kdir, "kmer.table.mem_map"))
-            synth.write_index_files(kdir, sig.n_functions, 0)
+        import cpu_checkers as cc
+        cc.ensure_built()
+        protos, batch = build_world(n_sigs, n_prot, sd, 0)
+        kdir = image_dir(tag + "_ref", 24 * synth.bucket_count(n_sigs))
+        if kdir is None:
+            emit({"impl": "reference", "unavailable": "no room for the image file under /dev/shm or /tmp"})
+            return 0
         T = cpu_threads()
         try:
+            write_image_dir(kdir, protos, n_sigs, 0, os.path.exists(cc.REF_SO))
             with stdout_to_stderr():
-                eng = CpuEngine(kdir, img, T)
+                eng = CpuEngine(kdir, T)
                 vals = []
                 for s in range(W + K):
                     r = eng.sample(batch, target_s=max(1.0, 40.0 / (W + K)))
@@ -262,13 +568,13 @@ def main():
                         vals.append(r)
                 eng.close()
         finally:
-            if kdir:
-                shutil.rmtree(kdir, ignore_errors=True)
+            shutil.rmtree(kdir, ignore_errors=True)
         v = float(np.mean([r["value"] for r in vals]))
-        ms = float(np.mean([r["seconds"] for r in vals])) * 1e3
         line = {"impl": "reference", "metric": "proteins/sec", "value": v, "unit": "proteins/s", "n_gpus": args.gpus, "steps": K,
-                "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "warmup": W, "ms_per_step": n_prot / v * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u64 keys / f32 scores", "data": "synthetic", "config": config,
+                "ms_per_step_note": f"time of the stated {n_prot}-protein step at the measured rate; every timed step ran a bounded sample of "
+                                    f"{vals[-1]['n']} proteins ({float(np.mean([r['seconds'] for r in vals])):.2f}s)",
                 "cpu_baseline": {k: vals[-1][k] for k in ("value", "unit", "cores", "kind", "sample")} | {"value": v},
                 "e2e": {"value": v, "unit": "proteins/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -291,67 +597,71 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    protos, batch = build_world(args.workload, n_sigs, n_prot, sd, rank)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+
+    protos, batch = build_world(n_sigs, n_prot, sd, rank)
     # rank 0 builds the image once and publishes it as a reference-format kmer dir; every rank opens that
     # directory with ckm_open (the reference's own load path: mmap + validate, kmer_image.cc:41-108)
     kdir = image_dir(tag, 24 * synth.bucket_count(n_sigs))
-    img = None
-    if rank == 0 or kdir is None:
-        sig, nb, img = build_image(protos, n_sigs, rank)
-        if kdir:
-            t0 = time.time()
-            img.tofile(os.path.join(kdir, "kmer.table.mem_map"))
-            synth.write_index_files(kdir, sig.n_functions, 0)
-            log(f"[bench r{rank}] wrote {kdir} in {time.time() - t0:.1f}s")
+    if kdir is None:
+        raise SystemExit("bench.py: no room for the image file under /dev/shm or /tmp")
+    if rank == 0:
+        write_image_dir(kdir, protos, n_sigs, rank, False)
     barrier()
     t0 = time.time()
-    guts = api.KmerGuts(kmer_dir=kdir, device=local) if kdir else api.KmerGuts(image=img, device=local)
+    guts = api.KmerGuts(kmer_dir=kdir, device=local)
     log(f"[bench r{rank}] table resident in HBM: {guts.num_sigs} buckets x {guts.slot_bytes} B in {time.time() - t0:.1f}s")
     guts.set_default_parameters()
-    L = api.lib()
     flags = api.WANT_BEST
     n = batch.n
     total = int(batch.offsets[-1])
     max_len = int(np.diff(batch.offsets.astype(np.int64)).max())
 
-    # device-resident copy of the batch (+16 B slack) for the kernel-resident measurement
+    # device-resident copy of the batch (+ slack) for the kernel-resident measurement
     d_res = torch.zeros(total + 64, dtype=torch.uint8, device="cuda")
     d_res[:total] = torch.from_numpy(batch.residues).cuda()
     d_off = torch.from_numpy(batch.offsets.astype(np.int64)).cuda()
-    # pinned host copy for the end-to-end measurement
-    import ctypes as C
-    hp_res, hp_off = C.c_void_p(), C.c_void_p()
-    api._check(L.ckm_host_alloc(C.byref(hp_res), total + 64))
-    api._check(L.ckm_host_alloc(C.byref(hp_off), (n + 1) * 8))
-    C.memmove(hp_res.value, batch.residues.ctypes.data, total)
-    C.memmove(hp_off.value, batch.offsets.ctypes.data, (n + 1) * 8)
+    pin = Pinned(api, batch)  # pinned host copies for the end-to-end measurements
 
     stream = torch.cuda.ExternalStream(guts.stream, device=torch.device("cuda", local))
 
     def step_resident():
         guts.call_batch_device(d_res.data_ptr(), d_off.data_ptr(), n, total, max_len, flags)
 
-    def step_e2e():
-        return guts.call_batch_raw(hp_res.value, hp_off.value, n, flags)
-
     sampler = ClockSampler(local)
     sampler.start()
     for _ in range(max(W, 3)):
         step_resident()
     guts.synchronize()
-    # parity spot check on the live workload: first 2000 proteins against the C oracle (never in the timed region)
+    # parity spot check on the live workload (never in the timed region): the first 2000 proteins against the reference's own
+    # object code when oracle/_ref is here, else the C port -- through the ASCII and the packed entry point
     if rank == 0:
         import cpu_checkers as cc
         cc.ensure_built()
-        m = min(n, 2000)
-        sb = synth.Batch(batch.residues[: int(batch.offsets[m])], batch.offsets[: m + 1])
-        orc = cc.Oracle()
-        orc.open(kdir) if kdir else orc.open_image(img)
-        want = orc.call_batch(sb, cc.WANT_BEST)["best"]
+        sb = sub_batch(batch, 2000)
+        with stdout_to_stderr():
+            if os.path.exists(cc.REF_SO):
+                chk = cc.Ref().open(kdir, 1)
+                chk.set_params()
+                checker = "oracle/_ref (reference object code)"
+            else:
+                chk = cc.Oracle()
+                chk.open(kdir)
+                checker = "oracle port"
+            want = chk.call_batch(sb, cc.WANT_BEST)["best"]
+            chk.close()
         got = guts.process_aa_seq_batch(sb.residues, sb.offsets, flags)["best"]
-        assert got.tobytes() == want.tobytes(), "bench: CUDA best calls differ from the oracle"
-        orc.close()
-        log(f"[bench] parity spot check ok ({m} proteins, {int((got['function_index'] >= 0).sum())} confident calls)")
+        assert got.tobytes() == want.tobytes(), "bench: CUDA best calls differ from " + checker
+        pk, woff = api.pack_residues(sb.residues, sb.offsets)
+        got = guts.process_packed_batch(pk, woff, flags)["best"]
+        assert got.tobytes() == want.tobytes(), "bench: CUDA best calls (packed entry) differ from " + checker
+        log(f"[bench] parity spot check ok vs {checker} ({sb.n} proteins, {int((got['function_index'] >= 0).sum())} confident calls)")
+        config["parity_spot_check"] = f"2000 proteins, best-call records bit-identical to {checker}, ASCII and packed entry"
 
     # ---- kernel-resident: K steps, device-timed on the ctx stream, max over ranks
     guts.profile_enable(True)
@@ -370,104 +680,127 @@ def main():
     launches = guts.launch_count - launches0
     probe_ms, scan_ms, nb_prof = guts.profile_read()
     guts.profile_enable(False)
+    fused = guts.last_batch_was_fused
     n_probes, n_hits, n_calls = guts.read_totals()
     chain = guts.chain_info
-    plain_probe_ms = None
-    if chain["entries"]:
-        # A/B, outside the timed region: the same steps with plain hash probing (probe_kernel) instead of
-        # hint_kernel + probe_hint_kernel -- identical results, every hit its own DRAM transaction
-        guts.set_tuning(32)
-        step_resident()
-        guts.synchronize()
-        guts.profile_enable(True)
-        guts.profile_read()
-        for _ in range(min(K, 5)):
+    ab = {}
+    if "plain" not in skip:
+        # A/B, outside the timed region: the same steps (i) through K1 + scan_kernel with 16-byte hit records in HBM (the round-1
+        # path) and (ii) with plain hash probing instead of the neighbour copy -- identical results
+        for name, bits in (("unfused_K1_plus_scan_kernel", api.TUNE_UNFUSED), ("plain_hash_probing", api.TUNE_PLAIN_PROBE | api.TUNE_NO_FALLBACK)):
+            if name == "plain_hash_probing" and not chain["entries"]:
+                continue
+            guts.set_tuning(bits)
             step_resident()
-        guts.synchronize()
-        pm, _, nbp = guts.profile_read()
-        guts.profile_enable(False)
-        plain_probe_ms = pm / max(nbp, 1)
+            guts.synchronize()
+            guts.profile_enable(True)
+            guts.profile_read()
+            for _ in range(min(K, 5)):
+                step_resident()
+            guts.synchronize()
+            pm, sm, nbp = guts.profile_read()
+            guts.profile_enable(False)
+            ab[name + "_ms"] = {"K1": pm / max(nbp, 1), "K2": sm / max(nbp, 1)}
         guts.set_tuning(0)
 
     # ---- end to end through the C ABI with HOST buffers (H2D + kernels + D2H in the timed region)
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(K):
-        out = step_e2e()
-    t_e2e = time.perf_counter() - t0
+    t_ascii, out = timed_host_calls(lambda: guts.call_batch_raw(pin.res, pin.off, n, flags), K, barrier)
     assert out.n_probes == n_probes, (out.n_probes, n_probes)
-    clocks = sampler.stop(t_clk0, time.time())  # both timed regions (device-resident steps, then end-to-end steps)
+    t_packed, out = timed_host_calls(lambda: guts.call_batch_packed_raw(pin.pk, pin.woff, n, flags), K, barrier)
+    assert out.n_probes == n_probes, (out.n_probes, n_probes)
+    clocks = sampler.stop(t_clk0, time.time())  # all timed regions (device-resident steps, then end-to-end steps)
 
-    ms_t = torch.tensor([ms_total, t_e2e * 1e3], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-        cnt = torch.tensor([n_probes, n], dtype=torch.float64, device="cuda")
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        probes_all, prot_all = float(cnt[0]), float(cnt[1])
-    else:
-        probes_all, prot_all = float(n_probes), float(n)
-    ms_total, ms_e2e = float(ms_t[0]), float(ms_t[1])
+    ms_total, ms_ascii, ms_packed = allreduce([ms_total, t_ascii * 1e3, t_packed * 1e3], "MAX", world, torch, dist)
+    probes_all, prot_all = allreduce([n_probes, n], "SUM", world, torch, dist)
 
+    line = None
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
         alg_bytes = 32.0 * n_probes + float(total)  # one 32 B sector per probe + 1 B per residue
         probe_ms_avg = probe_ms / max(nb_prof, 1)
         achieved = alg_bytes / (probe_ms_avg * 1e-3) / 1e9
-        traffic = None
+        step_ms = ms_total / K
+        traffic, traffic_src = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(
-                args.workload + ("_chain" if chain["entries"] else ""))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            ent = tj.get(args.workload + ("_fused" if fused else "_chain" if chain["entries"] else ""))
+            if isinstance(ent, dict):
+                traffic, traffic_src = ent.get("bytes"), {k: v for k, v in ent.items() if k != "bytes"}
+            elif ent is not None:
+                traffic, traffic_src = ent, {"note": "round-1 capture"}
         except (OSError, ValueError):
             pass
         # independent random 16 B reads over the resident table: best of a few occupancies
         cal_rate = max(guts.calibrate_gather(16, u, 64, b)[0] for u, b in ((1, 8), (4, 4), (4, 8)))
         value = prot_all * K / (ms_total * 1e-3)
-        probe_name = "hint_kernel+probe_hint_kernel" if chain["entries"] else "probe_kernel"
+        k1 = ("hint_kernel+" if chain["entries"] else "") + ("probe_pc_kernel+best_fixup_kernel" if fused else
+                                                            "probe_hint_kernel" if chain["entries"] else "probe_kernel")
+        h2d_packed = pin.words * 4 + (n + 1) * 8
         line = {
             "metric": "proteins/sec", "value": value, "unit": "proteins/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64 keys / f32 scores", "data": "synthetic", "config": config,
             "probes_per_s": probes_all * K / (ms_total * 1e-3),
             "per_step": {"proteins": n, "residues": total, "probes": n_probes, "hits": n_hits, "calls": n_calls},
-            "kernels_ms": {probe_name: probe_ms_avg, "scan_kernel": scan_ms / max(nb_prof, 1)},
-            "roofline": {"bound": "hbm", "kernel": probe_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic,
+            "kernels_ms": {k1: probe_ms_avg, "scan_kernel": scan_ms / max(nb_prof, 1)} | ab,
+            "roofline": {"bound": "hbm", "kernel": k1, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "frac_step": alg_bytes / (step_ms * 1e-3) / 1e9 / peak,
+                         "frac_step_note": "the same algorithmic bytes over the whole device-timed step (what `value` implies)",
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "gather_calibration": {"accesses_per_s": cal_rate, "as_32B_sectors_GBps": cal_rate * 32 / 1e9,
                                                 "probe_kernel_probes_per_s": n_probes / (probe_ms_avg * 1e-3),
                                                 "note": "ceiling of independent random reads over this table on this GPU "
                                                         "(DESIGN.md section 6); probes/s / accesses_per_s = fraction of it"}},
-            "e2e": {"value": prot_all * K / (ms_e2e * 1e-3), "unit": "proteins/s", "ms_per_step": ms_e2e / K,
-                    "h2d_bytes_per_step": total + (n + 1) * 8, "d2h_bytes_per_step": n * 28 + 24},
+            "e2e": {"value": prot_all * K / (ms_packed * 1e-3), "unit": "proteins/s", "ms_per_step": ms_packed / K,
+                    "h2d_bytes_per_step": h2d_packed, "d2h_bytes_per_step": n * 28 + 64,
+                    "entry": "ckm_call_batch_packed: residues packed five bits apiece in pinned host memory (what a parser emits in the "
+                             "pass it makes over every byte), unpacked on the device behind each chunk's copy",
+                    "host_read_GBps_per_rank": h2d_packed / (ms_packed / K * 1e-3) / 1e9},
+            "e2e_ascii": {"value": prot_all * K / (ms_ascii * 1e-3), "unit": "proteins/s", "ms_per_step": ms_ascii / K,
+                          "h2d_bytes_per_step": total + (n + 1) * 8, "d2h_bytes_per_step": n * 28 + 64,
+                          "entry": "ckm_call_batch: the reference's char* strings concatenated, pinned host memory",
+                          "host_read_GBps_per_rank": (total + (n + 1) * 8) / (ms_ascii / K * 1e-3) / 1e9},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "table": {"buckets": guts.num_sigs, "slot_bytes": guts.slot_bytes, "l2_fetch_granularity": guts.l2_fetch_granularity,
-                      "occupancy_bitmap": guts.has_occupancy_bitmap,
+                      "occupancy_bitmap": guts.has_occupancy_bitmap, "scan_inside_K1": bool(fused),
                       "neighbour_copy": {"entries": chain["entries"], "chains": chain["chains"], "build_ms": chain["build_ms"],
-                                         "hits_answered_from_copy": chain["hits_from_copy"],
-                                         "plain_hash_probe_kernel_ms": plain_probe_ms}},
+                                         "hits_answered_from_copy": chain["hits_from_copy"]}},
         }
         if not args.no_cpu_baseline and world == 1:
             with stdout_to_stderr():
-                eng = CpuEngine(kdir, img, cpu_threads())
+                eng = CpuEngine(kdir, cpu_threads())
                 cb = eng.sample(batch, target_s=8.0)
                 eng.close()
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "probes_per_s")}
-        emit(line)
     barrier()
     guts.close()
-    L.ckm_host_free(hp_res)
-    L.ckm_host_free(hp_off)
-    if kdir and rank == 0:
+    pin.free()
+    del d_res, d_off
+    torch.cuda.empty_cache()
+    if rank == 0:
         shutil.rmtree(kdir, ignore_errors=True)
+
+    # ---- the other BASELINE configs, as sub-records of the same line
+    subs = {}
+    for name, fn in (("c3_stream", lambda: run_c3_stream(api, torch, dist, rank, world, local, barrier, peak, args, tag)),
+                     ("fq", lambda: run_fq(api, torch, dist, rank, world, local, barrier, peak, args)),
+                     ("matrix", lambda: run_matrix(api, torch, dist, rank, world, local, barrier, peak, args))):
+        if name.split("_")[0] in skip or args.workload != "c2":
+            continue
+        t0 = time.time()
+        try:
+            subs[name] = fn()
+        except Exception as e:  # a sub-record must not take the headline line down with it
+            if world > 1:
+                raise
+            subs[name] = {"error": f"{type(e).__name__}: {e}"}
+        log(f"[bench r{rank}] {name}: {time.time() - t0:.1f}s")
+    if rank == 0:
+        line.update({k: v for k, v in subs.items() if v is not None})
+        emit(line)
+    barrier()
     if world > 1:
         dist.destroy_process_group()
     return 0

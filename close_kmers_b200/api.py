@@ -99,6 +99,10 @@ def lib() -> C.CDLL:
     L.ckm_encoded_aa_kmer.argtypes = [C.c_char_p]
     L.ckm_decoded_kmer.argtypes = [C.c_uint64, C.c_char_p]
     L.ckm_call_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(BatchOutC)]
+    L.ckm_call_batch_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(BatchOutC)]
+    L.ckm_packed_words.restype = C.c_uint64
+    L.ckm_packed_words.argtypes = [C.c_uint64]
+    L.ckm_pack_residues.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
     L.ckm_call_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32]
     L.ckm_device_results.argtypes = [C.c_void_p, C.POINTER(DeviceOutC)]
     L.ckm_read_totals.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
@@ -153,6 +157,20 @@ def lib() -> C.CDLL:
     L.ckm_host_free.argtypes = [C.c_void_p]
     _lib = L
     return L
+
+
+def pack_residues(residues: np.ndarray, offsets: np.ndarray) -> tuple:
+    """ASCII batch -> (packed uint32 words, word offsets): five bits per residue, every sequence from a word boundary
+    (csrc/ckm_packed.cuh)."""
+    residues = np.ascontiguousarray(residues, np.uint8)
+    offsets = np.ascontiguousarray(offsets, np.uint64)
+    n = len(offsets) - 1
+    lens = np.diff(offsets.astype(np.int64))
+    cap = int(((5 * lens + 31) // 32).sum()) if n else 0
+    packed = np.zeros(cap + 2, np.uint32)
+    woff = np.zeros(n + 1, np.uint64)
+    _check(lib().ckm_pack_residues(residues.ctypes.data, offsets.ctypes.data, n, packed.ctypes.data, cap, woff.ctypes.data))
+    return packed, woff
 
 
 def experiments_enabled() -> bool:
@@ -516,6 +534,29 @@ class KmerGuts:
         if o.best:
             r["best"] = _arr(o.best, n, BEST_DT)
         return r
+
+    def process_packed_batch(self, packed: np.ndarray, word_offsets: np.ndarray, flags: int) -> dict:
+        """process_aa_seq_batch for residues packed five bits apiece (pack_residues below; ckm_call_batch_packed)."""
+        packed = np.ascontiguousarray(packed, np.uint32)
+        word_offsets = np.ascontiguousarray(word_offsets, np.uint64)
+        n = len(word_offsets) - 1
+        o = BatchOutC()
+        _check(lib().ckm_call_batch_packed(self._h, packed.ctypes.data, word_offsets.ctypes.data, n, flags, C.byref(o)))
+        r = {"n": n, "n_probes": o.n_probes, "n_hits": o.n_hits}
+        for name, dt in (("call", CALL_DT), ("hit", HIT_DT), ("otu", OTU_DT)):
+            offp = getattr(o, f"{name}_offsets")
+            if offp:
+                off = _arr(offp, n + 1, np.uint64)
+                r[f"{name}_offsets"] = off
+                r[f"{name}s"] = _arr(getattr(o, f"{name}s"), int(off[-1]), dt)
+        if o.best:
+            r["best"] = _arr(o.best, n, BEST_DT)
+        return r
+
+    def call_batch_packed_raw(self, packed_ptr: int, word_offsets_ptr: int, n: int, flags: int) -> BatchOutC:
+        o = BatchOutC()
+        _check(lib().ckm_call_batch_packed(self._h, packed_ptr, word_offsets_ptr, n, flags, C.byref(o)))
+        return o
 
     def call_batch_raw(self, residues_ptr: int, offsets_ptr: int, n: int, flags: int) -> BatchOutC:
         """Same call with caller-owned (ideally pinned) host pointers and no result copies: for timing."""

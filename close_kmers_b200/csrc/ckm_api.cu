@@ -29,6 +29,7 @@
 #include "ckm_scan.cuh"
 #include "ckm_warp_scan.cuh"
 #include "ckm_pc.cuh"
+#include "ckm_packed.cuh"
 #include "ckm_util.cuh"
 
 using namespace ckm;
@@ -1077,21 +1078,37 @@ static int upload_batch(ckm_ctx *c, const char *residues, const uint64_t *offset
     return 0;
 }
 
+// error exit of the pipelined path after work was enqueued: nothing of the aborted batch may still run when the next one starts
+static int pipeline_abort(ckm_ctx *c, int rc) {
+    if (c->stream2) cudaStreamSynchronize(c->stream2);
+    cudaStreamSynchronize(c->stream);
+    (void)cudaGetLastError();
+    return rc;
+}
+
 // find_best_call-only batches (fixed-size results) are streamed: the batch is cut into chunks of about
 // pipeline_chunk_bytes residues that alternate between two CUDA streams, so that the H2D copy of chunk k+1 and the
 // D2H copy of chunk k-1 overlap the kernels of chunk k.  All chunks share the per-batch regions (indexed by residue
 // offset / sequence index, hence disjoint), so nothing is double-buffered.
-static int call_batch_pipelined(ckm_ctx *c, const char *residues, const uint64_t *offsets, uint32_t n, ckm_batch_out_t *out) {
+// `packed` != NULL: `offsets` are word offsets into the 5-bit packed stream (ckm_packed.cuh); every chunk is unpacked on the
+// device behind its copy, and one sequence takes 8 residue slots per word there.
+static int call_batch_pipelined(ckm_ctx *c, const char *residues, const uint32_t *packed, const uint64_t *offsets, uint32_t n,
+                                ckm_batch_out_t *out) {
+    const uint64_t unit = packed ? 8ull : 1ull;  // device residue slots per unit of `offsets`
     CU(cudaSetDevice(c->device));
     const uint64_t base0 = offsets[0];
     if (offsets[n] < base0) return ckm_fail(CKM_EINVAL, "offsets must be non-decreasing");
-    const uint64_t total = offsets[n] - base0;
+    const uint64_t total = (offsets[n] - base0) * unit;
     RunPlan plan;
     // max_len is only known chunk by chunk (validation is overlapped with the copies): size for the general kernel
     // lazily, below, if a chunk turns out to need it
     RC(prepare_regions(c, n, total, 1u, CKM_WANT_BEST, &plan));
     RC(c->in_res.ensure(total + 32));
     RC(c->in_off.ensure(((size_t)n + 1) * 8));
+    if (packed) {
+        RC(c->in_packed.ensure((offsets[n] - base0 + 2) * 4));
+        RC(c->in_woff.ensure(((size_t)n + 1) * 8));
+    }
     RC(c->h_best.ensure(((size_t)n + 1) * sizeof(ckm_best_t)));
     RC(c->h_totals.ensure(64));
     if (!c->stream2) {
@@ -1124,20 +1141,20 @@ static int call_batch_pipelined(ckm_ctx *c, const char *residues, const uint64_t
     uint32_t i0 = 0;
     int k = 0;
     while (i0 < n) {
-        const uint64_t start = offsets[i0] - base0, left = total - start;
+        const uint64_t start = (offsets[i0] - base0) * unit, left = total - start;
         uint64_t goal = want;
         if (left <= goal + tail) goal = left > 2 * tail ? left - tail : left;
         uint32_t i1 = i0, max_len = 0;
         while (i1 < n) {  // validate and size the chunk in one pass over its offsets
-            if (offsets[i1 + 1] < offsets[i1]) return ckm_fail(CKM_EINVAL, "offsets must be non-decreasing (at %u)", i1);
-            const uint64_t l = offsets[i1 + 1] - offsets[i1];
-            if (l > 500000000ull) return ckm_fail(CKM_EINVAL, "sequence %u longer than MAX_SEQ_LEN", i1);
-            if (i1 > i0 && offsets[i1 + 1] - base0 - start > goal) break;
+            if (offsets[i1 + 1] < offsets[i1]) return pipeline_abort(c, ckm_fail(CKM_EINVAL, "offsets must be non-decreasing (at %u)", i1));
+            const uint64_t l = (offsets[i1 + 1] - offsets[i1]) * unit;
+            if (l > 500000000ull) return pipeline_abort(c, ckm_fail(CKM_EINVAL, "sequence %u longer than MAX_SEQ_LEN", i1));
+            if (i1 > i0 && (offsets[i1 + 1] - base0) * unit - start > goal) break;
             max_len = std::max<uint32_t>(max_len, (uint32_t)l);
             if (reb) reb[i1 + 1] = offsets[i1 + 1] - base0;
             i1++;
         }
-        const uint64_t bytes = offsets[i1] - base0 - start;
+        const uint64_t bytes = (offsets[i1] - base0) * unit - start;
         RunPlan cp = plan;
         cp.general = max_len > kHitCap + CKM_KMER_SIZE || c->prm.order_constraint != 0;
         cp.fused = plan_fused(c, cp, CKM_WANT_BEST);
@@ -1161,8 +1178,18 @@ static int call_batch_pipelined(ckm_ctx *c, const char *residues, const uint64_t
         }
         cudaStream_t st = (k & 1) ? c->stream2 : c->stream;
         const uint64_t *src_off = reb ? reb : offsets;
-        CU(cudaMemcpyAsync((uint64_t *)c->in_off.p + i0, src_off + i0, ((size_t)(i1 - i0) + 1) * 8, cudaMemcpyHostToDevice, st));
-        if (bytes) CU(cudaMemcpyAsync((uint8_t *)c->in_res.p + start, residues + base0 + start, bytes, cudaMemcpyHostToDevice, st));
+        if (packed) {
+            const uint64_t w0 = offsets[i0] - base0, nw = offsets[i1] - offsets[i0];
+            CU(cudaMemcpyAsync((uint64_t *)c->in_woff.p + i0, src_off + i0, ((size_t)(i1 - i0) + 1) * 8, cudaMemcpyHostToDevice, st));
+            if (nw) CU(cudaMemcpyAsync((uint32_t *)c->in_packed.p + w0, packed + base0 + w0, nw * 4, cudaMemcpyHostToDevice, st));
+            const unsigned ub = (unsigned)std::min<uint64_t>(((uint64_t)(i1 - i0) + 1 + 7) / 8, (uint64_t)c->sm_count * 32);
+            unpack5_kernel<<<ub, 256, 0, st>>>((const uint32_t *)c->in_packed.p, (const uint64_t *)c->in_woff.p + i0, i1 - i0, 0ull,
+                                               (uint8_t *)c->in_res.p, (uint64_t *)c->in_off.p + i0);
+            c->launches++;
+        } else {
+            CU(cudaMemcpyAsync((uint64_t *)c->in_off.p + i0, src_off + i0, ((size_t)(i1 - i0) + 1) * 8, cudaMemcpyHostToDevice, st));
+            if (bytes) CU(cudaMemcpyAsync((uint8_t *)c->in_res.p + start, residues + base0 + start, bytes, cudaMemcpyHostToDevice, st));
+        }
         RC(launch_range(c, st, (const uint8_t *)c->in_res.p, (const uint64_t *)c->in_off.p, i0, i1 - i0, CKM_WANT_BEST, cp, nullptr));
         CU(cudaMemcpyAsync((ckm_best_t *)c->h_best.p + i0, (const ckm_best_t *)c->best.p + i0, (size_t)(i1 - i0) * sizeof(ckm_best_t),
                            cudaMemcpyDeviceToHost, st));
@@ -1184,6 +1211,8 @@ static int call_batch_pipelined(ckm_ctx *c, const char *residues, const uint64_t
     return 0;
 }
 
+static int finish_batch(ckm_ctx *c, uint32_t n, uint32_t flags, ckm_batch_out_t *out);
+
 extern "C" int ckm_call_batch(ckm_ctx *c, const char *residues, const uint64_t *offsets, uint32_t n, uint32_t flags,
                               ckm_batch_out_t *out) {
     if (!c || !out) return ckm_fail(CKM_EINVAL, "NULL argument");
@@ -1192,10 +1221,98 @@ extern "C" int ckm_call_batch(ckm_ctx *c, const char *residues, const uint64_t *
     uint64_t total = 0;
     uint32_t max_len = 0;
     if (flags == CKM_WANT_BEST && offsets && n > 1 && offsets[n] - offsets[0] >= c->pipeline_min_bytes)
-        return call_batch_pipelined(c, residues, offsets, n, out);
+        return call_batch_pipelined(c, residues, nullptr, offsets, n, out);
     RC(upload_batch(c, residues, offsets, n, &total, &max_len));
     RC(run_device(c, (const uint8_t *)c->in_res.p, (const uint64_t *)c->in_off.p, n, total, std::max(max_len, 1u), flags));
+    return finish_batch(c, n, flags, out);
+}
 
+// ---- 5-bit packed input (ckm_packed.cuh) ----
+extern "C" uint64_t ckm_packed_words(uint64_t n_residues) { return (5 * n_residues + 31) / 32; }
+
+extern "C" int ckm_pack_residues(const char *residues, const uint64_t *offsets, uint32_t n, uint32_t *packed, uint64_t packed_capacity_words,
+                                 uint64_t *word_offsets) {
+    if (!offsets || !word_offsets || (n && !residues && offsets[n] != offsets[0])) return ckm_fail(CKM_EINVAL, "NULL argument");
+    uint8_t code[256];
+    for (int ch = 0; ch < 256; ch++) code[ch] = (uint8_t)kPackInvalid;
+    for (int k = 0; k < 20; k++) code[(unsigned char)kProtAlpha[k]] = (uint8_t)k;
+    code[0] = (uint8_t)kPackEnd;  // an embedded NUL ends the sequence (strlen, kguts.cc:791)
+    uint64_t w = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (offsets[i + 1] < offsets[i]) return ckm_fail(CKM_EINVAL, "offsets must be non-decreasing (at %u)", i);
+        const uint64_t len = offsets[i + 1] - offsets[i], words = ckm_packed_words(len);
+        word_offsets[i] = w;
+        if (w + words > packed_capacity_words) return ckm_fail(CKM_EINVAL, "packed buffer too small (%llu words needed so far)", (unsigned long long)(w + words));
+        const unsigned char *p = (const unsigned char *)residues + offsets[i];
+        uint32_t *dst = packed + w;
+        uint64_t acc = 0;  // bits not yet written, low bits first
+        uint32_t nb = 0;
+        uint64_t r = 0, wi = 0;
+        bool ended = false;
+        const uint64_t slots = (32 * words) / 5;  // codes the sequence's words hold: the ones behind the last residue are "end"
+        for (; r < slots; r++) {
+            uint32_t cd = kPackEnd;
+            if (r < len && !ended) {
+                cd = code[p[r]];
+                ended = cd == kPackEnd;
+            }
+            acc |= (uint64_t)cd << nb;
+            nb += 5;
+            if (nb >= 32) {
+                dst[wi++] = (uint32_t)acc;
+                acc >>= 32;
+                nb -= 32;
+            }
+        }
+        if (wi < words) dst[wi++] = (uint32_t)acc;  // the last word's spare bits (fewer than five) stay zero
+        w += words;
+    }
+    word_offsets[n] = w;
+    return 0;
+}
+
+extern "C" int ckm_call_batch_packed(ckm_ctx *c, const uint32_t *packed, const uint64_t *word_offsets, uint32_t n, uint32_t flags,
+                                     ckm_batch_out_t *out) {
+    if (!c || !out || !word_offsets || (n && !packed && word_offsets[n] != word_offsets[0])) return ckm_fail(CKM_EINVAL, "NULL argument");
+    memset(out, 0, sizeof *out);
+    out->n = n;
+    if (flags == CKM_WANT_BEST && n > 1 && (word_offsets[n] - word_offsets[0]) * 4 >= c->pipeline_min_bytes)
+        return call_batch_pipelined(c, nullptr, packed, word_offsets, n, out);
+    CU(cudaSetDevice(c->device));
+    uint32_t max_words = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (word_offsets[i + 1] < word_offsets[i]) return ckm_fail(CKM_EINVAL, "word offsets must be non-decreasing (at %u)", i);
+        const uint64_t l = word_offsets[i + 1] - word_offsets[i];
+        if (8 * l > 500000000ull) return ckm_fail(CKM_EINVAL, "sequence %u longer than MAX_SEQ_LEN", i);  // kmer_params.h:6
+        max_words = std::max<uint32_t>(max_words, (uint32_t)l);
+    }
+    const uint64_t base0 = word_offsets[0], nw = word_offsets[n] - base0, total = 8 * nw;
+    RC(c->in_res.ensure(total + 32));
+    RC(c->in_off.ensure(((size_t)n + 1) * 8));
+    RC(c->in_packed.ensure((nw + 2) * 4));
+    RC(c->in_woff.ensure(((size_t)n + 1) * 8));
+    const uint64_t *h_woff = word_offsets;
+    if (base0 != 0) {
+        RC(c->h_off.ensure(((size_t)n + 1) * 8));
+        uint64_t *t = (uint64_t *)c->h_off.p;
+        for (uint32_t i = 0; i <= n; i++) t[i] = word_offsets[i] - base0;
+        h_woff = t;
+    }
+    if (nw) CU(cudaMemcpyAsync(c->in_packed.p, packed + base0, nw * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->in_woff.p, h_woff, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync((uint8_t *)c->in_res.p + total, 0, 32, c->stream));
+    {
+        const unsigned ub = (unsigned)std::min<uint64_t>(((uint64_t)n + 1 + 7) / 8, (uint64_t)c->sm_count * 32);
+        unpack5_kernel<<<ub, 256, 0, c->stream>>>((const uint32_t *)c->in_packed.p, (const uint64_t *)c->in_woff.p, n, 0ull, (uint8_t *)c->in_res.p,
+                                                  (uint64_t *)c->in_off.p);
+        c->launches++;
+    }
+    RC(run_device(c, (const uint8_t *)c->in_res.p, (const uint64_t *)c->in_off.p, n, total, std::max(8u * max_words, 1u), flags));
+    return finish_batch(c, n, flags, out);
+}
+
+// D2H of what `flags` asks for, after run_device
+static int finish_batch(ckm_ctx *c, uint32_t n, uint32_t flags, ckm_batch_out_t *out) {
     // totals decide the size of the compacted outputs
     RC(c->h_totals.ensure(64));
     uint64_t *ht = (uint64_t *)c->h_totals.p;

@@ -71,6 +71,7 @@ struct ckm_ctx {
     const uint64_t *cur_off = nullptr;
 
     // device work buffers
+    DevBuf in_packed, in_woff;  // 5-bit packed input of ckm_call_batch_packed and its word offsets
     DevBuf in_res, in_off, totals, hits, hit_keys, hit_avg, n_hits, stored_idx, calls, calls_work, n_calls;
     DevBuf work;   // work counters of probe_pc_kernel
     DevBuf hints;  // per 32-window segment: where the protein sits in chain[] (ckm_hint.cuh)
@@ -139,7 +140,7 @@ struct ckm_ctx {
             DevBuf *borrowed[] = {&fam.table, &fam.ids, &fam.fam_func, &fam.fam_pgf, &fam.func_sid};
             for (auto b : borrowed) *b = DevBuf();
         }
-        DevBuf *d[] = {&table, &occupied, &chain, &cpos, &cres, &cpay, &hints, &work, &in_res, &in_off, &totals, &hits, &hit_keys, &hit_avg, &n_hits, &stored_idx, &calls, &calls_work,
+        DevBuf *d[] = {&table, &occupied, &chain, &cpos, &cres, &cpay, &hints, &work, &in_packed, &in_woff, &in_res, &in_off, &totals, &hits, &hit_keys, &hit_avg, &n_hits, &stored_idx, &calls, &calls_work,
                        &n_calls, &otus, &n_otus, &best, &ps_blocks, &hit_off, &call_off, &otu_off, &hits_out, &calls_out,
                        &otus_out};
         for (auto b : d) b->release();

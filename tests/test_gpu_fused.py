@@ -152,3 +152,47 @@ def test_fused_scan_through_the_pipelined_host_path_and_device_entry(checkers):
         os.environ.pop("CKM_PIPELINE_MIN_KB", None)
         os.environ.pop("CKM_PIPELINE_CHUNK_KB", None)
         orc.close()
+
+
+def test_packed_residue_entry_matches_ascii_entry(checkers):
+    """ckm_call_batch_packed (five bits per residue, unpacked on the device) against the oracle on the ASCII strings: edge
+    sequences (empty, shorter than a k-mer, lowercase, ambiguity codes, an embedded NUL), every flag combination, a rebased
+    offsets array, and the chunked two-stream path that best-call-only batches take."""
+    protos, sig, img = wl.small_world(seed=6)
+    orc = checkers.Oracle().open_image(img)
+    rng = np.random.default_rng(5)
+    lens = [0, 1, 6, 7, 12, 13, 19, 25, 26, 31, 32, 33, 63, 64, 65, 127, 128, 129, 640, 641]  # around 5 L = 0 (mod 32)
+    aa = synth.AA
+    extra = synth.batch_from_strings([aa[rng.integers(0, 20, L)].tobytes() for L in lens])
+    batch = wl.concat_batches(wl.concat_batches(wl.edge_batch(protos), extra), synth.make_proteins(9, protos, 4000))
+    packed, woff = api.pack_residues(batch.residues, batch.offsets)
+    assert int(woff[-1]) == int(((5 * np.diff(batch.offsets.astype(np.int64)) + 31) // 32).sum())
+    try:
+        for chain in ("0", "1"):
+            g = _open(img, synth.function_names(sig.n_functions), chain)
+            for prm in (dict(), dict(order_constraint=1, min_hits=2, max_gap=30)):
+                orc.set_params(**prm)
+                g.set_parameters(prm)
+                want = orc.call_batch(batch, ALL)
+                got = g.process_packed_batch(packed, woff, ALL)
+                wl.assert_results_equal(got, want, f"packed entry, all flags, chain={chain} {prm}")
+                assert got["n_probes"] == want["n_probes"] and got["n_hits"] == len(want["hits"])
+                got = g.process_packed_batch(packed, woff, api.WANT_CALLS | api.WANT_BEST)
+                wl.assert_results_equal(got, {k: want[k] for k in ("call_offsets", "calls", "best")}, f"packed entry, fused {prm}")
+                k = 41
+                got = g.process_packed_batch(packed, woff[k:], api.WANT_BEST)
+                assert got["best"].tobytes() == want["best"][k:].tobytes()
+            g.close()
+        os.environ.update(CKM_PIPELINE_MIN_KB="0", CKM_PIPELINE_CHUNK_KB="64")
+        g = _open(img, synth.function_names(sig.n_functions), "1")
+        orc.set_params()
+        want = orc.call_batch(batch, api.WANT_BEST)
+        got = g.process_packed_batch(packed, woff, api.WANT_BEST)  # ~25 chunks on two streams, each unpacked behind its copy
+        assert got["best"].tobytes() == want["best"].tobytes() and got["n_probes"] == want["n_probes"]
+        got = g.process_packed_batch(packed, woff[17:], api.WANT_BEST)
+        assert got["best"].tobytes() == want["best"][17:].tobytes()
+        g.close()
+    finally:
+        os.environ.pop("CKM_PIPELINE_MIN_KB", None)
+        os.environ.pop("CKM_PIPELINE_CHUNK_KB", None)
+        orc.close()
