@@ -653,13 +653,23 @@ def main():
                 chk = cc.Oracle()
                 chk.open(kdir)
                 checker = "oracle port"
-            want = chk.call_batch(sb, cc.WANT_BEST)["best"]
+            ref_out = chk.call_batch(sb, cc.WANT_BEST)
             chk.close()
+        want, names = ref_out["best"], ref_out.get("best_function")
+
+        def same(got):  # the reference reports an ambiguous call as a string, not as a pair of indices (kguts.cc:1176-1196)
+            a, b = got.copy(), want.copy()
+            if names is not None:
+                for f in ("ambig_a", "ambig_b"):
+                    a[f] = 0
+                    b[f] = 0
+            return a.tobytes() == b.tobytes() and (names is None or [guts.best_function(r) for r in got] == names)
+
         got = guts.process_aa_seq_batch(sb.residues, sb.offsets, flags)["best"]
-        assert got.tobytes() == want.tobytes(), "bench: CUDA best calls differ from " + checker
+        assert same(got), "bench: CUDA best calls differ from " + checker
         pk, woff = api.pack_residues(sb.residues, sb.offsets)
         got = guts.process_packed_batch(pk, woff, flags)["best"]
-        assert got.tobytes() == want.tobytes(), "bench: CUDA best calls (packed entry) differ from " + checker
+        assert same(got), "bench: CUDA best calls (packed entry) differ from " + checker
         log(f"[bench] parity spot check ok vs {checker} ({sb.n} proteins, {int((got['function_index'] >= 0).sum())} confident calls)")
         config["parity_spot_check"] = f"2000 proteins, best-call records bit-identical to {checker}, ASCII and packed entry"
 

@@ -138,6 +138,10 @@ def lib() -> C.CDLL:
     L.ckm_postings_count.argtypes = [C.c_void_p]
     L.ckm_matrix_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
                                   C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.ckm_postings_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.ckm_postings_import_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.ckm_matrix_rows_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                         C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.ckm_mapping_new.restype = C.c_void_p
     L.ckm_mapping_free.argtypes = [C.c_void_p]
     L.ckm_mapping_encode_id.restype = C.c_uint32
@@ -418,8 +422,8 @@ class KmerGuts:
         return other
 
     def close(self):
-        if getattr(self, "_h", None):
-            lib().ckm_close(self._h)
+        if getattr(self, "_h", None) and _lib is not None and lib is not None:  # (module globals are gone at interpreter exit)
+            _lib.ckm_close(self._h)
             self._h = None
 
     __del__ = close
@@ -771,6 +775,26 @@ class KmerGuts:
         _check(lib().ckm_matrix_rows(self._h, eids.ctypes.data, residues.ctypes.data, offsets.ctypes.data, n, row_begin,
                                      n if row_end is None else row_end, C.byref(p), C.byref(npairs)))
         return _arr(p.value, npairs.value, PAIR_DT)
+
+    def postings_device(self) -> tuple:
+        """(device pointer of the k-mers, device pointer of the peg ids, count) of the postings this ctx holds."""
+        k, e, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        _check(lib().ckm_postings_device(self._h, C.byref(k), C.byref(e), C.byref(n)))
+        return k.value or 0, e.value or 0, n.value
+
+    def postings_import_device(self, d_keys: int, d_eids: int, n: int):
+        _check(lib().ckm_postings_import_device(self._h, d_keys, d_eids, n))
+
+    def matrix_rows_device(self, eids, residues, offsets, row_begin=0, row_end=None) -> tuple:
+        """ckm_matrix_rows with the tile left in HBM, rows ordered by partner id: (device pointer, pairs, postings walked)."""
+        eids = np.ascontiguousarray(eids, np.uint32)
+        residues = np.ascontiguousarray(residues, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        n = len(offsets) - 1
+        p, npairs, walked = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        _check(lib().ckm_matrix_rows_device(self._h, eids.ctypes.data, residues.ctypes.data, offsets.ctypes.data, n, row_begin,
+                                            n if row_end is None else row_end, C.byref(p), C.byref(npairs), C.byref(walked)))
+        return p.value or 0, npairs.value, walked.value
 
     def add_text(self, mapping: KmerPegMapping, ids, residues, offsets, silent=0) -> str:
         residues = np.ascontiguousarray(residues, np.uint8)

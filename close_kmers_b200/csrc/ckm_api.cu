@@ -396,6 +396,10 @@ static int ctx_create(int device, ckm_ctx **out) {
         if (g == 4 || g == 8 || g == 16 || g == 32) c->probe_group_override = (uint32_t)g;
     }
     c->staged_upload = !getenv("CKM_NO_STAGED_UPLOAD");
+    if (check_cuda(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
+        delete c;
+        return CKM_ECUDA;
+    }
     if (cudaFuncSetAttribute(probe_pc_kernel<kPcProducers, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pc_smem_bytes(kPcProducers)) != cudaSuccess) {
         const int rc = ckm_fail(CKM_ECUDA, "cudaFuncSetAttribute(probe_pc_kernel): %s", cudaGetErrorString(cudaGetLastError()));
         cudaStreamDestroy(c->stream);

@@ -110,6 +110,8 @@ struct ckm_ctx {
     // postings of the mappings that are not selected (ckm_postings_select): one KmerPegMapping per "/mapping/<key>"
     std::map<uint32_t, Post> post_store;
     uint32_t post_key = 0;
+    bool matrix_tile_on_device = false;  // ckm_matrix_rows_device: the COO tile stays in HBM, rows ordered by partner id
+    uint64_t matrix_walked = 0;
     uint64_t famnr_compact_at = 1ull << 28, famnr_last_unique = 0;  // dedupe the collected pairs once this many are held
 
     // fastq path (ckm_fq.cuh)

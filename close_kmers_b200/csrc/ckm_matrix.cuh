@@ -342,7 +342,12 @@ static int matrix_rows_impl(ckm_ctx *c, const uint32_t *eids, const char *residu
     c->launches += 2;
     RC(prefix_sum(c, (const uint32_t *)F.gcap.p, n_rows, (uint64_t *)F.gofs.p));
     RC(prefix_sum(c, (const uint32_t *)P.rcap.p, n_rows, (uint64_t *)P.rofs.p));
-    uint64_t gtotal = 0, rtotal = 0;
+    uint64_t gtotal = 0, rtotal = 0, gtotal_entries = 0;
+    if (c->matrix_tile_on_device) {  // the row block's work, for the caller's report: posting-list entries behind its hits
+        RC(P.out_off.ensure(((size_t)n_rows + 2) * 8));
+        RC(prefix_sum(c, (const uint32_t *)F.E.p, n_rows, (uint64_t *)P.out_off.p));
+        CU(cudaMemcpyAsync(&gtotal_entries, (const uint64_t *)P.out_off.p + n_rows, 8, cudaMemcpyDeviceToHost, c->stream));
+    }
     CU(cudaMemcpyAsync(&gtotal, (const uint64_t *)F.gofs.p + n_rows, 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(&rtotal, (const uint64_t *)P.rofs.p + n_rows, 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -366,9 +371,11 @@ static int matrix_rows_impl(ckm_ctx *c, const uint32_t *eids, const char *residu
     RC(P.out.ensure((np + 1) * sizeof(ckm_pair_t)));
     RC(P.h_out.ensure((np + 1) * sizeof(ckm_pair_t)));
     matrix_export_kernel<<<(unsigned)(((uint64_t)n_rows * 32 + 255) / 256), 256, 0, c->stream>>>(
-        (const uint64_t *)P.rofs.p, (const ckm_pair_t *)P.entries.p, (const uint64_t *)P.out_off.p, n_rows, (ckm_pair_t *)P.out.p, !filter);
+        (const uint64_t *)P.rofs.p, (const ckm_pair_t *)P.entries.p, (const uint64_t *)P.out_off.p, n_rows, (ckm_pair_t *)P.out.p,
+        !filter || c->matrix_tile_on_device);
     c->launches++;
-    if (np) CU(cudaMemcpyAsync(P.h_out.p, P.out.p, np * sizeof(ckm_pair_t), cudaMemcpyDeviceToHost, c->stream));
+    c->matrix_walked = gtotal_entries;
+    if (np && !c->matrix_tile_on_device) CU(cudaMemcpyAsync(P.h_out.p, P.out.p, np * sizeof(ckm_pair_t), cudaMemcpyDeviceToHost, c->stream));
     if (h_off) {
         RC(P.h_off.ensure(((size_t)n_rows + 2) * 8));
         CU(cudaMemcpyAsync(P.h_off.p, P.out_off.p, ((size_t)n_rows + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -378,6 +385,53 @@ static int matrix_rows_impl(ckm_ctx *c, const uint32_t *eids, const char *residu
     CU(cudaGetLastError());
     *pairs = (const ckm_pair_t *)P.h_out.p;
     *n_pairs = np;
+    return 0;
+}
+
+// ---- multi-GPU /matrix: hit extraction sharded by protein block, postings exchanged device to device ----
+// The (k-mer, peg id) pairs this ctx holds, in HBM: what a rank contributes to the all-gather of the postings.
+extern "C" int ckm_postings_device(ckm_ctx *c, const uint64_t **d_keys, const uint32_t **d_eids, uint64_t *n) {
+    if (!c || !d_keys || !d_eids || !n) return ckm_fail(CKM_EINVAL, "NULL argument");
+    *d_keys = (const uint64_t *)c->post.keys.p;
+    *d_eids = (const uint32_t *)c->post.eids.p;
+    *n = c->post.n;
+    return 0;
+}
+// Replace the ctx's postings by `n` pairs that already sit in HBM (the gathered postings of all ranks); device-to-device copy.
+extern "C" int ckm_postings_import_device(ckm_ctx *c, const uint64_t *d_keys, const uint32_t *d_eids, uint64_t n) {
+    if (!c || (n && (!d_keys || !d_eids))) return ckm_fail(CKM_EINVAL, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    ckm_ctx::Post &P = c->post;
+    RC(P.keys.ensure((n + 1) * 8));
+    RC(P.eids.ensure((n + 1) * 4));
+    if (n) {
+        CU(cudaMemcpyAsync(P.keys.p, d_keys, n * 8, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(P.eids.p, d_eids, n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    P.n = n;
+    P.dirty = true;
+    return 0;
+}
+// ckm_matrix_rows that leaves its COO tile in HBM (valid until the next call on the ctx), every row's entries ordered by partner
+// id: with ids that ascend in request order the tile is then already in the (eid_i, eid_j) order of the reference's std::map.
+// *postings_walked = posting-list entries the rows' hits carry (the row block's work).
+extern "C" int ckm_matrix_rows_device(ckm_ctx *c, const uint32_t *eids, const char *residues, const uint64_t *offsets, uint32_t n,
+                                      uint32_t row_begin, uint32_t row_end, const ckm_pair_t **d_pairs, uint64_t *n_pairs,
+                                      uint64_t *postings_walked) {
+    if (!c || !d_pairs || !n_pairs || (n && (!eids || !offsets))) return ckm_fail(CKM_EINVAL, "NULL argument");
+    *d_pairs = nullptr;
+    *n_pairs = 0;
+    if (postings_walked) *postings_walked = 0;
+    if (row_end > n) row_end = n;
+    if (row_begin >= row_end) return 0;
+    const ckm_pair_t *unused = nullptr;
+    c->matrix_tile_on_device = true;
+    const int rc = matrix_rows_impl(c, eids, residues, offsets, n, row_begin, row_end, true, &unused, n_pairs, nullptr);
+    c->matrix_tile_on_device = false;
+    if (rc) return rc;
+    *d_pairs = (const ckm_pair_t *)c->post.out.p;
+    if (postings_walked) *postings_walked = c->matrix_walked;
     return 0;
 }
 

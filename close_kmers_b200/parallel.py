@@ -57,3 +57,101 @@ def matrix_sharded(compute_rows, lengths, rank: int, world: int, group=None, dev
     begin, end = shard_rows(lengths, world)[rank]
     local = compute_rows(begin, end) if end > begin else np.zeros(0, PAIR_DT)
     return api.merge_pairs(gather_pairs(local, group, device))
+
+
+class _DeviceView:
+    """A raw device pointer as something torch.as_tensor can alias without a copy (__cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, count: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def _alias(ptr: int, count: int, typestr: str, torch, device):
+    if count == 0 or not ptr:
+        return torch.zeros(0, dtype={"<u8": torch.int64, "<u4": torch.int32, "|u1": torch.uint8}[typestr], device=device)
+    t = torch.as_tensor(_DeviceView(ptr, count, {"<u8": "<i8", "<u4": "<i4", "|u1": "|u1"}[typestr]), device=device)
+    return t
+
+
+def _all_gather_var(local, world, dist, torch, group=None):
+    """all_gather of 1-D device tensors of different lengths; returns the list of per-rank tensors (views of one buffer)."""
+    n = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
+    sizes = torch.zeros(world, dtype=torch.int64, device=local.device)
+    dist.all_gather_into_tensor(sizes, n, group=group)
+    sizes = [int(x) for x in sizes.tolist()]
+    mx = max(max(sizes), 1)
+    send = torch.zeros(mx, dtype=local.dtype, device=local.device)
+    send[: local.numel()] = local
+    recv = torch.empty(world * mx, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    return [recv[r * mx: r * mx + sizes[r]] for r in range(world)]
+
+
+class MatrixJob:
+    """/add + /matrix of one request over `world` GPUs (matrix_request.cc:78-95, 130-189):
+
+      1. hit extraction sharded by PROTEIN BLOCK: rank r runs ckm_postings_add on its contiguous block only;
+      2. the (k-mer, peg id) postings are exchanged DEVICE TO DEVICE (NCCL all-gather over NVLink on the postings buffers
+         themselves; no host bounce) and every rank installs the full set (ckm_postings_import_device);
+      3. every rank computes its ROW BLOCK of the strictly-lower-triangular count matrix (ckm_matrix_rows_device); blocks are
+         balanced by the posting work of their rows -- hits x posting-list length, for which the residue count stands in
+         (every row walks the whole list of each of its hits; the j < i rule filters entries, it does not shorten the walk);
+      4. the COO tiles, each already in (eid_i, eid_j) order, are all-gathered device to device and copied back once.
+
+    With world == 1 the same calls run without the collectives.  eids must be the request's ids; when they ascend in request
+    order (the usual case: KmerPegMapping::encode_id numbers ids in order of first appearance, kmer.cc:272-286) the
+    concatenated tiles are final, otherwise they go through api.merge_pairs."""
+
+    def __init__(self, guts, eids, batch, rank: int, world: int, device=None, group=None):
+        self.g, self.eids, self.batch, self.rank, self.world, self.device, self.group = guts, np.ascontiguousarray(eids, np.uint32), batch, rank, world, device, group
+        lengths = np.diff(batch.offsets.astype(np.int64))
+        self.blocks = shard_rows(lengths, world)
+        self.ascending = bool(np.all(np.diff(self.eids.astype(np.int64)) > 0)) if len(self.eids) > 1 else True
+
+    def _sub(self, a, b):
+        o = self.batch.offsets
+        return self.eids[a:b], self.batch.residues[int(o[a]): int(o[b])], (o[a: b + 1] - o[a]).astype(np.uint64)
+
+    def run(self):
+        import time
+        import torch
+        from . import api
+        g, world = self.g, self.world
+        t = [time.perf_counter()]
+        a, b = self.blocks[self.rank]
+        g.postings_clear()
+        if b > a:
+            g.postings_add(*self._sub(a, b))
+        t.append(time.perf_counter())
+        if world > 1:
+            import torch.distributed as dist
+            dk, de, n_local = g.postings_device()
+            keys = _all_gather_var(_alias(dk, n_local, "<u8", torch, self.device), world, dist, torch, self.group)
+            pegs = _all_gather_var(_alias(de, n_local, "<u4", torch, self.device), world, dist, torch, self.group)
+            all_keys, all_pegs = torch.cat(keys), torch.cat(pegs)
+            g.postings_import_device(all_keys.data_ptr(), all_pegs.data_ptr(), all_keys.numel())
+        t.append(time.perf_counter())
+        ptr, n_pairs, walked = g.matrix_rows_device(self.eids, self.batch.residues, self.batch.offsets, a, b)
+        t.append(time.perf_counter())
+        if world > 1:
+            tile = _alias(ptr, n_pairs * 16, "|u1", torch, self.device)
+            tiles = _all_gather_var(tile, world, dist, torch, self.group)
+            # every rank holds every tile in HBM; the host copy is made where the response is written
+            merged = torch.cat(tiles).cpu().numpy().view(PAIR_DT) if self.rank == 0 else np.zeros(0, PAIR_DT)
+            w = torch.tensor([walked], dtype=torch.int64, device=self.device)
+            dist.all_reduce(w, group=self.group)
+            walked = int(w)
+        else:
+            tile = _alias(ptr, n_pairs * 16, "|u1", torch, torch.device("cuda", torch.cuda.current_device()))
+            merged = tile.cpu().numpy().view(PAIR_DT)
+        t.append(time.perf_counter())
+        if not self.ascending:
+            merged = api.merge_pairs(merged)
+        t.append(time.perf_counter())
+        stats = {"postings": g.postings_count, "walked": walked, "row_blocks": self.blocks,
+                 "phase_ms": {"add_block": (t[1] - t[0]) * 1e3, "gather_postings": (t[2] - t[1]) * 1e3, "rows": (t[3] - t[2]) * 1e3,
+                              "gather_tiles": (t[4] - t[3]) * 1e3, "merge": (t[5] - t[4]) * 1e3}}
+        return merged, stats
+
+    def close(self):
+        pass

@@ -351,6 +351,17 @@ typedef struct {
 int ckm_matrix_rows(ckm_ctx *ctx, const uint32_t *eids, const char *residues, const uint64_t *offsets, uint32_t n,
                     uint32_t row_begin, uint32_t row_end, const ckm_pair_t **pairs, uint64_t *n_pairs);
 
+/* Multi-GPU /matrix (row blocks over the ranks; the caller's collective moves device memory, e.g. ncclAllGather): a rank
+ * extracts the hits of ITS protein block with ckm_postings_add, publishes them with ckm_postings_device, every rank installs the
+ * gathered postings of all ranks with ckm_postings_import_device and computes its row block with ckm_matrix_rows_device, whose
+ * tile stays in HBM with every row's entries ordered by partner id (*d_pairs is valid until the next call on the ctx;
+ * *postings_walked = posting-list entries behind the rows' hits).  close_kmers_b200/parallel.py drives this over torch.distributed. */
+int ckm_postings_device(ckm_ctx *ctx, const uint64_t **d_keys, const uint32_t **d_eids, uint64_t *n);
+int ckm_postings_import_device(ckm_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_eids, uint64_t n);
+int ckm_matrix_rows_device(ckm_ctx *ctx, const uint32_t *eids, const char *residues, const uint64_t *offsets, uint32_t n,
+                           uint32_t row_begin, uint32_t row_end, const ckm_pair_t **d_pairs, uint64_t *n_pairs,
+                           uint64_t *postings_walked);
+
 /* LookupRequest::on_hit without families (lookup_request.cc:466-478): for every sequence of the batch, the pegs of the
  * selected postings that share a hit k-mer with it and how many postings did (seq_score_[eid].hit_count).  pairs[k] =
  * {eid_i = sequence index in the batch, eid_j = peg id, count}; pair_offsets has n + 1 entries; pegs ascending per sequence. */

@@ -30,6 +30,7 @@ def world(checkers):
     guts_raw = api.KmerGuts(image=img, function_names=names)
     del os.environ["CKM_FORCE_RAW_SLOTS"]
     assert guts.slot_bytes == 16 and guts_raw.slot_bytes == 24
+    assert guts.stream != 0 and guts.stream != guts_raw.stream  # every context works on a stream of its own, never the default one
     yield protos, sig, img, orc, guts, guts_raw
     guts.close()
     guts_raw.close()

@@ -1,4 +1,5 @@
-"""End-to-end (host buffers in, best calls out) sweep over pipeline chunk sizes on the C2 workload (GPU box)."""
+"""End-to-end (host buffers in, best calls out) sweep over pipeline chunk sizes on the C2 workload (GPU box), through the ASCII
+entry point and the 5-bit packed one.  python tools/tune_e2e.py [n_proteins] [n_sigs]"""
 import ctypes as C
 import json
 import os
@@ -22,10 +23,13 @@ api._check(L.ckm_host_alloc(C.byref(hp_res), total + 64))
 api._check(L.ckm_host_alloc(C.byref(hp_off), (batch.n + 1) * 8))
 C.memmove(hp_res.value, batch.residues.ctypes.data, total)
 C.memmove(hp_off.value, batch.offsets.ctypes.data, (batch.n + 1) * 8)
-import torch
-props = torch.cuda.get_device_properties(0)
-print(json.dumps(dict(l2=props.L2_cache_size)), flush=True)
-for chunk_kb, ramp, tail in ((49152, 12, 8), (49152, 24, 8), (49152, 48, 16), (49152, 12, 16), (40960, 20, 10), (32768, 16, 8), (32768, 32, 16), (65536, 32, 16), (24576, 12, 8)):
+pk, woff = api.pack_residues(batch.residues, batch.offsets)
+hp_pk, hp_woff = C.c_void_p(), C.c_void_p()
+api._check(L.ckm_host_alloc(C.byref(hp_pk), pk.nbytes + 64))
+api._check(L.ckm_host_alloc(C.byref(hp_woff), (batch.n + 1) * 8))
+C.memmove(hp_pk.value, pk.ctypes.data, pk.nbytes)
+C.memmove(hp_woff.value, woff.ctypes.data, (batch.n + 1) * 8)
+for chunk_kb, ramp, tail in ((49152, 12, 8), (49152, 24, 16), (32768, 16, 8), (32768, 32, 16), (24576, 12, 8), (24576, 24, 16), (16384, 8, 8), (16384, 16, 16), (12288, 8, 8), (8192, 8, 8)):
     os.environ["CKM_PIPELINE_CHUNK_KB"] = str(chunk_kb)
     os.environ["CKM_PIPELINE_RAMP_DIV"] = str(ramp)
     os.environ["CKM_PIPELINE_TAIL_DIV"] = str(tail)
@@ -37,5 +41,12 @@ for chunk_kb, ramp, tail in ((49152, 12, 8), (49152, 24, 8), (49152, 48, 16), (4
     for _ in range(K):
         g.call_batch_raw(hp_res.value, hp_off.value, batch.n, api.WANT_BEST)
     dt = (time.perf_counter() - t0) / K
-    print(json.dumps(dict(chunk_kb=chunk_kb, ramp_div=ramp, tail_div=tail, e2e_ms=dt * 1e3, proteins_per_s=batch.n / dt)), flush=True)
+    for _ in range(2):
+        g.call_batch_packed_raw(hp_pk.value, hp_woff.value, batch.n, api.WANT_BEST)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        g.call_batch_packed_raw(hp_pk.value, hp_woff.value, batch.n, api.WANT_BEST)
+    dtp = (time.perf_counter() - t0) / K
+    print(json.dumps(dict(chunk_kb=chunk_kb, ramp_div=ramp, tail_div=tail, e2e_ms=dt * 1e3, proteins_per_s=batch.n / dt,
+                          packed_e2e_ms=dtp * 1e3, packed_proteins_per_s=batch.n / dtp)), flush=True)
     g.close()
