@@ -31,7 +31,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if os.path.exists(LIB):
             return LIB  # GPU box without a toolkit would still carry the prebuilt library
         raise RuntimeError(f"nvcc not found at {NVCC} and {LIB} is missing")
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(HERE, s) for s in SOURCES]
+    extra = os.environ.get("CKM_NVCC_EXTRA", "").split()  # e.g. -DCKM_EXPERIMENTS: the A/B kernels and tuning bits (tools/)
+    cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(HERE, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode:
         sys.stderr.write(r.stdout + r.stderr)

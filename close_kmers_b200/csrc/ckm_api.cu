@@ -182,7 +182,12 @@ static int upload_table(ckm_ctx *c, const ckm_image_header_t *hdr) {
     RC(raw.ensure(raw_bytes + 64));
     const size_t chunk = (size_t)1 << 28;
     for (size_t o = 0; o < raw_bytes; o += chunk)
-        CU(cudaMemcpyAsync((uint8_t *)raw.p + o, src + o, std::min(chunk, raw_bytes - o), cudaMemcpyHostToDevice, c->stream));
+        if (int rc = check_cuda(cudaMemcpyAsync((uint8_t *)raw.p + o, src + o, std::min(chunk, raw_bytes - o), cudaMemcpyHostToDevice, c->stream),
+                                "cudaMemcpyAsync(table)")) {
+            cudaStreamSynchronize(c->stream);
+            raw.release();
+            return rc;
+        }
     return install_table(c, raw, n);
 }
 
@@ -190,21 +195,42 @@ static int upload_table(ckm_ctx *c, const ckm_image_header_t *hdr) {
 // occupancy bitmap.  Takes ownership of `raw`.
 static int install_table(ckm_ctx *c, DevBuf raw, uint64_t n) {
     DevBuf packed, flag;
-    RC(packed.ensure((size_t)n * kPackedSlotBytes + 64));
-    RC(flag.ensure(256));
-    CU(cudaMemsetAsync(flag.p, 0, 4, c->stream));
-    if (n) {
-        const uint64_t blocks = (n + 255) / 256;
-        pack_table_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>((const uint64_t *)raw.p, n, (uint4 *)packed.p,
-                                                                    (unsigned int *)flag.p);
-        c->launches++;
-    }
     unsigned int misfit = 0;
-    CU(cudaMemcpyAsync(&misfit, flag.p, 4, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    CU(cudaGetLastError());
-    flag.release();
-    if (misfit || c->force_raw) {
+    // raw + packed need 40 B per bucket for a moment: without room for the packed copy the verbatim slots serve (RAW kernels)
+    bool no_room = !c->force_raw && packed.ensure((size_t)n * kPackedSlotBytes + 64) != 0;
+    if (no_room) {
+        (void)cudaGetLastError();
+        fprintf(stderr, "libckm: no device memory for the 16-byte slots (%s); keeping the 24-byte slots of the image\n", ckm_last_error());
+    }
+    if (!no_room && !c->force_raw) {
+        auto body = [&]() -> int {
+            RC(flag.ensure(256));
+            CU(cudaMemsetAsync(flag.p, 0, 4, c->stream));
+            if (n) {
+                const uint64_t blocks = (n + 255) / 256;
+                pack_table_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>((const uint64_t *)raw.p, n, (uint4 *)packed.p,
+                                                                            (unsigned int *)flag.p);
+                c->launches++;
+            }
+            CU(cudaMemcpyAsync(&misfit, flag.p, 4, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            CU(cudaGetLastError());
+            return 0;
+        };
+        const int rc = body();
+        flag.release();
+        if (rc) {
+            cudaStreamSynchronize(c->stream);
+            packed.release();
+            raw.release();
+            return rc;
+        }
+    } else if (int rc = check_cuda(cudaStreamSynchronize(c->stream), "cudaStreamSynchronize(table upload)")) {
+        packed.release();
+        raw.release();
+        return rc;
+    }
+    if (misfit || c->force_raw || no_room) {
         packed.release();
         c->table = raw;
         c->slot_bytes = kRawSlotBytes;
@@ -370,14 +396,17 @@ static int validate_image(const void *image, size_t bytes, const char *name) {
     if (!image || bytes < sizeof(ckm_image_header_t))
         return ckm_fail(CKM_EFORMAT, "Version mismatch for file %s: file size does not match", name);
     const ckm_image_header_t *h = (const ckm_image_header_t *)image;
-    if ((unsigned long long)bytes != sizeof(ckm_sig_kmer_t) * (unsigned long long)h->num_sigs + sizeof(ckm_image_header_t))
+    // the size check by division: a crafted num_sigs must not wrap sizeof(slot) * num_sigs around to the file size
+    const size_t body = bytes - sizeof(ckm_image_header_t);
+    if (body % sizeof(ckm_sig_kmer_t) != 0 || (unsigned long long)(body / sizeof(ckm_sig_kmer_t)) != (unsigned long long)h->num_sigs)
         return ckm_fail(CKM_EFORMAT, "Version mismatch for file %s: file size does not match", name);
     if (h->version != 1)
         return ckm_fail(CKM_EFORMAT, "Version mismatch for file %s: file has %lld code has %lld", name, (long long)h->version, 1LL);
     if (h->entry_size != sizeof(ckm_sig_kmer_t))
         return ckm_fail(CKM_EFORMAT, "Version mismatch for file %s: file has entry size %lld code has %lld", name,
                         (long long)h->entry_size, (long long)sizeof(ckm_sig_kmer_t));
-    if (h->num_sigs == 0) return ckm_fail(CKM_EFORMAT, "image %s has zero buckets", name);
+    // one bucket: floor(2^64 / 1) does not fit the 64-bit multiplier of fast_mod (ckm_common.cuh); no real image is that small
+    if (h->num_sigs < 2) return ckm_fail(CKM_EFORMAT, "image %s has fewer than two buckets", name);
     return 0;
 }
 
@@ -990,6 +1019,7 @@ extern "C" int ckm_read_totals(ckm_ctx *c, uint64_t totals[3]) {
     CU(cudaMemcpyAsync(t, c->totals.p, 64, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (t[7]) return ckm_fail(CKM_ECUDA, "probe_pc_kernel: a hand-off between probing and scan warps timed out");
+    if (t[6]) return ckm_fail(CKM_EINVAL, "a sequence is longer than the max_len the batch was announced with");
     totals[0] = t[0];
     totals[1] = t[1];
     totals[2] = t[2];
@@ -1209,6 +1239,7 @@ static int call_batch_pipelined(ckm_ctx *c, const char *residues, const uint32_t
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
     if (ht[7]) return ckm_fail(CKM_ECUDA, "probe_pc_kernel: a hand-off between probing and scan warps timed out");
+    if (ht[6]) return ckm_fail(CKM_EINVAL, "a sequence is longer than the max_len the batch was announced with");
     out->n_probes = ht[0];
     out->n_hits = ht[1];
     out->best = (const ckm_best_t *)c->h_best.p;
@@ -1323,6 +1354,7 @@ static int finish_batch(ckm_ctx *c, uint32_t n, uint32_t flags, ckm_batch_out_t 
     CU(cudaMemcpyAsync(ht, c->totals.p, 64, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (ht[7]) return ckm_fail(CKM_ECUDA, "probe_pc_kernel: a hand-off between probing and scan warps timed out");
+    if (ht[6]) return ckm_fail(CKM_EINVAL, "a sequence is longer than the max_len the batch was announced with");
     out->n_probes = ht[0];
     out->n_hits = ht[1];
     const uint64_t n_calls_total = ht[2];

@@ -305,6 +305,12 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
 
     constexpr uint32_t full = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#ifdef CKM_EXPERIMENTS  // ablation (wrong results on purpose): no scan warp, nobody waits -- the probing warps' own pace
+    const bool no_scan = tv.tuning & 0x400000u, no_left = tv.tuning & 0x800000u, no_pub = tv.tuning & 0x1000000u;
+    if (no_scan && warp >= (uint32_t)P) return;
+#else
+    constexpr bool no_scan = false, no_left = false, no_pub = false;
+#endif
     if (warp >= (uint32_t)P) {  // scan warp c serves producers [c * per, (c + 1) * per)
         constexpr uint32_t per = (P + C - 1) / C;
         const uint32_t first = (warp - P) * per;
@@ -331,7 +337,7 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
     // function indices in position order -- into slot (pubc & (kPcDepth - 1u)) once the scan lane has released it.  Returns the
     // step's hit count.
     auto publish = [&](uint32_t hm, uint32_t t0, uint32_t flags, uint32_t index, uint64_t seq_base) -> uint32_t {
-        if (pubc >= kPcDepth) {  // record pubc - kPcDepth consumed?
+        if (pubc >= kPcDepth && !no_scan) {  // record pubc - kPcDepth consumed?
             uint32_t spins = 0;
             while ((int32_t)(sy->done - (pubc - kPcDepth + 1u)) < 0) {
                 if (++spins > kPcSpinLimit || syncs[0].abort) {
@@ -424,6 +430,9 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
             const uint64_t seq_base = __ldg(offsets + i);
             const uint32_t len = (uint32_t)(__ldg(offsets + i + 1) - seq_base);
             uint32_t count = 0;
+            // this kernel runs the scan that assumes no protein can fill the 39 998-hit window: a caller of
+            // ckm_call_batch_device that understated max_len is told so instead of getting indices that silently diverge
+            if (len > kHitCap + CKM_KMER_SIZE && lane == 0) atomicExch(totals + 6, 1ull);
             if (len <= CKM_KMER_SIZE) {
                 publish(0u, 0u, kPcEnd, i, seq_base);
             } else {
@@ -543,7 +552,7 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
                     //      neighbour copy is in use) and scattered over the lanes, so they are queued in shared memory and probed
                     //      one per lane; a queue entry is the key and the window, the home bucket is recomputed and its occupancy
                     //      word re-read (an L1 hit) by the probing lane ----
-                    if (__any_sync(full, need != 0u)) {
+                    if (!no_left && __any_sync(full, need != 0u)) {
                         uint32_t n_left = 0;
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
@@ -592,7 +601,8 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
                         hm |= (sy->found[lane >> 3] >> (4u * (lane & 7u))) & need;
                     }
                     my_probes += __popc(act);
-                    count += publish(hm, t0, last ? kPcEnd : 0u, i, seq_base);
+                    if (no_pub) count += __reduce_add_sync(full, __popc(hm));
+                    else count += publish(hm, t0, last ? kPcEnd : 0u, i, seq_base);
                 }
             }
             if (lane == 0) n_hits[i] = count;

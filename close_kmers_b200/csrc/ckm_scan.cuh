@@ -242,6 +242,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(ScanArgs a) {
     const uint16_t *A = a.hit_avg ? a.hit_avg + base : nullptr;
     uint32_t *S = GENERAL ? a.stored_idx + base : nullptr;
     const uint32_t nh = a.n_hits[i];
+    if (!GENERAL && nh > kHitCap) atomicExch(a.totals + 6, 1ull);  // max_len was understated (ckm_call_batch_device): reported, not ignored
     ckm_call_t *calls = a.calls + call_region_base(base, a.index_base + i, a.prm.min_hits);
     ckm_otu_t *otus = a.otus ? a.otus + base : nullptr;
     const int min_hits = a.prm.min_hits;

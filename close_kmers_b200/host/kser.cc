@@ -226,6 +226,10 @@ struct Mapping {  // one KmerPegMapping: peg ids on the host, postings on engine
     uint32_t post_key = 0;
 };
 
+constexpr int kMaxConnections = 256;                 // concurrent connections (a thread each)
+constexpr int kSocketTimeoutSeconds = 600;           // SO_RCVTIMEO / SO_SNDTIMEO of accepted sockets
+constexpr size_t kMaxMatrixBody = (size_t)4 << 30;   // /matrix buffers the whole body
+
 struct Server {
     Options opt;
     std::vector<std::unique_ptr<Engine>> engines;
@@ -716,10 +720,26 @@ void handle_post(Server &s, Conn &c, const Request &r, const Decision &d) {
             }
         }
     };
+    if (is_matrix && d.content_length > kMaxMatrixBody) {  // /matrix holds the whole request in memory (as the reference does): bounded
+        respond(c, r, 500, "Failed", "Caught exception request body too large\n");
+        return;
+    }
     std::thread worker(work);
+    struct Join {  // whatever leaves this function -- a bad_alloc in the parser included -- closes the queue and joins the worker
+        JobQueue &q;
+        std::thread &t;
+        ~Join() {
+            q.close();
+            if (t.joinable()) t.join();
+        }
+    } join_guard{jobs, worker};
 
     // ---- this thread: socket -> (inflate) -> parser -> batches ----
     ckm_seq_parser *parser = ckm_seq_parser_new(is_fq ? CKM_FORMAT_FASTQ : CKM_FORMAT_FASTA);
+    struct FreeParser {
+        ckm_seq_parser *p;
+        ~FreeParser() { ckm_seq_parser_free(p); }
+    } parser_guard{parser};
     Inflater gz;
     size_t remaining = d.content_length;
     bool first_bytes = true, finished = false, ok = true;
@@ -748,7 +768,6 @@ void handle_post(Server &s, Conn &c, const Request &r, const Decision &d) {
     }
     jobs.close();
     worker.join();
-    ckm_seq_parser_free(parser);
 }
 
 void handle_connection(Server *sp, int fd) {
@@ -941,9 +960,24 @@ extern "C" int ckm_kser_main(int argc, char **argv) {
         if (pf[0].revents & POLLIN) {
             const int fd = accept(lfd, nullptr, nullptr);
             if (fd < 0) continue;
+            if (s.active.load() >= kMaxConnections) {  // one thread per connection: bounded
+                static const char busy[] = "HTTP/1.1 503 Service Unavailable\nContent-type: text/plain\n\nToo many connections\n";
+                ssize_t w = write(fd, busy, sizeof busy - 1);
+                (void)w;
+                close(fd);
+                continue;
+            }
             setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
+            timeval tmo = {kSocketTimeoutSeconds, 0};  // a client that stops sending or reading does not hold a thread for ever
+            setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tmo, sizeof tmo);
+            setsockopt(fd, SOL_SOCKET, SO_SNDTIMEO, &tmo, sizeof tmo);
             s.active++;
-            std::thread(handle_connection, &s, fd).detach();
+            try {
+                std::thread(handle_connection, &s, fd).detach();
+            } catch (const std::system_error &) {
+                s.active--;
+                close(fd);
+            }
         }
     }
     close(lfd);
@@ -952,6 +986,12 @@ extern "C" int ckm_kser_main(int argc, char **argv) {
     if (s.active.load() == 0) {
         for (size_t e = s.engines.size(); e-- > 0;) ckm_close(s.engines[e]->ctx);  // clones first
         for (auto &m : s.mappings) ckm_mapping_free(m.second.ids);
+    }
+    else {
+        // connection threads still hold pointers into `s`, which lives on the caller's stack: do not return underneath them
+        std::cout << std::flush;
+        std::cerr << "kser_b200: " << s.active.load() << " connection(s) still busy after 30 s; exiting\n" << std::flush;
+        _exit(0);
     }
     g_server = nullptr;
     return 0;

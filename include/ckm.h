@@ -200,10 +200,11 @@ uint64_t ckm_packed_words(uint64_t n_residues); /* ceil(5 n / 32) */
 int ckm_pack_residues(const char *residues, const uint64_t *offsets, uint32_t n, uint32_t *packed, uint64_t packed_capacity_words,
                       uint64_t *word_offsets /* n + 1 */);
 
-/* Device-resident form for pipelines that already hold the batch in HBM: d_residues must have 16
- * readable bytes after offsets[n] and offsets[0] must be 0; max_len is the longest sequence (0 = unknown,
- * which selects the general scan kernel).  Results stay on the device (ckm_device_results); the call
- * only enqueues work on ckm_stream(ctx). */
+/* Device-resident form for pipelines that already hold the batch in HBM: d_residues must have 32
+ * readable bytes after offsets[n] (the library's own uploads zero them) and offsets[0] must be 0; max_len is the
+ * longest sequence (0 = unknown, which selects the general scan kernel).  An understated max_len is detected on
+ * the device and reported by the next ckm_read_totals (CKM_EINVAL).  Results stay on the device
+ * (ckm_device_results); the call only enqueues work on ckm_stream(ctx). */
 int ckm_call_batch_device(ckm_ctx *ctx, const void *d_residues, const uint64_t *d_offsets, uint32_t n,
                           uint64_t total_residues, uint32_t max_len, uint32_t flags);
 

@@ -90,3 +90,28 @@ def test_signature_weight_formula(checkers):
     for c in cases:
         got, want = api.signature_weight(*c), R.ref_signature_weight(*c)
         assert np.float32(got).tobytes() == np.float32(want).tobytes(), c
+
+
+def test_image_header_validation_rejects_crafted_sizes():
+    """T2 (kmer_image.cc:87-105) on hostile headers, before any device is touched: a bucket count whose 24 * num_sigs wraps
+    around to the file size, and a one-bucket image (floor(2^64 / 1) does not fit the 64-bit multiplier of key % num_sigs)."""
+    def header(num_sigs, entry=24, version=1):
+        return np.array([num_sigs, entry, version], np.uint64).view(np.uint8)
+
+    body = np.zeros(24 * 4, np.uint8)
+    wrapped = (2**64 + 24 * 4) // 24  # 24 * wrapped == 96 (mod 2^64) only if 24 divided 2^64 + 96; search the next one that does
+    for k in range(1, 25):
+        if (k * 2**64 + 24 * 4) % 24 == 0:
+            wrapped = (k * 2**64 + 24 * 4) // 24
+            break
+    cases = [np.concatenate([header(1), np.zeros(24, np.uint8)]),
+             np.concatenate([header(0), np.zeros(0, np.uint8)]),
+             np.concatenate([header(5), body]),
+             np.concatenate([header(4), body])[:-1]]
+    if wrapped < 2**64:
+        assert (24 * wrapped) % 2**64 == 24 * 4
+        cases.append(np.concatenate([header(wrapped), body]))
+    for bad in cases:
+        with pytest.raises(api.CkmError) as ei:
+            api.KmerGuts(image=np.ascontiguousarray(bad))
+        assert ei.value.code == -3, ei.value
