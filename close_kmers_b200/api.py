@@ -92,6 +92,7 @@ def lib() -> C.CDLL:
     L.ckm_set_tuning.argtypes = [C.c_void_p, C.c_uint32]
     L.ckm_last_batch_was_fused.argtypes = [C.c_void_p]
     L.ckm_chain_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.ckm_copy_state.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
     L.ckm_set_default_params.argtypes = [C.c_void_p]
     L.ckm_set_params.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     L.ckm_get_params.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
@@ -478,6 +479,13 @@ class KmerGuts:
     @property
     def has_occupancy_bitmap(self) -> bool:
         return bool(lib().ckm_has_occupancy_bitmap(self._h))
+
+    @property
+    def copy_state(self) -> dict:
+        """Automatic fall-back of K1 from the neighbour copy to plain hash probing (ckm_copy_state)."""
+        st = (C.c_uint32 * 3)()
+        _check(lib().ckm_copy_state(self._h, st))
+        return {"suspended": bool(st[0]), "retry_in": int(st[1]), "suspensions": int(st[2])}
 
     @property
     def chain_info(self) -> dict:

@@ -623,10 +623,17 @@ extern "C" int ckm_chain_info(ckm_ctx *c, uint64_t info[4]) {
     info[1] = c->n_chains;
     info[2] = (uint64_t)(c->chain_build_ms * 1000.0);
     info[3] = 0;
-    if (c->totals.p && c->n_chain) {
+    if (c->totals.p && c->n_chain && c->last_used_copy) {
         CU(cudaMemcpyAsync(&info[3], (const uint64_t *)c->totals.p + 4, 8, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
     }
+    return 0;
+}
+extern "C" int ckm_copy_state(const ckm_ctx *c, uint32_t state[3]) {
+    if (!c || !state) return ckm_fail(CKM_EINVAL, "NULL argument");
+    state[0] = c->copy_suspended ? 1u : 0u;
+    state[1] = c->copy_retry_in;
+    state[2] = c->copy_suspensions;
     return 0;
 }
 extern "C" void *ckm_stream(ckm_ctx *c) { return (void *)c->stream; }
@@ -815,11 +822,37 @@ static bool use_neighbour_copy(const ckm_ctx *c) {
     return c->slot_bytes == kPackedSlotBytes && c->n_chain && !(c->tuning & CKM_TUNE_PLAIN_PROBE) && !c->copy_suspended;
 }
 
+// Automatic fall-back from the neighbour copy to plain hash probing.  The copy pays when a good part of a batch's probes is
+// answered from it (dense signature sets: 0.59 of C2's probes, K1 4.0 ms against 6.7); when the signatures are a sparse
+// subset of the windows the chains are a k-mer or two long, hints lead nowhere and the hinted step only adds work
+// (profiles/r2/sparse_worlds.jsonl: break-even at ~0.12 of the probes).  So every batch that went through the copy and whose
+// counters reach the host is judged: below kCopyMinShare the copy is suspended for `backoff` batches (16, doubling up to
+// 1024 while it keeps failing), then tried again on one batch.  Results never depend on the path; CKM_TUNE_NO_FALLBACK pins it.
+constexpr uint64_t kCopyJudgeMinProbes = 200000;  // smaller batches say too little
+constexpr double kCopyMinShare = 0.12;
+static void adapt_probe_path(ckm_ctx *c, uint64_t probes, uint64_t from_copy) {
+    if (!c->n_chain || (c->tuning & (CKM_TUNE_NO_FALLBACK | CKM_TUNE_PLAIN_PROBE))) return;
+    if (c->copy_suspended) {
+        if (c->copy_retry_in == 0 || --c->copy_retry_in == 0) c->copy_suspended = false;  // the next batch is the retry
+        return;
+    }
+    if (!c->last_used_copy || probes < kCopyJudgeMinProbes) return;
+    if ((double)from_copy < kCopyMinShare * (double)probes) {
+        c->copy_suspended = true;
+        c->copy_retry_in = c->copy_backoff;
+        c->copy_backoff = std::min<uint32_t>(c->copy_backoff * 2, 1024);
+        c->copy_suspensions++;
+    } else {
+        c->copy_backoff = 16;
+    }
+}
+
 // K1 (+ K2) for sequences [i0, i0+cnt) of the batch on `stream`
 static int launch_range(ckm_ctx *c, cudaStream_t stream, const uint8_t *d_res, const uint64_t *d_off, uint32_t i0, uint32_t cnt,
                         uint32_t flags, const RunPlan &plan, ckm_ctx::ProfEv *pe) {
     if (cnt == 0) return 0;
     c->last_fused = plan.fused;
+    c->last_used_copy = plan.probe_group >= 32u && use_neighbour_copy(c);
     const TableView tv = table_view(c);
     const bool packed = c->slot_bytes == kPackedSlotBytes;
     FusedArgs fa;
@@ -1020,6 +1053,7 @@ extern "C" int ckm_read_totals(ckm_ctx *c, uint64_t totals[3]) {
     CU(cudaStreamSynchronize(c->stream));
     if (t[7]) return ckm_fail(CKM_ECUDA, "probe_pc_kernel: a hand-off between probing and scan warps timed out");
     if (t[6]) return ckm_fail(CKM_EINVAL, "a sequence is longer than the max_len the batch was announced with");
+    adapt_probe_path(c, t[0], t[4]);
     totals[0] = t[0];
     totals[1] = t[1];
     totals[2] = t[2];
@@ -1240,6 +1274,7 @@ static int call_batch_pipelined(ckm_ctx *c, const char *residues, const uint32_t
     CU(cudaGetLastError());
     if (ht[7]) return ckm_fail(CKM_ECUDA, "probe_pc_kernel: a hand-off between probing and scan warps timed out");
     if (ht[6]) return ckm_fail(CKM_EINVAL, "a sequence is longer than the max_len the batch was announced with");
+    adapt_probe_path(c, ht[0], ht[4]);
     out->n_probes = ht[0];
     out->n_hits = ht[1];
     out->best = (const ckm_best_t *)c->h_best.p;
@@ -1355,6 +1390,7 @@ static int finish_batch(ckm_ctx *c, uint32_t n, uint32_t flags, ckm_batch_out_t 
     CU(cudaStreamSynchronize(c->stream));
     if (ht[7]) return ckm_fail(CKM_ECUDA, "probe_pc_kernel: a hand-off between probing and scan warps timed out");
     if (ht[6]) return ckm_fail(CKM_EINVAL, "a sequence is longer than the max_len the batch was announced with");
+    adapt_probe_path(c, ht[0], ht[4]);
     out->n_probes = ht[0];
     out->n_hits = ht[1];
     const uint64_t n_calls_total = ht[2];

@@ -38,8 +38,8 @@ struct ckm_ctx {
     // automatic fall-back of K1 from the neighbour copy to plain hash probing (see ckm_api.cu: adapt_probe_path)
     bool last_fused = false;  // the last batch went through probe_pc_kernel
     uint64_t pc_seq = 0;  // launches of probe_pc_kernel so far (picks the work counter)
-    bool copy_suspended = false;
-    uint32_t copy_retry_in = 0;
+    bool copy_suspended = false, last_used_copy = false;
+    uint32_t copy_retry_in = 0, copy_backoff = 16, copy_suspensions = 0;
     int l2_fetch = 0;  // cudaLimitMaxL2FetchGranularity in effect
 
     // signature table in HBM

@@ -32,22 +32,22 @@
 
 namespace ckm {
 
-constexpr uint32_t kPcEnd = 1u;     // the protein ends with this record
-constexpr uint32_t kPcFin = 2u;     // the producer has no more work
-constexpr uint32_t kPcOneRun = 4u;  // all hits of the step share one function index
+constexpr uint32_t kPcEnd = 1u;    // the protein ends with this record
+constexpr uint32_t kPcFin = 2u;    // the producer has no more work
+constexpr uint32_t kPcEmit = 4u;   // after the record's weights: the run is over, a call is due if its weighted sum suffices
+constexpr uint32_t kPcReset = 8u;  // after the record's weights: the run is over without a call
 constexpr int kPcProducers = 31;    // probing warps per block: 31 + 1 scan warp = 1 024 threads x 64 registers fill an SM
 constexpr uint32_t kPcChunk = 4u;   // sequences claimed per atomic
-constexpr uint32_t kPcDepth = 2u;   // published steps a producer may be ahead of its scan lane
+constexpr uint32_t kPcDepth = 2u;   // published records a producer may be ahead of its scan lane
 constexpr uint32_t kPcSpinLimit = 1u << 21;  // polls (a few tenths of a second) before a hand-off is declared stuck
 
-// One published step.  `hits` bit e: window t0 + e hit.  `starts` is the subset of `hits` that begin a run: the step's first
-// hit and every hit whose function index differs from the hit before it.  The payload of the step -- weight and function index
-// of every hit, in position order -- is in the W / FI arrays of the same slot (record number % kPcDepth).
+// One published record: "add these n_w weights to the run's sum, in this order; then, if the flags say so, the run is over".
+// The weights are in the W array of the same slot (record number % kPcDepth).  The call fields describe the run that ends
+// (kPcEmit): everything of a call but its weighted sum, which only the scan lane knows.
 struct __align__(16) PcRecord {
-    uint32_t hits[4];
-    uint32_t starts[4];
-    uint32_t t0, flags, index, n;
-    uint64_t seq_base, pad_;
+    uint32_t n_w, flags, index, count;
+    uint32_t start, end, fI, pad_;
+    uint64_t seq_base, pad2_;
 };
 struct __align__(16) PcSync {
     volatile uint32_t pub;    // records published (written by the producer)
@@ -56,19 +56,30 @@ struct __align__(16) PcSync {
     uint32_t pad_;
     uint32_t found[4];        // producer-private: left-over windows of the step whose hash probe hit
 };
-static_assert(sizeof(PcRecord) == 64 && sizeof(PcSync) == 32, "shared-memory layout");
+// The run state of KmerGuts::gather_hits that decides control flow (kguts.cc:816-856), carried by the probing warp from step to
+// step (warp-uniform; parked in shared memory between steps): everything but the weighted sum.
+struct __align__(16) PcRun {
+    uint32_t cur, num, cnt, first;            // current_fI, stored hits, matching hits, position of the run's first hit
+    uint32_t lastm, p1_pos, p1_fI, p1_wt;     // last matching position; the newest stored hit
+};
+static_assert(sizeof(PcRecord) == 48 && sizeof(PcSync) == 32 && sizeof(PcRun) == 32, "shared-memory layout");
 
-// Dynamic shared memory of a block with P producers:
-//   residue LUT | sync[P] | records[P][D] | queue[P][128] (8 B: key, window) | stage[P][128] (8 B: weight, function word) | W[P][D][128] | FI[P][D][128]
-//   | land[P][2][20] (residue string of the neighbour copy behind the step)
-// 4.2 KB per producer, as much as probe_hint_kernel uses per warp -- on purpose: what shared memory takes, the L1 loses, and
-// this kernel lives on its L1 (with the carve-out at its maximum probe_hint_kernel itself takes 7.1 ms per C2 step instead
-// of 4.0; profiles/r2/carveout_ab.jsonl).
-constexpr uint32_t kPcWSlot = kTile + 4;  // weights of a step + zero padding (the scan lane adds them four at a time)
+constexpr uint32_t kPcWSlot = kTile + 8;  // weights of a record: a step's hits, one carried over from the step before, zero padding
 constexpr uint32_t kPcLandWords = 20;  // residue bytes of the neighbour copy behind one 64-window half of a step: 64 + 7 (+3 of alignment)
-constexpr size_t kPcPerProducer = sizeof(PcSync) + kPcDepth * sizeof(PcRecord) + kTile * sizeof(uint2) + kTile * sizeof(uint2) +
-                                  kPcDepth * (kPcWSlot + kTile) * 4 + 2 * kPcLandWords * 4;
-constexpr size_t pc_smem_bytes(int P) { return 256 + (size_t)P * kPcPerProducer; }
+// Everything a probing warp and its scan lane share, in one block of shared memory: a single base register addresses all of
+// it (the kernel runs at the 64-register limit of a 1 024-thread block).  3.4 KB per producer -- what shared memory takes, the L1
+// loses, and this kernel lives on its L1 (with the carve-out at its maximum probe_hint_kernel itself takes 7.1 ms per C2 step
+// instead of 4.0; profiles/r2/k1_experiments.md).
+struct __align__(16) PcWarp {
+    PcSync sync;
+    PcRun run;
+    PcRecord rec[kPcDepth];
+    uint2 queue[kTile];  // left-over windows of the step: (key low word, key high bits | window << 8)
+    uint2 stage[kTile];  // (weight bits, word 3 of the packed slot) behind each window of the step that hit
+    float W[kPcDepth][kPcWSlot];
+    uint32_t land[2][kPcLandWords];  // residue string of the neighbour copy behind each half of the step
+};
+constexpr size_t pc_smem_bytes(int P) { return 256 + (size_t)P * sizeof(PcWarp); }
 
 // floor(off / max(1, min_hits)) by a multiply: exact for off < 2^64 / min_hits (call_region_base, ckm_scan.cuh)
 static inline uint64_t call_region_magic(int min_hits) { return min_hits > 1 ? ~0ull / (uint64_t)min_hits + 1ull : 0ull; }
@@ -80,94 +91,35 @@ __device__ __forceinline__ uint64_t call_region_base_fast(uint64_t off, uint32_t
 // ones per instruction (the asynchronous copy); XOR-ing the low four bits with the next three keeps both conflict-free
 __device__ __forceinline__ uint32_t stage8_at(uint32_t e) { return e ^ ((e >> 4) & 15u); }
 
-// 128-bit window masks of a step
-struct M128 {
-    uint64_t lo, hi;
-};
-__device__ __forceinline__ bool m_any(const M128 &m) { return (m.lo | m.hi) != 0ull; }
-__device__ __forceinline__ uint32_t m_first(const M128 &m) { return m.lo ? __ffsll((long long)m.lo) - 1 : 63 + __ffsll((long long)m.hi); }
-__device__ __forceinline__ uint32_t m_last(const M128 &m) { return m.hi ? 127 - __clzll((long long)m.hi) : 63 - __clzll((long long)m.lo); }
-__device__ __forceinline__ uint32_t m_count(const M128 &m) { return __popcll(m.lo) + __popcll(m.hi); }
-__device__ __forceinline__ M128 m_below(uint32_t n) {  // bits [0, n), n <= 128
-    M128 r;
-    r.lo = n >= 64u ? ~0ull : ((1ull << n) - 1ull);
-    r.hi = n <= 64u ? 0ull : (n >= 128u ? ~0ull : ((1ull << (n - 64u)) - 1ull));
-    return r;
-}
-__device__ __forceinline__ M128 m_and(const M128 &a, const M128 &b) { return M128{a.lo & b.lo, a.hi & b.hi}; }
-__device__ __forceinline__ M128 m_andnot(const M128 &a, const M128 &b) { return M128{a.lo & ~b.lo, a.hi & ~b.hi}; }
-__device__ __forceinline__ void m_drop_first(M128 &m) {
-    if (m.lo) m.lo &= m.lo - 1ull;
-    else m.hi &= m.hi - 1ull;
-}
-__device__ __forceinline__ void m_drop_last(M128 &m) {
-    if (m.hi) m.hi &= ~(1ull << (63 - __clzll((long long)m.hi)));
-    else m.lo &= ~(1ull << (63 - __clzll((long long)m.lo)));
-}
-
-// The scan warp.  Lane w < P serves producer w.  A record is taken run by run: the first hits of a run go through rs_hit one
-// at a time until the run's function is the current one (two hits at most: kguts.cc:852-856 flushes on the second and the
-// carry-over makes it current); from there on every further hit of the run does nothing but num++, count++, weight added,
-// last position -- applied in bulk, the weights added in order.  (With max_gap < 127 a gap can fall between two hits of one
-// step, and every hit takes rs_hit.)  find_best_call of a protein with a single call is made here from registers; proteins
-// with several calls (a tenth of C2's) are left to best_fixup_kernel so that their long, divergent walk does not hold up
-// the other lanes.  What counts here is the length of the longest path through one iteration, not the work per record: the lanes
-// run in lockstep and a producer waits for its lane once it is two steps ahead (a separate shorter path for one-run
-// records made the iteration longer -- both paths are walked whenever one lane needs the general one -- and K1 8 % slower;
-// more scan warps cost probing warps, 1.6 % each: profiles/r2/k1_experiments.md).
+// The scan warp.  Lane w < P serves producer w.  The probing warp has already run the control part of the state machine
+// (which hits count for the current run, where runs end: pc_scan_step below); what is left for a thread is what only a thread
+// can do bit-exactly -- the f32 sum of a run's matching weights in hit order (kguts.cc:744-751) -- and, where a run ends, the
+// test of that sum against min_weighted_hits, the call record, and at the end of the protein find_best_call of a single
+// call (proteins with several calls, a tenth of C2's, are left to best_fixup_kernel so that their long, divergent walk does
+// not hold up the other lanes).  One record per iteration and lane; the lanes run in lockstep, so the iteration is as long
+// as the longest record -- at most a step's hits -- whatever the mix of functions among the hits.
 // first / count: the producers this scan warp serves
-__device__ __forceinline__ void pc_consume(PcSync *syncs, const PcRecord *recs, const float *wts, const uint32_t *fis, uint32_t lane,
-                                           uint32_t first, uint32_t count, uint32_t index_base, const FusedArgs &fa,
-                                           unsigned long long *totals) {
+__device__ __forceinline__ void pc_consume(PcWarp *warps, uint32_t lane, uint32_t first, uint32_t count, uint32_t index_base,
+                                           const FusedArgs &fa, unsigned long long *totals) {
     constexpr uint32_t full = 0xffffffffu;
     const bool mine = lane < count;
-    const uint32_t w = first + (mine ? lane : 0u);
-    PcSync *sy = syncs + w;
-    const PcRecord *recD = recs + kPcDepth * w;
-    const float *wtsD = wts + (size_t)w * kPcDepth * kPcWSlot;
-    const uint32_t *fisD = fis + (size_t)w * kPcDepth * kTile;
-    const float *W = wtsD;
-    const uint32_t *FI = fisD;
-    const bool per_hit = fa.prm.max_gap < kTile - 1;
-    bool fin = !mine, have = false, at_start = true;
-    uint32_t seen = 0, t0 = 0, flags = 0, index = 0, n = 0, k = 0, my_calls = 0, idle = 0;
-    M128 H = {0ull, 0ull}, R = {0ull, 0ull};
+    PcWarp *me = warps + first + (mine ? lane : 0u);
+    PcSync *sy = &me->sync;
+    PcSync *sy0 = &warps[0].sync;
+    const float min_weighted = (float)fa.prm.min_weighted_hits;
+    bool fin = !mine, at_start = true;
+    uint32_t seen = 0, my_calls = 0, idle = 0, nc = 0;
+    float ws = 0.0f;
     ckm_call_t *calls = nullptr;
-    RunState S;
-    rs_begin(S);
+    uint32_t c_fI = 0;  // the last call emitted: find_best_call of a single call needs no memory
+    int32_t c_count = 0;
+    float c_weighted = 0.0f;
     while (!__all_sync(full, fin)) {
-        if (!fin && !have && sy->pub != seen) {
-            __threadfence_block();
-            const uint32_t slot = seen & (kPcDepth - 1u);
-            const PcRecord *r = recD + slot;
-            const uint4 mh = *reinterpret_cast<const uint4 *>(r->hits);
-            const uint4 ms = *reinterpret_cast<const uint4 *>(r->starts);
-            const uint4 q = *reinterpret_cast<const uint4 *>(&r->t0);
-            H.lo = (uint64_t)mh.x | ((uint64_t)mh.y << 32);
-            H.hi = (uint64_t)mh.z | ((uint64_t)mh.w << 32);
-            R.lo = (uint64_t)ms.x | ((uint64_t)ms.y << 32);
-            R.hi = (uint64_t)ms.z | ((uint64_t)ms.w << 32);
-            t0 = q.x;
-            flags = q.y;
-            index = q.z;
-            n = q.w;
-            k = 0;
-            W = wtsD + slot * kPcWSlot;
-            FI = fisD + slot * kTile;
-            if (flags & kPcFin) {
-                fin = true;
-            } else {
-                have = true;
-                if (at_start) {
-                    calls = fa.calls + call_region_base_fast(r->seq_base, index_base + index, fa.call_magic);
-                    at_start = false;
-                }
-            }
-        }
+        const bool have = !fin && sy->pub != seen;
         if (!__any_sync(full, have)) {  // nothing published anywhere: leave the issue slots to the producers
-            if (++idle > kPcSpinLimit || syncs[0].abort) {
+            if (++idle > kPcSpinLimit || sy0->abort) {
                 if (lane == 0) atomicExch(totals + 7, 1ull);
-                syncs[0].abort = 1u;
+                sy0->abort = 1u;
                 break;
             }
             __nanosleep(100);
@@ -175,65 +127,46 @@ __device__ __forceinline__ void pc_consume(PcSync *syncs, const PcRecord *recs, 
         }
         idle = 0;
         if (have) {
-            if (k < n) {  // ---- one run ----
-                M128 run = H;
-                uint32_t L = n;
-                if (!(flags & kPcOneRun)) {
-                    const uint32_t s = m_first(H);
-                    R = m_andnot(R, m_below(s + 1u));
-                    const uint32_t nxt = m_any(R) ? m_first(R) : (uint32_t)kTile;
-                    run = m_and(H, m_below(nxt));
-                    H = m_andnot(H, run);
-                    L = m_count(run);
+            __threadfence_block();
+            const uint32_t slot = seen & (kPcDepth - 1u);
+            const PcRecord *r = &me->rec[slot];
+            const uint4 q = *reinterpret_cast<const uint4 *>(&r->n_w);  // n_w, flags, index, count
+            if (q.y & kPcFin) {
+                fin = true;
+            } else {
+                if (at_start) {
+                    calls = fa.calls + call_region_base_fast(r->seq_base, index_base + q.z, fa.call_magic);
+                    at_start = false;
                 }
-                const uint32_t G = FI[k];
-                uint32_t i = 0;
-                do {
-                    const uint32_t e = m_first(run);
-                    m_drop_first(run);
-                    rs_hit(S, fa.prm, t0 + e, G, W[k + i], calls);
-                    i++;
-                } while (i < L && (per_hit || !(S.num > 0 && S.cur_fI == G)));
-                if (i < L) {  // the rest of the run in bulk
-                    const uint32_t r = L - i;
-                    float ws = S.wsum;
-                    uint32_t x = k + i;
-                    const uint32_t xe = k + L;
-                    for (; (x & 3u) && x < xe; x++) ws += W[x];
-                    for (; x + 4u <= xe; x += 4u) {
-                        const float4 v = *reinterpret_cast<const float4 *>(W + x);
-                        ws += v.x;
-                        ws += v.y;
-                        ws += v.z;
-                        ws += v.w;
-                    }
-                    for (; x < xe; x++) ws += W[x];
-                    S.wsum = ws;
-                    S.num += r;
-                    S.fI_count += (int32_t)r;
-                    const uint32_t pl = t0 + m_last(run);
-                    S.last_match_pos = pl;
-                    if (r >= 2u) {
-                        m_drop_last(run);
-                        S.p2_pos = t0 + m_last(run);
-                        S.p2_fI = G;
-                        S.p2_wt = W[xe - 2u];
-                    } else {
-                        S.p2_pos = S.p1_pos;
-                        S.p2_fI = S.p1_fI;
-                        S.p2_wt = S.p1_wt;
-                    }
-                    S.p1_pos = pl;
-                    S.p1_fI = G;
-                    S.p1_wt = W[xe - 1u];
+                const float *W = me->W[slot];
+                float s = ws;
+                for (uint32_t x = 0; x < q.x; x += 4u) {  // padded with +0 up to a multiple of four: x + (+0) == x
+                    const float4 v = *reinterpret_cast<const float4 *>(W + x);
+                    s += v.x;
+                    s += v.y;
+                    s += v.z;
+                    s += v.w;
                 }
-                k += L;
-            }
-            if (k >= n) {
-                if (flags & kPcEnd) {
-                    if ((int)S.num >= fa.prm.min_hits) rs_flush(S, fa.prm, calls);
-                    const uint32_t nc = S.n_calls;
-                    fa.n_calls[index] = nc;
+                ws = s;
+                if (q.y & (kPcEmit | kPcReset)) {  // process_set_of_hits, kguts.cc:753-759 (the count test was made by the producer)
+                    if ((q.y & kPcEmit) && ws >= min_weighted) {
+                        const uint4 cf = *reinterpret_cast<const uint4 *>(&r->start);  // start, end, fI
+                        ckm_call_t c;
+                        c.start = cf.x;
+                        c.end = cf.y;
+                        c.count = (int32_t)q.w;
+                        c.function_index = cf.z;
+                        c.weighted_hits = ws;
+                        calls[nc] = c;
+                        c_fI = cf.z;
+                        c_count = (int32_t)q.w;
+                        c_weighted = ws;
+                        nc++;
+                    }
+                    ws = 0.0f;
+                }
+                if (q.y & kPcEnd) {
+                    fa.n_calls[q.z] = nc;
                     if (fa.best && nc <= 1u) {  // several calls: best_fixup_kernel
                         ckm_best_t b;
                         b.function_index = -1;
@@ -244,20 +177,20 @@ __device__ __forceinline__ void pc_consume(PcSync *syncs, const PcRecord *recs, 
                             b.flags = CKM_BEST_HAS_CALLS;
                             Top2 top;
                             top.n = 0;
-                            const FScore fs = {(int)S.c_fI, S.c_count, S.c_weighted};
+                            const FScore fs = {(int)c_fI, c_count, c_weighted};
                             top.push(fs);
                             best_from_top2(top, b);
                         }
-                        fa.best[index] = b;
+                        fa.best[q.z] = b;
                     }
                     my_calls += nc;
-                    rs_begin(S);
+                    nc = 0;
+                    ws = 0.0f;
                     at_start = true;
                 }
-                __threadfence_block();  // the payload reads above come before the release of the slot
-                sy->done = ++seen;
-                have = false;
             }
+            __threadfence_block();  // the payload reads above come before the release of the slot
+            sy->done = ++seen;
         }
     }
 #pragma unroll
@@ -288,18 +221,14 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
                 unsigned long long *__restrict__ work) {
     extern __shared__ __align__(16) uint8_t pc_smem[];
     uint8_t *lut = pc_smem;
-    PcSync *syncs = reinterpret_cast<PcSync *>(pc_smem + 256);
-    PcRecord *recs = reinterpret_cast<PcRecord *>(syncs + P);
-    uint2 *queues = reinterpret_cast<uint2 *>(recs + kPcDepth * P);
-    uint2 *stages = queues + P * kTile;
-    float *wts = reinterpret_cast<float *>(stages + P * kTile);
-    uint32_t *fis = reinterpret_cast<uint32_t *>(wts + (size_t)P * kPcDepth * kPcWSlot);
-    uint32_t *lands = fis + (size_t)P * kPcDepth * kTile;
+    PcWarp *warps = reinterpret_cast<PcWarp *>(pc_smem + 256);
     fill_aa_lut(lut);
     if (threadIdx.x < P) {
-        syncs[threadIdx.x].pub = 0;
-        syncs[threadIdx.x].done = 0;
-        syncs[threadIdx.x].abort = 0;
+        warps[threadIdx.x].sync.pub = 0;
+        warps[threadIdx.x].sync.done = 0;
+        warps[threadIdx.x].sync.abort = 0;
+        warps[threadIdx.x].run.num = 0;
+        warps[threadIdx.x].run.cnt = 0;
     }
     __syncthreads();
 
@@ -314,17 +243,17 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
     if (warp >= (uint32_t)P) {  // scan warp c serves producers [c * per, (c + 1) * per)
         constexpr uint32_t per = (P + C - 1) / C;
         const uint32_t first = (warp - P) * per;
-        pc_consume(syncs, recs, wts, fis, lane, first, first < (uint32_t)P ? min(per, (uint32_t)P - first) : 0u, index_base, fa, totals);
+        pc_consume(warps, lane, first, first < (uint32_t)P ? min(per, (uint32_t)P - first) : 0u, index_base, fa, totals);
         return;
     }
 
-    PcSync *sy = syncs + warp;
-    PcRecord *recD = recs + kPcDepth * warp;
-    uint2 *queue = queues + warp * kTile;  // left-over windows of the step: (key low word, key high bits | window << 8)
-    uint2 *stage = stages + warp * kTile;  // (weight bits, word 3 of the packed slot) behind each window of the step that hit
-    float *wtsD = wts + (size_t)warp * kPcDepth * kPcWSlot;
-    uint32_t *fisD = fis + (size_t)warp * kPcDepth * kTile;
-    uint32_t *land = lands + (size_t)warp * 2 * kPcLandWords;
+    PcWarp *const me = warps + warp;
+    PcSync *const sy = &me->sync;
+    PcSync *const sy0 = &warps[0].sync;
+    uint2 *const queue = me->queue;
+    uint2 *const stage = me->stage;
+    PcRun *const run = &me->run;
+    uint32_t *const land = &me->land[0][0];
     uint32_t pubc = 0;  // records this warp has published
     const uint32_t lt = (1u << lane) - 1u;
     const uint4 *__restrict__ slots = reinterpret_cast<const uint4 *>(tv.slots);
@@ -333,86 +262,263 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
     const uint64_t pol_first = policy_evict_first();
     const uint32_t m35 = tv.m35;
 
-    // hm: this lane's windows that hit (their slots are in `stage`).  Publishes the step -- hit mask, run starts, weights and
-    // function indices in position order -- into slot (pubc & (kPcDepth - 1u)) once the scan lane has released it.  Returns the
-    // step's hit count.
-    auto publish = [&](uint32_t hm, uint32_t t0, uint32_t flags, uint32_t index, uint64_t seq_base) -> uint32_t {
+    const uint32_t max_gap = (uint32_t)fa.prm.max_gap;
+    const int min_hits = fa.prm.min_hits;
+
+    // waits until the scan lane has released the slot record number pubc goes into
+    auto wait_slot = [&]() {
         if (pubc >= kPcDepth && !no_scan) {  // record pubc - kPcDepth consumed?
             uint32_t spins = 0;
             while ((int32_t)(sy->done - (pubc - kPcDepth + 1u)) < 0) {
-                if (++spins > kPcSpinLimit || syncs[0].abort) {
+                if (++spins > kPcSpinLimit || sy0->abort) {
                     if (lane == 0) atomicExch(totals + 7, 1ull);
-                    syncs[0].abort = 1u;
+                    sy0->abort = 1u;
                     break;
                 }
                 __nanosleep(200);
             }
             __threadfence_block();
         }
-        const uint32_t slot = pubc & (kPcDepth - 1u);
-        PcRecord *r = recD + slot;
-        float *W = wtsD + slot * kPcWSlot;
-        uint32_t *FI = fisD + slot * kTile;
-        uint32_t n_step = 0, rs = 0, n_runs = 0;
+    };
+    // the entry of `stage` behind window e of the step: (weight bits, function index)
+    auto staged = [&](uint32_t e) -> uint2 {
+        const uint2 z = stage[stage8_at(e)];
+        return make_uint2(z.x, z.y & (kPackedFieldLimit - 1));
+    };
+
+    // One step's hits through the CONTROL part of gather_hits (kguts.cc:816-856, 873-876) -- in parallel.  hm: this lane's
+    // windows that hit (their (weight, function word) are in `stage`).  The state machine's decisions depend on the hits'
+    // function indices and positions only, and they have a closed form.  With "pair" = two consecutive hits of one run with
+    // the same function:
+    //   * a run begins at the first hit ever and at every hit that follows a gap of more than max_gap (821-836);
+    //   * current_fI after a hit = the function of the latest run-begin hit or pair up to it (a pair of another function than
+    //     current_fI is what ends a run, 852-856, and the carry-over, 772-777, makes the pair's function the current one);
+    //   * a hit counts for its run when its function is current_fI, and the first hit of a run-ending pair counts for the NEW
+    //     run (carried over), which it begins.
+    // So the warp marks run beginnings and matching hits with two short per-lane walks joined by ballots and shuffles, cuts
+    // the step at the run beginnings (none in nearly every step) and publishes, per piece, the matching weights in order --
+    // the one thing that must be done serially, by the scan lane: "add these n_w weights to the run's sum; then, if the flags
+    // say so, the run is over".  Hits of other functions scattered through a run cost nothing extra.  In nearly every step all
+    // hits are of the run's own function (`simple`) and none of the walks is made.  Returns the step's hit count.
+    auto scan_step = [&](uint32_t hm, uint32_t t0, bool last, uint32_t index, uint64_t seq_base) -> uint32_t {
         const uint32_t anyb = __ballot_sync(full, hm != 0u);
+        if (!anyb && !last) return 0u;  // nothing the scan lane needs to hear of
+        const uint4 sa = *reinterpret_cast<const uint4 *>(&run->cur);
+        uint32_t cur = sa.x, num = sa.y, cnt = sa.z, first = sa.w, lastm = run->lastm;
+        uint32_t n_step = 0, addm = 0, startm = 0, beginm = 0, lo = 0xFu;  // lo: this lane's windows not yet accounted for
+        uint32_t e_last = 0;  // the step's last hit (window index)
+        bool pre = false;     // the step's first hit completes a run-ending pair with the last hit of the step before
+        bool simple = false;
         if (anyb) {
-            uint32_t fi[4] = {0u, 0u, 0u, 0u}, wz[4] = {0u, 0u, 0u, 0u}, lastf = 0;
+            uint32_t fi[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (hm & (1u << j)) {
-                    const uint2 zw = stage[stage8_at(4u * lane + j)];
-                    wz[j] = zw.x;
-                    fi[j] = zw.y & (kPackedFieldLimit - 1);
-                    lastf = fi[j];
+            for (int j = 0; j < 4; j++) fi[j] = staged(4u * lane + j).y;  // (whatever is there for windows that did not hit)
+            const uint32_t fl = __ffs(anyb) - 1u, ll = 31u - __clz(anyb);  // first / last lane with a hit
+            n_step = __reduce_add_sync(full, __popc(hm));
+            const uint32_t e0 = 4u * fl + (__ffs(__shfl_sync(full, hm, fl)) - 1u);
+            e_last = 4u * ll + (31u - __clz(__shfl_sync(full, hm, ll)));
+            // Nearly every step: all hits of one function, which is the run's (or there is no run yet), and no gap in front
+            const uint32_t F0 = staged(e0).y;
+            const uint32_t neq = (fi[0] != F0 ? 1u : 0u) | (fi[1] != F0 ? 2u : 0u) | (fi[2] != F0 ? 4u : 0u) | (fi[3] != F0 ? 8u : 0u);
+            simple = fa.prm.max_gap >= (int)kTile - 1 && !__any_sync(full, (neq & hm) != 0u) &&  // (a negative max_gap wraps: every hit a gap)
+                     (num == 0u || (F0 == cur && !((uint32_t)(run->p1_pos + max_gap) < t0 + e0)));
+            if (simple) {
+                addm = hm;
+                if (num == 0u) {  // 833-836
+                    cur = F0;
+                    first = t0 + e0;
                 }
-            // run starts: a hit whose function index differs from the hit before it (or that has none before it in this step)
-            const uint32_t below = anyb & lt;
-            uint32_t pf = __shfl_sync(full, lastf, below ? 31 - __clz(below) : 0);
-            bool hp = below != 0u;
+                num += n_step;
+                cnt += n_step;
+                lastm = t0 + e_last;
+            } else {
+                const uint32_t wbase = t0 + 4u * lane;
+                const uint32_t my_last_pos = wbase + (hm ? 31u - __clz(hm) : 0u);
+                uint32_t lastf = 0;
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (hm & (1u << j)) {
-                    if (!hp || fi[j] != pf) rs |= 1u << j;
-                    pf = fi[j];
-                    hp = true;
+                for (int j = 0; j < 4; j++)
+                    if (hm & (1u << j)) lastf = fi[j];
+                // the hit before this lane's first one: the last hit of the nearest lane below that has one, else the one carried in
+                const uint32_t below = anyb & lt;
+                const uint32_t src = below ? 31u - __clz(below) : 0u;
+                uint32_t qF = __shfl_sync(full, lastf, src), qP = __shfl_sync(full, my_last_pos, src);
+                bool qh = true;
+                if (!below) {
+                    qF = run->p1_fI;
+                    qP = run->p1_pos;
+                    qh = num > 0u;
                 }
-            n_runs = __reduce_add_sync(full, __popc(rs));
-            // payload in position order
-            const uint32_t cnt = __popc(hm);
-            uint32_t incl = cnt;
+                // walk 1: run-begin hits, pairs, and the function of this lane's last "setter" (run-begin hit or pair)
+                uint32_t pairm = 0, setF = 0;
+                bool has_set = false;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(full, incl, d);
-                if (lane >= (uint32_t)d) incl += t;
+                for (int j = 0; j < 4; j++)
+                    if (hm & (1u << j)) {
+                        const uint32_t pos = wbase + j;
+                        const bool beg = !qh || (uint32_t)(qP + max_gap) < pos;  // 821: unsigned arithmetic, as there
+                        const bool pair = !beg && fi[j] == qF;
+                        beginm |= beg ? (1u << j) : 0u;
+                        pairm |= pair ? (1u << j) : 0u;
+                        if (beg || pair) {
+                            setF = fi[j];
+                            has_set = true;
+                        }
+                        qF = fi[j];
+                        qP = pos;
+                        qh = true;
+                    }
+                // current_fI on entry to this lane
+                const uint32_t setb = __ballot_sync(full, has_set);
+                const uint32_t sbelow = setb & lt;
+                uint32_t c = __shfl_sync(full, setF, sbelow ? 31u - __clz(sbelow) : 0u);
+                if (!sbelow) c = cur;
+                // walk 2: pairs that end a run, hits that match
+                uint32_t trigm = 0, matchm = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (hm & (1u << j)) {
+                        if (beginm & (1u << j)) {
+                            c = fi[j];
+                        } else if (pairm & (1u << j)) {
+                            trigm |= fi[j] != c ? (1u << j) : 0u;
+                            c = fi[j];
+                        }
+                        matchm |= fi[j] == c ? (1u << j) : 0u;
+                    }
+                // the hit before a run-ending pair's second hit begins the new run (and counts for it)
+                uint32_t predm = 0;
+#pragma unroll
+                for (int j = 1; j < 4; j++)
+                    if (trigm & (1u << j)) {
+                        const uint32_t lower = hm & ((1u << j) - 1u);
+                        if (lower) predm |= 1u << (31 - __clz(lower));
+                    }
+                const uint32_t tb = __ballot_sync(full, (trigm & hm & (0u - hm)) != 0u);  // lanes whose FIRST hit ends a run
+                const uint32_t above = anyb & ~lt & ~(1u << lane);
+                if (hm && above && ((tb >> (__ffs(above) - 1)) & 1u)) predm |= 1u << (31 - __clz(hm));
+                addm = matchm | predm;
+                startm = beginm | predm;
+                pre = (tb >> fl) & 1u;
             }
-            n_step = __shfl_sync(full, incl, 31);
-            uint32_t o = incl - cnt;
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (hm & (1u << j)) {
-                    W[o] = __uint_as_float(wz[j]);
-                    FI[o] = fi[j];
-                    o++;
-                }
-            if (lane < 4u) W[n_step + lane] = 0.0f;  // x + (+0) == x: the scan lane adds the weights four at a time
         }
-        const uint32_t sh4 = 4u * (lane & 7u), gm = 0xFFu << (lane & 24u);
-        const uint32_t hw = __reduce_or_sync(gm, hm << sh4), sw = __reduce_or_sync(gm, rs << sh4);
-        if ((lane & 7u) == 0u) {
-            r->hits[lane >> 3] = hw;
-            r->starts[lane >> 3] = sw;
+        // The step in pieces, cut where runs begin: [the carried pair's run end] [run beginnings inside the step]* [the rest].
+        // One record at most per piece, all from this one place (the kernel has to stay inside the instruction cache).
+        bool prepend = false;
+        for (;;) {
+            uint32_t seg = lo, flags = 0, sl = 0, sj = 0, eb = 0, rel = 0, kind = 2u;
+            bool is_begin = false;
+            if (pre) {
+                kind = 0u;
+                seg = 0u;
+            } else if (const uint32_t sbal = simple ? 0u : __ballot_sync(full, (startm & lo) != 0u)) {
+                kind = 1u;
+                sl = __ffs(sbal) - 1u;
+                sj = __ffs(__shfl_sync(full, startm & lo, sl)) - 1u;
+                eb = 4u * sl + sj;  // the window the new run begins with
+                rel = eb > 4u * lane ? min(eb - 4u * lane, 4u) : 0u;
+                seg = lo & ((1u << rel) - 1u);
+                is_begin = (__shfl_sync(full, beginm, sl) >> sj) & 1u;
+            }
+            const uint32_t a4 = addm & seg;
+            const uint32_t ab = __ballot_sync(full, a4 != 0u);
+            if (!simple) {  // account for the windows in `seg`: stored hits, matching hits, last matching position
+                const uint32_t both = __reduce_add_sync(full, (__popc(a4) << 16) | __popc(hm & seg));
+                num += both & 0xFFFFu;
+                cnt += both >> 16;
+                if (ab) {
+                    const uint32_t hl = 31u - __clz(ab);
+                    lastm = t0 + 4u * hl + (31u - __clz(__shfl_sync(full, a4, hl)));
+                }
+            }
+            // the run that ends here: a run-ending pair flushes unconditionally (852-856), a gap only a run of min_hits stored
+            // hits (821-831), the end of the protein likewise (873-876); a call needs min_hits matching hits (753) and, by
+            // the scan lane's judgement, its weighted sum
+            if (kind == 0u || (kind == 1u && !is_begin)) flags = (int)cnt >= min_hits ? kPcEmit : kPcReset;
+            else if (kind == 1u && num > 0u) flags = ((int)num >= min_hits && (int)cnt >= min_hits) ? kPcEmit : kPcReset;
+            else if (kind == 2u && last) flags = kPcEnd | ((int)num < min_hits ? 0u : (int)cnt >= min_hits ? kPcEmit : kPcReset);
+            if (flags || prepend || ab) {
+                // the record: this lane's weights of a4, compacted in position order (behind the carried hit's if `prepend`)
+                wait_slot();
+                const uint32_t slot = pubc & (kPcDepth - 1u);
+                float *W = me->W[slot];
+                uint32_t n_w = prepend ? 1u : 0u;
+                if (ab) {
+                    const uint32_t c4 = __popc(a4);
+                    uint32_t incl = c4;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t t = __shfl_up_sync(full, incl, d);
+                        if (lane >= (uint32_t)d) incl += t;
+                    }
+                    const uint32_t o = n_w + incl - c4;
+                    n_w += __shfl_sync(full, incl, 31);
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (a4 & (1u << j)) W[o + __popc(a4 & ((1u << j) - 1u))] = __uint_as_float(stage[stage8_at(4u * lane + j)].x);
+                }
+                if (lane < 4u) W[n_w + lane] = 0.0f;  // x + (+0) == x: the scan lane adds the weights four at a time
+                if (lane == 0) {
+                    if (prepend) W[0] = __uint_as_float(run->p1_wt);
+                    PcRecord *r = &me->rec[slot];
+                    *reinterpret_cast<uint4 *>(&r->n_w) = make_uint4(n_w, flags, index, cnt);
+                    *reinterpret_cast<uint4 *>(&r->start) = make_uint4(first, lastm + (CKM_KMER_SIZE - 1), cur, 0u);
+                    r->seq_base = seq_base;
+                }
+                __syncwarp();
+                pubc++;
+                if (lane == 0) {
+                    __threadfence_block();
+                    sy->pub = pubc;
+                }
+            }
+            prepend = false;
+            if (kind == 2u) break;
+            if (kind == 0u) {  // the carried hit begins the new run; its weight goes in front of this step's
+                cur = run->p1_fI;
+                first = run->p1_pos;
+                lastm = first;
+                num = 1;
+                cnt = 1;
+                prepend = true;
+                pre = false;
+            } else {
+                cur = staged(eb).y;
+                first = t0 + eb;
+                num = 0;
+                cnt = 0;
+                lo &= ~((1u << rel) - 1u);
+                if (lane == sl) startm &= ~(1u << sj);
+            }
+        }
+        if (last) {
+            num = 0;
+            cnt = 0;
         }
         if (lane == 0) {
-            *reinterpret_cast<uint4 *>(&r->t0) = make_uint4(t0, flags | (n_runs == 1u ? kPcOneRun : 0u), index, n_step);
-            r->seq_base = seq_base;
+            *reinterpret_cast<uint4 *>(&run->cur) = make_uint4(cur, num, cnt, first);
+            run->lastm = lastm;
+            if (anyb) {  // the newest stored hit
+                const uint2 z = staged(e_last);
+                run->p1_pos = t0 + e_last;
+                run->p1_fI = z.y;
+                run->p1_wt = z.x;
+            }
         }
         __syncwarp();
+        return n_step;
+    };
+    // a record without weights: an empty protein's end, or this warp's last word
+    auto emit_bare = [&](uint32_t flags, uint32_t index, uint64_t seq_base) {
+        wait_slot();
+        PcRecord *r = &me->rec[pubc & (kPcDepth - 1u)];
         pubc++;
         if (lane == 0) {
+            *reinterpret_cast<uint4 *>(&r->n_w) = make_uint4(0u, flags, index, 0u);
+            r->seq_base = seq_base;
             __threadfence_block();
             sy->pub = pubc;
         }
-        return n_step;
+        __syncwarp();
     };
     auto claim = [&]() -> uint32_t {
         unsigned long long c = 0;
@@ -434,7 +540,7 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
             // ckm_call_batch_device that understated max_len is told so instead of getting indices that silently diverge
             if (len > kHitCap + CKM_KMER_SIZE && lane == 0) atomicExch(totals + 6, 1ull);
             if (len <= CKM_KMER_SIZE) {
-                publish(0u, 0u, kPcEnd, i, seq_base);
+                emit_bare(kPcEnd, i, seq_base);
             } else {
                 uint32_t nwin = len - CKM_KMER_SIZE;  // the last window is never probed (kguts.cc:792, 798)
                 const uint32_t nseg = (nwin + kHintSeg - 1) >> kHintShift;
@@ -602,14 +708,14 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
                     }
                     my_probes += __popc(act);
                     if (no_pub) count += __reduce_add_sync(full, __popc(hm));
-                    else count += publish(hm, t0, last ? kPcEnd : 0u, i, seq_base);
+                    else count += scan_step(hm, t0, last, i, seq_base);
                 }
             }
             if (lane == 0) n_hits[i] = count;
             if (lane == 0) my_hits += count;
         }
     }
-    publish(0u, 0u, kPcFin, 0u, 0ull);
+    emit_bare(kPcFin, 0u, 0ull);
 
     // batch totals: one atomic per warp (totals[4] = hits answered from the neighbour copy)
 #pragma unroll

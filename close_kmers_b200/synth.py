@@ -119,6 +119,23 @@ def make_signatures(protos: Prototypes, n_sigs: int, n_functions: int | None = N
     return Signatures(keys, fI, oI, avg, wt, F)
 
 
+def make_signatures_sparse(protos: Prototypes, n_sigs: int, keep: float = 0.4, jitter: int = 12, foreign: float = 0.1,
+                           n_functions: int | None = None, seed: int = 1, dedupe: bool = True) -> Signatures:
+    """Signature sets as build_signature_kmers leaves them, not as make_signatures idealises them: only a random ``keep``
+    fraction of every prototype's windows are signatures (the discriminating ones), ``avg_from_end`` is an average over the
+    proteins a k-mer was seen in (here: the true distance jittered by up to ``jitter``), and a ``foreign`` fraction of a
+    prototype's signatures belongs to some other function.  Consecutive signatures of a prototype therefore overlap by
+    seven residues only with probability ``keep``: the worst case for the neighbour-ordered copy of the table."""
+    rng = np.random.default_rng(seed)
+    dense = make_signatures(protos, 1 << 62, n_functions=n_functions, dedupe=dedupe)
+    take = np.flatnonzero(rng.random(len(dense.keys)) < keep)[:n_sigs]
+    keys, fI, avg, wt = dense.keys[take], dense.fI[take].copy(), dense.avg[take].astype(np.int64), dense.wt[take]
+    avg = np.clip(avg + rng.integers(-jitter, jitter + 1, len(avg)), 0, 65535).astype(np.uint16)
+    other = rng.random(len(fI)) < foreign
+    fI[other] = rng.integers(0, dense.n_functions, int(other.sum()), dtype=np.int32)
+    return Signatures(keys, fI, dense.oI[take], avg, wt, dense.n_functions)
+
+
 def function_names(n: int) -> list[str]:
     return [f"function {i}" for i in range(n)]
 

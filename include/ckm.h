@@ -169,6 +169,11 @@ int ckm_chain_info(ckm_ctx *ctx, uint64_t info[4]);
 #define CKM_TUNE_NO_FALLBACK 0x200000u
 void ckm_set_tuning(ckm_ctx *ctx, uint32_t bits);
 int ckm_experiments_enabled(void); /* 1 when built with -DCKM_EXPERIMENTS */
+/* The automatic fall-back of K1: a batch that went through the neighbour copy but had fewer than 12 % of its probes answered
+ * from it suspends the copy for 16 batches (doubling up to 1024 while retries keep failing), after which one batch tries it
+ * again.  state[0] = suspended now, state[1] = batches until the retry, state[2] = suspensions so far.  Results are the same
+ * on either path. */
+int ckm_copy_state(const ckm_ctx *ctx, uint32_t state[3]);
 /* 1 when the last batch of this ctx was served by probe_pc_kernel (scoring scan inside K1, no hit records in HBM) */
 int ckm_last_batch_was_fused(const ckm_ctx *ctx);
 

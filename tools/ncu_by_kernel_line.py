@@ -16,24 +16,28 @@ import tempfile
 
 rep, lib, kern, body = sys.argv[1:5]
 thr = float(sys.argv[5]) if len(sys.argv) > 5 else 0.3
+innermost = len(sys.argv) > 6 and sys.argv[6] == "inner"  # charge to the innermost frame inside `body` (lambdas of the kernel) instead
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, check=True, capture_output=True)
 cubin = max((os.path.join(tmp, f) for f in os.listdir(tmp)), key=os.path.getsize)
 dis = subprocess.run(["nvdisasm", "-gi", cubin], capture_output=True, text=True).stdout.split("\n")
 start = next(i for i, l in enumerate(dis) if l.startswith(".text." + kern))
-outer = []  # per instruction: line of `body` (outermost frame)
+outer = []  # per instruction: line of `body` (outermost frame, or innermost with "inner")
 cur = None
+in_block = False  # inside a run of "//## File" annotation lines (innermost frame first, then its callers)
+fixed = False
 for l in dis[start + 1:]:
     if l.startswith(".text.") or l.startswith("\t.section") or l.startswith(".section"):
         break
-    m = re.search(r'//## File "([^"]+)", line (\d+)', l)
-    if m:
-        # the innermost frame comes first; later annotation lines of the same block are its callers
-        frames = re.findall(r'File "([^"]+)", line (\d+)', l)
-        for f, n in frames:
-            if f.endswith(body):
+    if "//## File" in l:
+        if not in_block:
+            in_block, fixed = True, False
+        for f, n in re.findall(r'File "([^"]+)", line (\d+)', l):
+            if f.endswith(body) and not fixed:
                 cur = int(n)
+                fixed = innermost
         continue
+    in_block = False
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
         outer.append(cur)
 csvtxt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"],
