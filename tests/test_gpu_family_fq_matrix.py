@@ -194,10 +194,13 @@ def test_handler_texts_match_reference(checkers, world):
         assert guts.query_text(ids, batch.residues, batch.offsets, details, fbc) == ref.query_text(ids, batch, details, fbc)
     reads = wl.concat_batches(synth.batch_from_strings(DNA_EDGE), synth.make_reads(8, protos, 500))
     rids = [f"read{i}" if i != 3 else "" for i in range(reads.n)]
-    mine, theirs = _lines_by_id(guts.fq_text(rids, reads.residues, reads.offsets)), _lines_by_id(ref.fq_text(rids, reads))
+    got_text, want_text = guts.fq_text(rids, reads.residues, reads.offsets), ref.fq_text(rids, reads)
+    mine, theirs = _lines_by_id(got_text), _lines_by_id(want_text)
     assert mine.keys() == theirs.keys() and len(mine) > 300
-    diff = [k for k in mine if mine[k] != theirs[k]]
-    assert len(diff) <= 10, diff[:5]  # exact ties between families are broken by unordered_map order in the reference
+    # a line may differ from the reference's only in the NAME of a family, and only where the score printed next to it is the
+    # same on both sides: an exact tie, which the reference breaks by unordered_map iteration order (family_mapper.cc:137-197)
+    named = wl.assert_fq_text_equal(got_text, want_text)
+    assert named == sum(1 for k in mine if mine[k] != theirs[k])
 
 
 def test_add_and_matrix(checkers, world):

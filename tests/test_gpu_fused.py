@@ -196,3 +196,25 @@ def test_packed_residue_entry_matches_ascii_entry(checkers):
         os.environ.pop("CKM_PIPELINE_MIN_KB", None)
         os.environ.pop("CKM_PIPELINE_CHUNK_KB", None)
         orc.close()
+
+
+@pytest.mark.parametrize("chain", ["0", "1"])
+def test_fused_scan_sparse_signatures_with_foreign_functions(checkers, chain):
+    """Signature sets as build_signature_kmers leaves them (synth.make_signatures_sparse): a random subset of every prototype's
+    windows, a share of them of some other function, avg_from_end jittered.  Nearly every run carries stray hits of other
+    functions -- singly (no effect on the run), in pairs (a run-ending pair, kguts.cc:852-856, with its carry-over), at step
+    boundaries -- which is what the parallel form of the run logic in probe_pc_kernel has to get right."""
+    for seed, keep, foreign, nf in ((3, 0.7, 0.15, 6), (4, 0.4, 0.3, 3), (5, 1.0, 0.05, 50)):
+        protos = synth.make_prototypes(seed, 300, 300, 40.0)
+        sig = synth.make_signatures_sparse(protos, 80_000, keep=keep, foreign=foreign, n_functions=nf, seed=seed)
+        img = api.build_image(synth.bucket_count(len(sig.keys)), sig.keys, sig.fI, sig.oI, sig.avg, sig.wt)
+        orc = checkers.Oracle().open_image(img)
+        g = _open(img, synth.function_names(sig.n_functions), chain)
+        try:
+            batch = wl.concat_batches(wl.edge_batch(protos), synth.make_proteins(seed + 10, protos, 3000))
+            for prm in (dict(), dict(min_hits=2, max_gap=30), dict(min_hits=1, max_gap=3), dict(min_hits=3, min_weighted_hits=8, max_gap=127)):
+                _check(g, orc, batch, prm, f"sparse world keep={keep} foreign={foreign} functions={nf} chain={chain}")
+        finally:
+            orc.set_params()
+            g.close()
+            orc.close()
