@@ -11,7 +11,8 @@ is BASELINE.json configs[1] ("c2": 1M proteins, mean 300 aa, vs a 100M-k-mer ima
 Keys of the JSON line: see DESIGN.md "Measurement".  `value` is kernel-resident (inputs already in HBM); `e2e` goes
 through the C ABI with pinned HOST buffers (H2D + kernels + D2H inside the timed region) -- ckm_call_batch_packed, the
 entry point a parser feeds (5 bits per residue), with `e2e_ascii` (ckm_call_batch, the reference's char* strings) beside it.
-Sub-records of the same line: `c3_stream` (BASELINE configs[2]: 100M proteins streamed against an 80M-k-mer image, strong-scaled
+Sub-records of the same line: `sparse_signatures` (a signature set that is a sparse subset of the windows: the neighbour copy
+pinned on, plain probing, and what the automatic fall-back picks), `c3_stream` (BASELINE configs[2]: 100M proteins streamed against an 80M-k-mer image, strong-scaled
 over the ranks), `fq` (configs[3]: reads -> 6 frames -> calling -> family voting -> best frame) and `matrix` (configs[4]: 50k
 proteins, row blocks over the ranks, NCCL tile gather).
 """
@@ -512,6 +513,63 @@ def run_matrix(api, torch, dist, rank, world, local, barrier, peak, args):
     return rec
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# Signature sets that are a sparse subset of the windows, some of another function (what build_signature_kmers leaves): the
+# worst case for the neighbour copy, and the test of the automatic fall-back to plain hash probing
+# ----------------------------------------------------------------------------------------------------------------------
+def run_sparse(api, torch, rank, local, peak, args):
+    if rank != 0:
+        return None
+    n_sigs, n_prot, keep, foreign = args.sparse_sigs, args.sparse_proteins, 0.5, 0.05
+    t0 = time.time()
+    protos = synth.make_prototypes(2468, int(-(-n_sigs // 293) / keep) + 8, 300, 60.0)
+    batch = synth.make_proteins_parallel(2469, protos, n_prot)
+    sig = synth.make_signatures_sparse(protos, n_sigs, keep=keep, foreign=foreign, dedupe=False)
+    img = api.build_image(synth.bucket_count(len(sig.keys)), sig.keys, sig.fI, sig.oI, sig.avg, sig.wt)
+    log(f"[sparse r{rank}] world ({len(sig.keys)} k-mers = {keep:.0%} of the prototypes' windows, {foreign:.0%} of another function, "
+        f"{n_prot} proteins) in {time.time() - t0:.1f}s")
+    total = int(batch.offsets[-1])
+    max_len = int(np.diff(batch.offsets.astype(np.int64)).max())
+    d_res = torch.zeros(total + 64, dtype=torch.uint8, device="cuda")
+    d_res[:total] = torch.from_numpy(batch.residues).cuda()
+    d_off = torch.from_numpy(batch.offsets.astype(np.int64)).cuda()
+    g = api.KmerGuts(image=img, device=local)
+    rec = {"workload": f"{n_prot} proteins vs a {len(sig.keys)}-k-mer image ({g.num_sigs} buckets, larger than L2) whose signatures are a random "
+                       f"{keep:.0%} of every prototype's windows, {foreign:.0%} of them of another function, avg_from_end jittered "
+                       f"(synth.make_signatures_sparse); device-resident batch, WANT_BEST",
+           "neighbour_copy": {"entries": g.chain_info["entries"], "chains": g.chain_info["chains"]}}
+    best = {}
+    for name, tuning in (("copy_pinned", api.TUNE_NO_FALLBACK), ("plain_pinned", api.TUNE_NO_FALLBACK | api.TUNE_PLAIN_PROBE), ("automatic", 0)):
+        g.set_tuning(tuning)
+        for _ in range(3):
+            g.call_batch_device(d_res.data_ptr(), d_off.data_ptr(), batch.n, total, max_len, api.WANT_BEST)
+            g.read_totals()  # the counters reach the host: the automatic fall-back judges the batch
+        g.profile_enable(True)
+        g.profile_read()
+        for _ in range(max(3, min(args.steps, 10))):
+            g.call_batch_device(d_res.data_ptr(), d_off.data_ptr(), batch.n, total, max_len, api.WANT_BEST)
+        p, s_ms, nb = g.profile_read()
+        g.profile_enable(False)
+        probes, hits, calls = g.read_totals()
+        ms = (p + s_ms) / nb
+        rec[name] = {"ms_per_step": ms, "proteins_per_s": batch.n / (ms * 1e-3), "probes_per_s": probes / (ms * 1e-3),
+                     "roofline_frac": (32.0 * probes + total) / (ms * 1e-3) / 1e9 / peak}
+        if name == "copy_pinned":
+            rec["per_step"] = {"proteins": batch.n, "probes": probes, "hits": hits, "calls": calls}
+            rec["share_of_probes_answered_from_copy"] = g.chain_info["hits_from_copy"] / max(probes, 1)
+        if name == "automatic":
+            rec["automatic"]["state"] = g.copy_state
+        o = g.device_results()
+        from close_kmers_b200 import parallel
+        best[name] = parallel._alias(o.d_best, batch.n * 28, "|u1", torch, torch.device("cuda", local)).cpu().numpy().tobytes()
+    rec["identical_best_calls_on_all_three_paths"] = len(set(best.values())) == 1
+    rec["automatic_never_slower_than_plain"] = rec["automatic"]["ms_per_step"] <= 1.03 * rec["plain_pinned"]["ms_per_step"]
+    g.close()
+    del d_res, d_off
+    torch.cuda.empty_cache()
+    return rec
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -523,7 +581,7 @@ def main():
     ap.add_argument("--sigs", type=int, default=0, help="override signature k-mer count")
     ap.add_argument("--proteins", type=int, default=0, help="override proteins per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--skip", default="", help="comma-separated sub-records to leave out: c3,fq,matrix,plain")
+    ap.add_argument("--skip", default="", help="comma-separated sub-records to leave out: c3,fq,matrix,sparse,plain")
     ap.add_argument("--c3-proteins", type=int, default=100_000_000)
     ap.add_argument("--c3-pool", type=int, default=2_000_000, help="proteins in the host pool each rank cycles through")
     ap.add_argument("--c3-sigs", type=int, default=0)
@@ -531,6 +589,8 @@ def main():
     ap.add_argument("--fq-pool", type=int, default=2_000_000)
     ap.add_argument("--fq-sigs", type=int, default=20_000_000)
     ap.add_argument("--matrix-proteins", type=int, default=50_000)
+    ap.add_argument("--sparse-sigs", type=int, default=20_000_000)
+    ap.add_argument("--sparse-proteins", type=int, default=300_000)
     args = ap.parse_args()
     skip = set(x for x in args.skip.split(",") if x)
 
@@ -776,7 +836,9 @@ def main():
             "table": {"buckets": guts.num_sigs, "slot_bytes": guts.slot_bytes, "l2_fetch_granularity": guts.l2_fetch_granularity,
                       "occupancy_bitmap": guts.has_occupancy_bitmap, "scan_inside_K1": bool(fused),
                       "neighbour_copy": {"entries": chain["entries"], "chains": chain["chains"], "build_ms": chain["build_ms"],
-                                         "hits_answered_from_copy": chain["hits_from_copy"]}},
+                                         "hits_answered_from_copy": chain["hits_from_copy"],
+                                         "share_of_probes_answered_from_copy": chain["hits_from_copy"] / max(n_probes, 1),
+                                         "automatic_fallback": guts.copy_state}},
         }
         if not args.no_cpu_baseline and world == 1:
             with stdout_to_stderr():
@@ -796,7 +858,8 @@ def main():
     subs = {}
     for name, fn in (("c3_stream", lambda: run_c3_stream(api, torch, dist, rank, world, local, barrier, peak, args, tag)),
                      ("fq", lambda: run_fq(api, torch, dist, rank, world, local, barrier, peak, args)),
-                     ("matrix", lambda: run_matrix(api, torch, dist, rank, world, local, barrier, peak, args))):
+                     ("matrix", lambda: run_matrix(api, torch, dist, rank, world, local, barrier, peak, args)),
+                     ("sparse_signatures", lambda: run_sparse(api, torch, rank, local, peak, args))):
         if name.split("_")[0] in skip or args.workload != "c2":
             continue
         t0 = time.time()

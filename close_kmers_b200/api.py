@@ -694,6 +694,23 @@ class KmerGuts:
                                  residues.ctypes.data, offsets.ctypes.data, len(offsets) - 1, C.byref(t)))
         return self._take_text(t)
 
+    def find_all_matches_text(self, ids, residues, offsets, families) -> str:
+        """FamilyMapper::find_all_matches (family_mapper.cc:207-285) for one chunk; families as for lookup_text."""
+        residues = np.ascontiguousarray(residues, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        arr = (FamilyDataC * max(len(families), 1))()
+        for k, f in enumerate(families):
+            arr[k] = FamilyDataC(f[0].encode(), f[1].encode(), f[2].encode(), f[3], f[4], f[5])
+        bs = [s.encode() if isinstance(s, str) else s for s in ids]
+        idarr = (C.c_char_p * max(len(bs), 1))(*bs)
+        L = lib()
+        L.ckm_family_all_matches_text.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                                  C.POINTER(C.c_void_p)]
+        t = C.c_void_p()
+        _check(L.ckm_family_all_matches_text(self._h, arr, len(families), idarr, residues.ctypes.data, offsets.ctypes.data,
+                                             len(offsets) - 1, C.byref(t)))
+        return self._take_text(t)
+
     def find_best_family_match_batch(self, residues, offsets) -> np.ndarray:
         """FamilyMapper::find_best_family_match (family_mapper.cc:65-205) for every sequence."""
         residues = np.ascontiguousarray(residues, np.uint8)

@@ -157,3 +157,13 @@ extern "C" int ckm_lookup_text(ckm_ctx *ctx, ckm_mapping *pegs, const ckm_family
     *text = os.dup();
     return *text ? 0 : CKM_ENOMEM;
 }
+
+// FamilyMapper::find_all_matches (family_mapper.cc:207-285): family mode, no best match, kmer_hit_threshold_ = 3 (family_mapper.cc:7)
+extern "C" int ckm_family_all_matches_text(ckm_ctx *ctx, const ckm_family_data_t *fams, uint32_t n_fams, const char *const *ids,
+                                           const char *residues, const uint64_t *offsets, uint32_t n, char **text) {
+    ckm_lookup_options_t o;
+    memset(&o, 0, sizeof o);
+    o.family_mode = 1;
+    o.kmer_hit_threshold = 3;
+    return ckm_lookup_text(ctx, nullptr, fams, n_fams, &o, ids, residues, offsets, n, text);
+}

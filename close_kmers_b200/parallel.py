@@ -74,17 +74,52 @@ def _alias(ptr: int, count: int, typestr: str, torch, device):
 
 
 def _all_gather_var(local, world, dist, torch, group=None):
-    """all_gather of 1-D device tensors of different lengths; returns the list of per-rank tensors (views of one buffer)."""
+    """all_gather of 1-D tensors of different lengths (device tensors over NCCL, host tensors over gloo); returns the list of
+    per-rank tensors (views of one buffer)."""
     n = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
-    sizes = torch.zeros(world, dtype=torch.int64, device=local.device)
-    dist.all_gather_into_tensor(sizes, n, group=group)
-    sizes = [int(x) for x in sizes.tolist()]
+    sizes = [torch.zeros(1, dtype=torch.int64, device=local.device) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(x) for x in sizes]
     mx = max(max(sizes), 1)
     send = torch.zeros(mx, dtype=local.dtype, device=local.device)
     send[: local.numel()] = local
     recv = torch.empty(world * mx, dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(recv, send, group=group)
+    if local.is_cuda:
+        dist.all_gather_into_tensor(recv, send, group=group)
+    else:
+        dist.all_gather(list(recv.view(world, mx).unbind(0)), send, group=group)
     return [recv[r * mx: r * mx + sizes[r]] for r in range(world)]
+
+
+class GpuMatrixOps:
+    """What MatrixJob needs from one rank's engine, on the GPU: the postings and the tile stay in HBM and are handed to the
+    collective as torch tensors that alias the library's buffers (no copy)."""
+
+    def __init__(self, guts, device):
+        import torch
+        self.g, self.torch = guts, torch
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+
+    def clear(self):
+        self.g.postings_clear()
+
+    def add(self, eids, residues, offsets):
+        self.g.postings_add(eids, residues, offsets)
+
+    def export(self):
+        dk, de, n = self.g.postings_device()
+        return _alias(dk, n, "<u8", self.torch, self.device), _alias(de, n, "<u4", self.torch, self.device)
+
+    def install(self, keys, pegs):
+        self.g.postings_import_device(keys.data_ptr(), pegs.data_ptr(), keys.numel())
+
+    def rows(self, eids, residues, offsets, a, b):
+        ptr, n_pairs, walked = self.g.matrix_rows_device(eids, residues, offsets, a, b)
+        return _alias(ptr, n_pairs * 16, "|u1", self.torch, self.device), walked
+
+    @property
+    def postings_count(self):
+        return self.g.postings_count
 
 
 class MatrixJob:
@@ -100,10 +135,14 @@ class MatrixJob:
 
     With world == 1 the same calls run without the collectives.  eids must be the request's ids; when they ascend in request
     order (the usual case: KmerPegMapping::encode_id numbers ids in order of first appearance, kmer.cc:272-286) the
-    concatenated tiles are final, otherwise they go through api.merge_pairs."""
+    concatenated tiles are final, otherwise they go through api.merge_pairs.
 
-    def __init__(self, guts, eids, batch, rank: int, world: int, device=None, group=None):
-        self.g, self.eids, self.batch, self.rank, self.world, self.device, self.group = guts, np.ascontiguousarray(eids, np.uint32), batch, rank, world, device, group
+    `ops` is the per-rank engine: GpuMatrixOps(guts) by default; the CPU test of the sharding / exchange logic
+    (tests/test_parallel_gloo.py, gloo, world_size 2) passes the plain-C oracle behind the same five calls."""
+
+    def __init__(self, guts, eids, batch, rank: int, world: int, device=None, group=None, ops=None):
+        self.eids, self.batch, self.rank, self.world, self.group = np.ascontiguousarray(eids, np.uint32), batch, rank, world, group
+        self.ops = ops if ops is not None else GpuMatrixOps(guts, device)
         lengths = np.diff(batch.offsets.astype(np.int64))
         self.blocks = shard_rows(lengths, world)
         self.ascending = bool(np.all(np.diff(self.eids.astype(np.int64)) > 0)) if len(self.eids) > 1 else True
@@ -116,39 +155,36 @@ class MatrixJob:
         import time
         import torch
         from . import api
-        g, world = self.g, self.world
+        ops, world = self.ops, self.world
         t = [time.perf_counter()]
         a, b = self.blocks[self.rank]
-        g.postings_clear()
+        ops.clear()
         if b > a:
-            g.postings_add(*self._sub(a, b))
+            ops.add(*self._sub(a, b))
         t.append(time.perf_counter())
         if world > 1:
             import torch.distributed as dist
-            dk, de, n_local = g.postings_device()
-            keys = _all_gather_var(_alias(dk, n_local, "<u8", torch, self.device), world, dist, torch, self.group)
-            pegs = _all_gather_var(_alias(de, n_local, "<u4", torch, self.device), world, dist, torch, self.group)
-            all_keys, all_pegs = torch.cat(keys), torch.cat(pegs)
-            g.postings_import_device(all_keys.data_ptr(), all_pegs.data_ptr(), all_keys.numel())
+            k_local, p_local = ops.export()
+            keys = _all_gather_var(k_local, world, dist, torch, self.group)
+            pegs = _all_gather_var(p_local, world, dist, torch, self.group)
+            ops.install(torch.cat(keys), torch.cat(pegs))
         t.append(time.perf_counter())
-        ptr, n_pairs, walked = g.matrix_rows_device(self.eids, self.batch.residues, self.batch.offsets, a, b)
+        tile, walked = ops.rows(self.eids, self.batch.residues, self.batch.offsets, a, b)
         t.append(time.perf_counter())
         if world > 1:
-            tile = _alias(ptr, n_pairs * 16, "|u1", torch, self.device)
             tiles = _all_gather_var(tile, world, dist, torch, self.group)
-            # every rank holds every tile in HBM; the host copy is made where the response is written
+            # every rank holds every tile; the host copy is made where the response is written
             merged = torch.cat(tiles).cpu().numpy().view(PAIR_DT) if self.rank == 0 else np.zeros(0, PAIR_DT)
-            w = torch.tensor([walked], dtype=torch.int64, device=self.device)
+            w = torch.tensor([walked], dtype=torch.int64, device=tile.device)
             dist.all_reduce(w, group=self.group)
             walked = int(w)
         else:
-            tile = _alias(ptr, n_pairs * 16, "|u1", torch, torch.device("cuda", torch.cuda.current_device()))
             merged = tile.cpu().numpy().view(PAIR_DT)
         t.append(time.perf_counter())
         if not self.ascending:
             merged = api.merge_pairs(merged)
         t.append(time.perf_counter())
-        stats = {"postings": g.postings_count, "walked": walked, "row_blocks": self.blocks,
+        stats = {"postings": ops.postings_count, "walked": walked, "row_blocks": self.blocks,
                  "phase_ms": {"add_block": (t[1] - t[0]) * 1e3, "gather_postings": (t[2] - t[1]) * 1e3, "rows": (t[3] - t[2]) * 1e3,
                               "gather_tiles": (t[4] - t[3]) * 1e3, "merge": (t[5] - t[4]) * 1e3}}
         return merged, stats

@@ -222,6 +222,19 @@ public:
         return out;
     }
 
+    // FamilyMapper::find_all_matches(os, id, seq) (family_mapper.cc:207-285) over a work list; `families` is the reference's
+    // family_data_ (kmer.h:118-127) as the C ABI takes it
+    void find_all_matches(std::ostream &os, const work_list_t &work, const std::vector<ckm_family_data_t> &families) {
+        Flat f(work);
+        std::vector<const char *> ids;
+        for (const auto &w : work) ids.push_back(w.first.c_str());
+        char *text = nullptr;
+        check(ckm_family_all_matches_text(kguts_->ctx(), families.data(), (uint32_t)families.size(), ids.data(), f.residues.data(),
+                                          f.offsets.data(), (uint32_t)work.size(), &text));
+        os << text;
+        ckm_free_text(text);
+    }
+
 private:
     KmerGuts *kguts_;
 };

@@ -80,6 +80,15 @@ typedef struct {
 int ckm_lookup_text(ckm_ctx *ctx, ckm_mapping *m, const ckm_family_data_t *fams, uint32_t n_fams, const ckm_lookup_options_t *opt,
                     const char *const *ids, const char *residues, const uint64_t *offsets, uint32_t n, char **text);
 
+/* FamilyMapper::find_all_matches (family_mapper.cc:207-285; its only caller is the reference's test_family_mapper.cc:128) for
+ * every sequence of a chunk: "<id>\n", then one line per family the sequence's hits touched -- hit count, hit total, weighted
+ * total, PGF, PLF, total size, count, hit count / total size, function -- best weighted total first, up to the first family
+ * with fewer than three hits (kmer_hit_threshold_, family_mapper.cc:7), then "//\n".  The same listing as POST /lookup in
+ * family mode without find_best_match (lookup_request.cc:329-377); families with exactly equal weighted totals come out by
+ * ascending id here (std::sort over unordered_map order in the reference). */
+int ckm_family_all_matches_text(ckm_ctx *ctx, const ckm_family_data_t *fams, uint32_t n_fams, const char *const *ids,
+                                const char *residues, const uint64_t *offsets, uint32_t n, char **text);
+
 /* FamilyMapper::find_best_family_match as text, one "<gfam>\t<gscore>\t<lfam>\t<lscore>\t<function>\t<score>\n"
  * line per sequence (operator<< of best_match_t, family_mapper.h:70-75) */
 int ckm_family_text(ckm_ctx *ctx, const char *residues, const uint64_t *offsets, uint32_t n, char **text);

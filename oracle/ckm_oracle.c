@@ -812,6 +812,15 @@ void orc_postings_add(const orc_table *t, const orc_params_t *prm, orc_postings 
     p->sorted = 0;
     orc_out_free(o);
 }
+/* the postings as parallel arrays, and back: what a rank contributes to / receives from the all-gather of the multi-GPU /matrix */
+void orc_postings_export(const orc_postings *p, uint64_t *keys, uint32_t *eids) {
+    for (uint64_t i = 0; i < p->n; i++) { keys[i] = p->p[i].k; eids[i] = p->p[i].e; }
+}
+void orc_postings_import(orc_postings *p, const uint64_t *keys, const uint32_t *eids, uint64_t n) {
+    p->n = 0;
+    for (uint64_t i = 0; i < n; i++) { post_t e = {keys[i], eids[i]}; VEC_PUSH(*p, e); }
+    p->sorted = 0;
+}
 static int post_cmp(const void *a, const void *b) {
     const post_t *x = a, *y = b;
     return x->k < y->k ? -1 : x->k > y->k;

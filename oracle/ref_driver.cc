@@ -691,6 +691,15 @@ char *ref_family_text(void *hv, const char *residues, const uint64_t *offsets, u
     return dup_text(os.str());
 }
 
+// FamilyMapper::find_all_matches itself (family_mapper.cc:207-285), one mapper for the block like test_family_mapper.cc:117-128
+char *ref_find_all_matches_text(void *hv, const char *const *ids, const char *residues, const uint64_t *offsets, uint32_t n) {
+    RefHandle *h = (RefHandle *)hv;
+    FamilyMapper mapper(h->guts[0], h->mapping);
+    std::ostringstream os;
+    for (uint32_t i = 0; i < n; i++) mapper.find_all_matches(os, ids[i], seq_at(residues, offsets, i));
+    return dup_text(os.str());
+}
+
 // structured form: exact f32 scores + the three strings of best_match_t, one mapper for the whole block
 char *ref_family_batch(void *hv, const char *residues, const uint64_t *offsets, uint32_t n, float *gscore, float *lscore,
                        float *score) {

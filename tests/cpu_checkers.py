@@ -292,6 +292,14 @@ class Ref:
                                                  kmer_hit_threshold, int(find_best_match), int(find_reps),
                                                  int(allow_ambiguous_functions), target_genus_id))
 
+    def find_all_matches_text(self, ids, batch):
+        """FamilyMapper::find_all_matches (family_mapper.cc:207-285), the reference's own code."""
+        res = np.ascontiguousarray(batch.residues, np.uint8)
+        off = np.ascontiguousarray(batch.offsets, np.uint64)
+        self.L.ref_find_all_matches_text.restype = C.c_void_p
+        self.L.ref_find_all_matches_text.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        return self._text(self.L.ref_find_all_matches_text(self.h, _cstr_array(ids), res.ctypes.data, off.ctypes.data, batch.n))
+
     def parse_text(self, fastq: bool, text: bytes, cuts=()):
         """Reference FastaParser / FastqParser over `text` fed packet by packet; returns [(id, seq)] as bytes."""
         cuts = np.ascontiguousarray(sorted(cuts), np.uint64)
@@ -540,6 +548,17 @@ class Oracle:
         off = np.ascontiguousarray(batch.offsets, np.uint64)
         self.L.orc_postings_add(self.t, C.byref(self.params), self.post, eids.ctypes.data, res.ctypes.data, off.ctypes.data,
                                 batch.n)
+
+    def postings_export(self):
+        self.L.orc_postings_count.restype = C.c_uint64
+        n = self.L.orc_postings_count(self.post)
+        keys, eids = np.zeros(n, np.uint64), np.zeros(n, np.uint32)
+        self.L.orc_postings_export(self.post, keys.ctypes.data_as(C.c_void_p), eids.ctypes.data_as(C.c_void_p))
+        return keys, eids
+
+    def postings_import(self, keys, eids):
+        keys, eids = np.ascontiguousarray(keys, np.uint64), np.ascontiguousarray(eids, np.uint32)
+        self.L.orc_postings_import(self.post, keys.ctypes.data_as(C.c_void_p), eids.ctypes.data_as(C.c_void_p), C.c_uint64(len(keys)))
 
     def matrix_rows(self, eids, batch, row_begin=0, row_end=None):
         eids = np.ascontiguousarray(eids, np.uint32)

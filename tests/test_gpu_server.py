@@ -78,6 +78,8 @@ def test_family_scores_and_lookup_text(checkers, world):
         for thr in (0, 3, 7):
             mine = guts.lookup_text(ids, batch.residues, batch.offsets, rows, kmer_hit_threshold=thr, find_reps=thr == 7)
             assert_lookup_listing_equal(mine, ref.lookup_text(ids, batch, kmer_hit_threshold=thr, find_reps=thr == 7))
+        # FamilyMapper::find_all_matches: the reference's own function (its threshold is fixed at three hits)
+        assert_lookup_listing_equal(guts.find_all_matches_text(ids, batch.residues, batch.offsets, rows), ref.find_all_matches_text(ids, batch))
         # best match per sequence: strings exact, the rolled-up PGF score within 1e-6 (sum order), rest exact
         for ambig, genus in ((0, 0), (1, 1), (0, 2)):
             mine = guts.lookup_text(ids, batch.residues, batch.offsets, rows, find_best_match=True, allow_ambiguous_functions=bool(ambig),
