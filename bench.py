@@ -505,7 +505,11 @@ def run_matrix(api, torch, dist, rank, world, local, barrier, peak, args):
                                        "sample": f"/add + /matrix of the first {m} proteins, {dt:.2f}s on one thread (the reference's KmerGuts "
                                                  f"object code under the restated AddRequest / MatrixRequest loops; cost grows with n^2 / prototypes)"}
                 rec["equals_reference_text_on_sample"] = bool(got == want)
-            whole = api.merge_pairs(g.matrix_rows(eids, batch.residues, batch.offsets)) if world > 1 else merged
+            # the whole request on one GPU, in a context of its own (/add of every protein, then every row)
+            g1 = api.KmerGuts(image=img, device=local)
+            g1.postings_add(eids, batch.residues, batch.offsets)
+            whole = api.merge_pairs(g1.matrix_rows(eids, batch.residues, batch.offsets))
+            g1.close()
             rec["equals_single_gpu"] = bool(whole.tobytes() == merged.tobytes())
     barrier()
     job.close()

@@ -111,6 +111,10 @@ class GpuMatrixOps:
         return _alias(dk, n, "<u8", self.torch, self.device), _alias(de, n, "<u4", self.torch, self.device)
 
     def install(self, keys, pegs):
+        # the gathered tensors were produced on torch's streams (NCCL, torch.cat); the library copies them on the context's own
+        # non-blocking stream, which does not wait for those: finish them first.  (The other direction needs nothing: every
+        # library call returns with its stream synchronised.)
+        self.torch.cuda.current_stream(self.device).synchronize()
         self.g.postings_import_device(keys.data_ptr(), pegs.data_ptr(), keys.numel())
 
     def rows(self, eids, residues, offsets, a, b):

@@ -40,13 +40,15 @@ for l in dis[start + 1:]:
     in_block = False
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
         outer.append(cur)
-csvtxt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"],
+short = re.sub(r"^_ZN\d+[a-z]+(\d+)", "", kern)  # _ZN3ckm15probe_pc_kernelILi31E... -> probe_pc_kernel
+short = re.match(r"[A-Za-z_0-9]+?(?=I[LS]|E|$)", short).group(0) if short else kern
+csvtxt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", "--kernel-name", "regex:" + short],
                         capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(csvtxt)))
 hdr = next(r for r in rows if r and r[0] == "Address")
 iI, iN = hdr.index("Instructions Executed"), hdr.index("# Samples")
 stall_cols = [(i, h) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
-body_rows = [r for r in rows if len(r) == len(hdr) and r[0].startswith("0x")]
+body_rows = [r for r in rows if len(r) == len(hdr) and r[0].startswith("0x")][:len(outer)]  # (the first launch that matches)
 assert len(body_rows) == len(outer), (len(body_rows), len(outer))
 ins, smp = collections.Counter(), collections.Counter()
 stalls = collections.defaultdict(collections.Counter)
