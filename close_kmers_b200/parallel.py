@@ -150,10 +150,44 @@ class MatrixJob:
         lengths = np.diff(batch.offsets.astype(np.int64))
         self.blocks = shard_rows(lengths, world)
         self.ascending = bool(np.all(np.diff(self.eids.astype(np.int64)) > 0)) if len(self.eids) > 1 else True
+        self._pinned = None
 
     def _sub(self, a, b):
         o = self.batch.offsets
         return self.eids[a:b], self.batch.residues[int(o[a]): int(o[b])], (o[a: b + 1] - o[a]).astype(np.uint64)
+
+    def _gather_sizes(self, vals, ref, dist, torch):
+        """all_gather of a few int64 per rank -> list of lists"""
+        mine = torch.tensor(vals, dtype=torch.int64, device=ref.device)
+        got = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(got, mine, group=self.group)
+        return [[int(x) for x in g] for g in got]
+
+    def _gather_bytes(self, local, sizes, dist, torch):
+        """all_gather of one uint8 tensor per rank (sizes[r] bytes from rank r); returns the per-rank views"""
+        mx = (max(max(sizes), 1) + 15) // 16 * 16
+        send = torch.zeros(mx, dtype=torch.uint8, device=local.device)
+        send[: local.numel()] = local
+        recv = torch.empty(self.world * mx, dtype=torch.uint8, device=local.device)
+        if local.is_cuda:
+            dist.all_gather_into_tensor(recv, send, group=self.group)
+        else:
+            dist.all_gather(list(recv.view(self.world, mx).unbind(0)), send, group=self.group)
+        return [recv[r * mx: r * mx + sizes[r]] for r in range(self.world)]
+
+    def _to_host(self, parts, torch):
+        """the tiles, one after the other, in host memory (page-locked and reused from call to call on a GPU)"""
+        total = sum(int(p.numel()) for p in parts)
+        if not parts or not parts[0].is_cuda:
+            return torch.cat(parts).numpy().view(PAIR_DT) if parts else np.zeros(0, PAIR_DT)
+        if self._pinned is None or self._pinned.numel() < total:
+            self._pinned = torch.empty(max(total, 1 << 20), dtype=torch.uint8, pin_memory=True)
+        o = 0
+        for p in parts:
+            self._pinned[o: o + p.numel()].copy_(p, non_blocking=True)
+            o += int(p.numel())
+        torch.cuda.current_stream(parts[0].device).synchronize()
+        return self._pinned[:total].numpy().view(PAIR_DT).copy()
 
     def run(self):
         import time
@@ -169,21 +203,25 @@ class MatrixJob:
         if world > 1:
             import torch.distributed as dist
             k_local, p_local = ops.export()
-            keys = _all_gather_var(k_local, world, dist, torch, self.group)
-            pegs = _all_gather_var(p_local, world, dist, torch, self.group)
+            n_local = int(k_local.numel())
+            # two collectives: the counts, then keys and peg ids of a rank as one run of bytes (8 n + 4 n)
+            counts = [c[0] for c in self._gather_sizes([n_local], k_local, dist, torch)]
+            packed = torch.cat([k_local.view(torch.uint8), p_local.view(torch.uint8)]) if n_local else torch.zeros(0, dtype=torch.uint8, device=k_local.device)
+            got = self._gather_bytes(packed, [12 * c for c in counts], dist, torch)
+            keys = [g[: 8 * c].view(torch.int64) for g, c in zip(got, counts)]
+            pegs = [g[8 * c: 12 * c].view(torch.int32) for g, c in zip(got, counts)]
             ops.install(torch.cat(keys), torch.cat(pegs))
         t.append(time.perf_counter())
         tile, walked = ops.rows(self.eids, self.batch.residues, self.batch.offsets, a, b)
         t.append(time.perf_counter())
         if world > 1:
-            tiles = _all_gather_var(tile, world, dist, torch, self.group)
+            info = self._gather_sizes([int(tile.numel()), int(walked)], tile, dist, torch)
+            tiles = self._gather_bytes(tile, [i[0] for i in info], dist, torch)
+            walked = sum(i[1] for i in info)
             # every rank holds every tile; the host copy is made where the response is written
-            merged = torch.cat(tiles).cpu().numpy().view(PAIR_DT) if self.rank == 0 else np.zeros(0, PAIR_DT)
-            w = torch.tensor([walked], dtype=torch.int64, device=tile.device)
-            dist.all_reduce(w, group=self.group)
-            walked = int(w)
+            merged = self._to_host(tiles, torch) if self.rank == 0 else np.zeros(0, PAIR_DT)
         else:
-            merged = tile.cpu().numpy().view(PAIR_DT)
+            merged = self._to_host([tile], torch)
         t.append(time.perf_counter())
         if not self.ascending:
             merged = api.merge_pairs(merged)
