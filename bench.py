@@ -156,6 +156,27 @@ def write_image_dir(kdir, protos, n_sigs, rank, with_reference_builder):
     return sig, nb
 
 
+def host_info(local):
+    """Where this rank's GPU hangs and what the process may run on: the end-to-end figures are host-memory / PCIe figures."""
+    info = {"cpus_allowed": cpu_threads()}
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev = torch.cuda.get_device_properties(local).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        info["gpu_pci"] = f"{dom:04x}:{bus:02x}:{dev:02x}.0"
+        info["gpu_numa_node"] = int(open(path).read().strip())
+    except Exception as e:  # not every box exposes it
+        info["gpu_numa_node"] = None
+        info["note"] = f"{type(e).__name__}"
+    try:
+        info["numa_nodes"] = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")])
+    except OSError:
+        pass
+    return info
+
+
 def cpu_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -836,6 +857,7 @@ def main():
                           "entry": "ckm_call_batch: the reference's char* strings concatenated, pinned host memory",
                           "host_read_GBps_per_rank": (total + (n + 1) * 8) / (ms_ascii / K * 1e-3) / 1e9},
             "gpu_launches": int(launches),
+            "host": host_info(local) | {"pinned_buffers": "cudaMallocHost (ckm_host_alloc); one pool per rank"},
             "clocks": clocks,
             "table": {"buckets": guts.num_sigs, "slot_bytes": guts.slot_bytes, "l2_fetch_granularity": guts.l2_fetch_granularity,
                       "occupancy_bitmap": guts.has_occupancy_bitmap, "scan_inside_K1": bool(fused),

@@ -17,13 +17,17 @@ rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 cc.ensure_built()
 ALL = api.WANT_CALLS | api.WANT_HITS | api.WANT_OTU | api.WANT_BEST
 t_start = time.time()
-stats = dict(rounds=0, proteins=0, hits=0, calls=0, family_entries=0, reads=0, hits_from_copy=0)
+stats = dict(rounds=0, proteins=0, hits=0, calls=0, family_entries=0, reads=0, hits_from_copy=0, fused_batches=0)
 for rnd in range(rounds):
     rng = np.random.default_rng(1000 + rnd)
     mean_len = int(rng.choice([60, 150, 300, 600]))
     protos, sig, img = wl.small_world(seed=50 + rnd, n_protos=int(rng.integers(100, 500)), n_sigs=int(rng.integers(20_000, 120_000)),
                                       n_functions=int(rng.choice([3, 40, 400])), otu_mode=str(rng.choice(["mixed", "minus1"])),
                                       mean_len=mean_len, sd=float(rng.choice([0.0, 40.0])))
+    if rnd % 3 == 1:  # signatures a sparse subset of the windows, a share of them of another function (stray hits inside runs)
+        sig = synth.make_signatures_sparse(protos, len(sig.keys), keep=float(rng.choice([0.4, 0.7, 1.0])), foreign=float(rng.choice([0.05, 0.2])),
+                                           n_functions=sig.n_functions, seed=rnd)
+        img = api.build_image(synth.bucket_count(len(sig.keys)), sig.keys, sig.fI, sig.oI, sig.avg, sig.wt)
     fam = synth.make_families(rnd, sig, fams_per_function=int(rng.choice([2, 4, 40])), max_list=int(rng.choice([3, 8, 40])),
                               coverage=float(rng.choice([0.5, 0.9, 1.0])))
     if rnd % 3 == 0:  # wide lists over many families: the vote kernel's overflow / global-scratch paths
@@ -58,6 +62,14 @@ for rnd in range(rounds):
     from_copy = g.chain_info["hits_from_copy"]
     wl.assert_results_equal(got, want, f"round {rnd} calls {prm}")
     assert got["n_probes"] == want["n_probes"]
+    # the same batch asking for calls and best calls only: the scan runs inside K1 (probe_pc_kernel) unless the order constraint
+    # is on; through the ASCII and the packed entry point, and on a world whose signatures are a sparse, mixed-function subset
+    for flags in (api.WANT_CALLS | api.WANT_BEST, api.WANT_BEST):
+        few = g.process_aa_seq_batch(batch.residues, batch.offsets, flags)
+        wl.assert_results_equal(few, {k: want[k] for k in ("call_offsets", "calls", "best") if k in few}, f"round {rnd} fused flags {flags} {prm}")
+        stats["fused_batches"] += int(g.last_batch_was_fused)
+    pk, woff = api.pack_residues(batch.residues, batch.offsets)
+    wl.assert_results_equal(g.process_packed_batch(pk, woff, api.WANT_BEST), {"best": want["best"]}, f"round {rnd} packed entry")
     sc, so = orc.family_scores(batch)
     fs = g.family_scores(batch.residues, batch.offsets)
     assert np.array_equal(fs["score_offsets"], so), f"round {rnd} score offsets"
