@@ -91,6 +91,8 @@ def lib() -> C.CDLL:
     L.ckm_has_occupancy_bitmap.argtypes = [C.c_void_p]
     L.ckm_set_tuning.argtypes = [C.c_void_p, C.c_uint32]
     L.ckm_last_batch_was_fused.argtypes = [C.c_void_p]
+    L.ckm_table_buckets.restype = C.c_uint64
+    L.ckm_table_buckets.argtypes = [C.c_void_p]
     L.ckm_chain_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.ckm_copy_state.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
     L.ckm_set_default_params.argtypes = [C.c_void_p]
@@ -479,6 +481,11 @@ class KmerGuts:
     @property
     def has_occupancy_bitmap(self) -> bool:
         return bool(lib().ckm_has_occupancy_bitmap(self._h))
+
+    @property
+    def table_buckets(self) -> int:
+        """Buckets of the table in HBM (ckm_table_buckets): the image's, or the power of two of the library's own table."""
+        return int(lib().ckm_table_buckets(self._h))
 
     @property
     def copy_state(self) -> dict:

@@ -120,6 +120,40 @@ pack_table_kernel(const uint64_t *__restrict__ raw /* 3 x u64 per slot */, uint6
     packed[i] = v;
 }
 
+// The library's own table: every k-mer of the image re-inserted, by linear probing from own_home(key), into 2^hbits packed slots.
+// An image may hold a k-mer twice (the reference's builder never checks, kguts.cc:202-222); lookup_hash_entry then always ends
+// at the first one in probe order, so only that one is carried over and a lookup here returns what a lookup there returns.
+__global__ void __launch_bounds__(256) fill_empty_kernel(uint4 *__restrict__ slots, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) slots[i] = make_uint4(0u, 0x8u, 0u, 0u);
+}
+__global__ void __launch_bounds__(256)
+rehash_kernel(const uint64_t *__restrict__ raw /* 3 x u64 per slot */, uint64_t image_buckets, uint64_t image_magic, uint4 *__restrict__ slots,
+              uint32_t hbits, unsigned int *__restrict__ misfit) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= image_buckets) return;
+    const uint64_t k = raw[3 * i], a = raw[3 * i + 1], b = raw[3 * i + 2];
+    if (k > CKM_MAX_ENCODED) return;
+    // is slot i where the reference's lookup of k ends?  (every slot between k's home and i is taken: k was inserted past them)
+    for (uint64_t h = fast_mod(k, image_buckets, image_magic); h != i; h = (h + 1 == image_buckets) ? 0 : h + 1)
+        if (raw[3 * h] == k) return;
+    const int32_t oI = (int32_t)(uint32_t)a;
+    const uint32_t avg = (uint32_t)(a >> 32) & 0xFFFFu, fI = (uint32_t)b, wt = (uint32_t)(b >> 32), o1 = (uint32_t)(oI + 1);
+    if (fI >= kPackedFieldLimit || oI < -1 || o1 >= kPackedFieldLimit) {
+        atomicOr(misfit, 1u);
+        return;
+    }
+    const uint32_t x = (uint32_t)k, y = (uint32_t)(k >> 32) | (avg << 4) | ((o1 & 0xFFFu) << 20);
+    const unsigned long long mine = (unsigned long long)x | ((unsigned long long)y << 32), empty = 0x8ull << 32;
+    const uint32_t mask = hbits == 32u ? 0xFFFFFFFFu : (1u << hbits) - 1u;
+    for (uint32_t h = own_home(k, hbits);; h = (h + 1u) & mask) {
+        if (atomicCAS(reinterpret_cast<unsigned long long *>(slots + h), empty, mine) == empty) {
+            reinterpret_cast<uint2 *>(slots + h)[1] = make_uint2(wt, (fI & (kPackedFieldLimit - 1)) | ((o1 >> 12) << 22));
+            return;
+        }
+    }
+}
+
 // bit h of occupied[] = slot h holds a k-mer; one thread per 32 slots
 template <bool PACKED>
 __global__ void __launch_bounds__(256)
@@ -196,6 +230,52 @@ static int upload_table(ckm_ctx *c, const ckm_image_header_t *hdr) {
 static int install_table(ckm_ctx *c, DevBuf raw, uint64_t n) {
     DevBuf packed, flag;
     unsigned int misfit = 0;
+    c->image_buckets = n;
+    c->hbits = 0;
+    // The library's own table (rehash_kernel) where it applies: 16-byte slots fit the image's fields, fewer than 2^32 buckets,
+    // and room for it beside the image for a moment.  Otherwise the image's order and hashing stay (packed or verbatim slots).
+    if (!c->force_raw && !c->reference_hash && n) {
+        uint32_t hbits = 6;
+        while (hbits < 31u && (1ull << hbits) < n) hbits++;
+        if ((1ull << hbits) >= n) {
+            const uint64_t nb = 1ull << hbits;
+            DevBuf own;
+            auto body = [&]() -> int {
+                RC(flag.ensure(256));
+                CU(cudaMemsetAsync(flag.p, 0, 4, c->stream));
+                fill_empty_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, c->stream>>>((uint4 *)own.p, nb);
+                rehash_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const uint64_t *)raw.p, n, (uint64_t)((((unsigned __int128)1) << 64) / n),
+                                                                                   (uint4 *)own.p, hbits, (unsigned int *)flag.p);
+                c->launches += 2;
+                CU(cudaMemcpyAsync(&misfit, flag.p, 4, cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+                CU(cudaGetLastError());
+                return 0;
+            };
+            if (own.ensure((size_t)nb * kPackedSlotBytes + 64) == 0) {
+                const int rc = body();
+                flag.release();
+                if (rc) {
+                    cudaStreamSynchronize(c->stream);
+                    own.release();
+                    raw.release();
+                    return rc;
+                }
+                if (!misfit) {
+                    raw.release();
+                    c->table = own;
+                    c->slot_bytes = kPackedSlotBytes;
+                    c->hbits = hbits;
+                    n = nb;  // from here on: the buckets of the table in HBM
+                } else {
+                    own.release();  // a field does not fit 22 bits: the verbatim slots below
+                }
+            } else {
+                (void)cudaGetLastError();
+            }
+        }
+    }
+    if (!c->hbits) {
     // raw + packed need 40 B per bucket for a moment: without room for the packed copy the verbatim slots serve (RAW kernels)
     bool no_room = !c->force_raw && packed.ensure((size_t)n * kPackedSlotBytes + 64) != 0;
     if (no_room) {
@@ -238,6 +318,7 @@ static int install_table(ckm_ctx *c, DevBuf raw, uint64_t n) {
         raw.release();
         c->table = packed;
         c->slot_bytes = kPackedSlotBytes;
+    }
     }
     c->num_sigs = n;
     c->magic = n ? (uint64_t)((((unsigned __int128)1) << 64) / n) : 0;
@@ -309,6 +390,7 @@ static int build_chain(ckm_ctx *c) {
     tv.num_sigs = n;
     tv.magic = c->magic;
     tv.m35 = magic35(n);
+    tv.hbits = c->hbits;
     tv.occupied = (const uint32_t *)c->occupied.p;
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
@@ -418,6 +500,7 @@ static int ctx_create(int device, ckm_ctx **out) {
     if (const char *pr = getenv("CKM_PIPELINE_RAMP_DIV")) c->pipeline_ramp_div = std::max(1, atoi(pr));
     if (const char *pt = getenv("CKM_PIPELINE_TAIL_DIV")) c->pipeline_tail_div = std::max(1, atoi(pt));
     if (const char *pm = getenv("CKM_PIPELINE_MIN_KB")) c->pipeline_min_bytes = (uint64_t)atol(pm) << 10;
+    if (const char *rh = getenv("CKM_REFERENCE_HASH")) c->reference_hash = rh[0] == '1';
     const char *fr = getenv("CKM_FORCE_RAW_SLOTS");
     c->force_raw = fr && fr[0] == '1';
     if (const char *pg = getenv("CKM_PROBE_GROUP")) {
@@ -545,6 +628,8 @@ extern "C" int ckm_clone(ckm_ctx *parent, ckm_ctx **out) {
     c->n_chain = parent->n_chain;
     c->n_chains = parent->n_chains;
     c->num_sigs = parent->num_sigs;
+    c->image_buckets = parent->image_buckets;
+    c->hbits = parent->hbits;
     c->magic = parent->magic;
     c->slot_bytes = parent->slot_bytes;
     c->force_raw = parent->force_raw;
@@ -604,7 +689,8 @@ extern "C" const char *ckm_otu_at_index(const ckm_ctx *c, int32_t i) {
 }
 extern "C" int32_t ckm_function_count(const ckm_ctx *c) { return (int32_t)c->functions.size(); }
 extern "C" int32_t ckm_otu_count(const ckm_ctx *c) { return (int32_t)c->otu_names.size(); }
-extern "C" uint64_t ckm_num_sigs(const ckm_ctx *c) { return c->num_sigs; }
+extern "C" uint64_t ckm_num_sigs(const ckm_ctx *c) { return c->image_buckets; }
+extern "C" uint64_t ckm_table_buckets(const ckm_ctx *c) { return c->num_sigs; }
 extern "C" int ckm_table_slot_bytes(const ckm_ctx *c) { return c->slot_bytes; }
 extern "C" int ckm_l2_fetch_granularity(const ckm_ctx *c) { return c->l2_fetch; }
 extern "C" void ckm_set_tuning(ckm_ctx *c, uint32_t bits) { c->tuning = bits; }
@@ -814,6 +900,7 @@ static TableView table_view(const ckm_ctx *c) {
     tv.cpay = (const uint2 *)c->cpay.p;
     tv.n_chain = c->n_chain;
     tv.m35 = magic35(c->num_sigs);
+    tv.hbits = c->hbits;
     return tv;
 }
 

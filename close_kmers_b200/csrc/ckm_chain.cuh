@@ -45,7 +45,7 @@ __device__ __forceinline__ bool packed_match(const uint4 &v, uint64_t key) {
 
 // lookup_hash_entry (kguts.cc:585-602) over the packed table: slot index of `key`, or kNoSlot
 __device__ __forceinline__ uint32_t packed_find(const TableView &tv, uint64_t key, uint4 &v) {
-    uint64_t h = fast_mod(key, tv.num_sigs, tv.magic);
+    uint64_t h = table_home(tv, key);
     for (uint64_t guard = 0; guard < tv.num_sigs; guard++) {
         if (tv.occupied && !((__ldg(tv.occupied + (h >> 5)) >> (h & 31u)) & 1u)) return kNoSlot;
         v = __ldg(reinterpret_cast<const uint4 *>(tv.slots) + h);
@@ -262,7 +262,7 @@ probe_chain_kernel(TableView tv, const uint8_t *__restrict__ residues, const uin
                 const uint32_t act = tk.act;
                 uint32_t h[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) h[j] = (uint32_t)fast_mod(tk.key[j], tv.num_sigs, tv.magic);
+                for (int j = 0; j < 4; j++) h[j] = (uint32_t)table_home(tv, tk.key[j]);
 
                 HitWords hv[4];       // the slot behind each hit
                 uint32_t hm = 0;      // windows that hit

@@ -48,7 +48,16 @@ struct TableView {
     const uint2 *cpay;
     uint32_t n_chain;
     uint32_t m35;  // floor(2^35 / num_sigs) when 64 <= num_sigs < 2^32 (fast_mod35), else 0
+    // != 0: the table is the library's own -- 2^hbits 16-byte slots, home bucket = top hbits bits of a multiplicative hash of the
+    // key (own_home), every key of the image re-inserted by linear probing (rehash_kernel) -- instead of the image's slots in the
+    // image's order under key % num_sigs.  A lookup is a function of the key alone, so it returns the same fields either way;
+    // the hash costs 3 instructions where the modulo by the image's (odd, non-power-of-two) bucket count costs 13, four times
+    // per lane and step of K1.
+    uint32_t hbits;
 };
+__host__ __device__ __forceinline__ uint32_t own_home(uint64_t key, uint32_t hbits) {
+    return ((uint32_t)key * 0x9E3779B1u + (uint32_t)(key >> 32) * 0x85EBCA77u) >> (32u - hbits);
+}
 
 // One table hit as the ordered scoring scan consumes it (KmerHit, kguts.h:154-163, minus the key).
 struct __align__(16) HitRec {
@@ -125,7 +134,12 @@ __device__ __forceinline__ uint32_t fast_mod35(uint64_t key, uint32_t d, uint32_
 }
 // home bucket of a valid 8-mer key
 __device__ __forceinline__ uint64_t table_home(const TableView &tv, uint64_t key) {
+    if (tv.hbits) return own_home(key, tv.hbits);
     return tv.m35 ? (uint64_t)fast_mod35(key, (uint32_t)tv.num_sigs, tv.m35) : fast_mod(key, tv.num_sigs, tv.magic);
+}
+// the same without fast_mod35 (probe_kernel: the 32-bit path costs it sixteen registers, profiles/r1/tune_hint_v11_1M.jsonl)
+__device__ __forceinline__ uint64_t table_home_wide(const TableView &tv, uint64_t key) {
+    return tv.hbits ? (uint64_t)own_home(key, tv.hbits) : fast_mod(key, tv.num_sigs, tv.magic);
 }
 static inline uint32_t magic35(uint64_t num_sigs) {
     return (num_sigs >= 64 && num_sigs < 0xFFFFFFFFull) ? (uint32_t)((1ull << 35) / num_sigs) : 0u;

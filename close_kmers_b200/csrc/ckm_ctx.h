@@ -53,7 +53,10 @@ struct ckm_ctx {
     int l2_bytes = 0;
     bool has_l2_window = false;
     cudaAccessPolicyWindow l2_window;  // persisting window over `occupied`
-    uint64_t num_sigs = 0, magic = 0;
+    uint64_t num_sigs = 0, magic = 0;  // buckets of the table in HBM (the image's, or the library's own power of two)
+    uint64_t image_buckets = 0;        // num_sigs of the image header (what ckm_num_sigs reports)
+    uint32_t hbits = 0;                // TableView::hbits
+    bool reference_hash = false;       // CKM_REFERENCE_HASH=1 (read once): keep the image's slot order and key % num_sigs
     int slot_bytes = 0;
 
     std::vector<std::string> functions, otu_names;  // function.index / otu.index

@@ -78,7 +78,7 @@ hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64_t *
             }
             uint32_t hint = kNoHint;
             if (!(bad & kInvalidCode)) {
-                uint32_t h = tv.m35 ? fast_mod35(key, nsig, tv.m35) : (uint32_t)fast_mod(key, tv.num_sigs, tv.magic);
+                uint32_t h = (uint32_t)table_home(tv, key);
                 for (uint32_t steps = 0; steps < nsig; steps++) {
                     if (tv.occupied && !((__ldg(tv.occupied + (h >> 5)) >> (h & 31u)) & 1u)) break;
                     const uint4 v = __ldg(slots + h);
@@ -135,7 +135,6 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
     constexpr uint64_t pol_last = 0;
 #endif
     const uint64_t pol_first = policy_evict_first();
-    const uint32_t m35 = tv.m35;
 
     for (uint32_t i = warp0; i < n; i += n_warps) {
         const uint64_t seq_base = __ldg(offsets + i);
@@ -206,7 +205,7 @@ probe_hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint
                 }
                 uint32_t h[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) h[j] = m35 ? fast_mod35(tk.key[j], nsig, m35) : (uint32_t)fast_mod(tk.key[j], tv.num_sigs, tv.magic);
+                for (int j = 0; j < 4; j++) h[j] = (uint32_t)table_home(tv, tk.key[j]);
 
                 // ---- occupancy words (L2) ----
                 uint32_t bw[4] = {0u, 0u, 0u, 0u};

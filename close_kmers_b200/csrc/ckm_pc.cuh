@@ -260,7 +260,6 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
     const uint32_t nsig = (uint32_t)tv.num_sigs;
     uint32_t my_probes = 0, my_hits = 0, my_chain = 0;
     const uint64_t pol_first = policy_evict_first();
-    const uint32_t m35 = tv.m35;
 
     const uint32_t max_gap = (uint32_t)fa.prm.max_gap;
     const int min_hits = fa.prm.min_hits;
@@ -615,7 +614,7 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
                     if (t0 == 0 && hints && i + 1 < c1 && lane == 2u) prefetch_l2(hints + hint_region(seq_base + len, index_base + i + 1));
                     uint32_t h[4];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) h[j] = m35 ? fast_mod35(tk.key[j], nsig, m35) : (uint32_t)fast_mod(tk.key[j], tv.num_sigs, tv.magic);
+                    for (int j = 0; j < 4; j++) h[j] = (uint32_t)table_home(tv, tk.key[j]);
 
                     // ---- occupancy words (L2) ----
                     uint32_t bw[4] = {0u, 0u, 0u, 0u};
@@ -672,7 +671,7 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
                         for (uint32_t k = lane; k < n_left; k += 32u) {
                             const uint2 it = queue[k];
                             const uint64_t key = (uint64_t)it.x | ((uint64_t)(it.y & 0xFFu) << 32);
-                            const uint32_t h0 = m35 ? fast_mod35(key, nsig, m35) : (uint32_t)fast_mod(key, tv.num_sigs, tv.magic);
+                            const uint32_t h0 = (uint32_t)table_home(tv, key);
                             uint32_t hh = h0;
                             uint4 v = ldg_v4_hint(slots + hh, pol_first);
                             const uint32_t ow0 = tv.occupied ? __ldg(tv.occupied + (hh >> 5)) : 0u;

@@ -215,7 +215,7 @@ probe_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64_t 
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     key[j] = tk.key[j];
-                    h[j] = fast_mod(key[j], tv.num_sigs, tv.magic);
+                    h[j] = table_home_wide(tv, key[j]);
                 }
 
                 // ---- probe: occupancy bits from L2 first, then the sector loads that are still needed ----

@@ -150,6 +150,10 @@ int32_t ckm_function_count(const ckm_ctx *ctx);
 int32_t ckm_otu_count(const ckm_ctx *ctx);
 uint64_t ckm_num_sigs(const ckm_ctx *ctx);
 /* 16 = packed sector-friendly slots, 24 = verbatim slots (chosen at load, results identical) */
+/* Buckets of the table as it sits in HBM: the image's count, or -- the default for images whose fields fit the 16-byte slots -- the
+ * power of two at or above it of the library's own open-addressed table, filled from the image at load with a cheaper hash
+ * (CKM_REFERENCE_HASH=1 keeps the image's order and key % num_sigs).  ckm_num_sigs reports the image's count. */
+uint64_t ckm_table_buckets(const ckm_ctx *ctx);
 int ckm_table_slot_bytes(const ckm_ctx *ctx);
 /* cudaLimitMaxL2FetchGranularity in effect on the ctx's device (the loader asks for 32-byte sectors) */
 int ckm_l2_fetch_granularity(const ckm_ctx *ctx);

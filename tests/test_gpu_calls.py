@@ -294,3 +294,29 @@ def test_image_built_on_gpu_is_byte_identical(checkers, world):
     wl.assert_results_equal(g2.process_aa_seq_batch(batch.residues, batch.offsets, ALL), orc.call_batch(batch, ALL), "ckm_open_built")
     assert g2.slot_bytes == guts.slot_bytes
     g2.close()
+
+
+@pytest.mark.parametrize("chain", ["0", "1"])
+def test_reference_hash_layout_and_own_table_agree(checkers, world, chain):
+    """The default table is the library's own (a power of two of 16-byte slots under a multiplicative hash, filled from the image
+    at load); CKM_REFERENCE_HASH=1 keeps the image's slot order and key % num_sigs.  Same answers, with and without the copy."""
+    protos, sig, img, orc, guts, _ = world
+    assert guts.table_buckets >= guts.num_sigs and guts.table_buckets & (guts.table_buckets - 1) == 0
+    os.environ.update(CKM_REFERENCE_HASH="1", CKM_CHAIN=chain, CKM_OCCUPANCY_BITMAP="1")
+    try:
+        g = api.KmerGuts(image=img, function_names=synth.function_names(sig.n_functions))
+    finally:
+        for k in ("CKM_REFERENCE_HASH", "CKM_CHAIN", "CKM_OCCUPANCY_BITMAP"):
+            os.environ.pop(k, None)
+    try:
+        assert g.table_buckets == g.num_sigs == guts.num_sigs and g.slot_bytes == 16
+        batch = wl.concat_batches(wl.edge_batch(protos), synth.make_proteins(31, protos, 2500))
+        orc.set_params()
+        g.set_default_parameters()
+        want = orc.call_batch(batch, ALL)
+        wl.assert_results_equal(g.process_aa_seq_batch(batch.residues, batch.offsets, ALL), want, f"reference hash, chain={chain}")
+        few = g.process_aa_seq_batch(batch.residues, batch.offsets, api.WANT_CALLS | api.WANT_BEST)
+        assert g.last_batch_was_fused
+        wl.assert_results_equal(few, {k: want[k] for k in ("call_offsets", "calls", "best")}, f"reference hash fused, chain={chain}")
+    finally:
+        g.close()
