@@ -700,7 +700,7 @@ def main():
     barrier()
     t0 = time.time()
     guts = api.KmerGuts(kmer_dir=kdir, device=local)
-    log(f"[bench r{rank}] table resident in HBM: {guts.num_sigs} buckets x {guts.slot_bytes} B in {time.time() - t0:.1f}s")
+    log(f"[bench r{rank}] table resident in HBM: {guts.table_buckets} buckets x {guts.slot_bytes} B (image: {guts.num_sigs} buckets) in {time.time() - t0:.1f}s")
     guts.set_default_parameters()
     flags = api.WANT_BEST
     n = batch.n
@@ -859,7 +859,7 @@ def main():
             "gpu_launches": int(launches),
             "host": host_info(local) | {"pinned_buffers": "cudaMallocHost (ckm_host_alloc); one pool per rank"},
             "clocks": clocks,
-            "table": {"buckets": guts.num_sigs, "slot_bytes": guts.slot_bytes, "l2_fetch_granularity": guts.l2_fetch_granularity,
+            "table": {"buckets": guts.num_sigs, "buckets_in_hbm": guts.table_buckets, "slot_bytes": guts.slot_bytes, "l2_fetch_granularity": guts.l2_fetch_granularity,
                       "occupancy_bitmap": guts.has_occupancy_bitmap, "scan_inside_K1": bool(fused),
                       "neighbour_copy": {"entries": chain["entries"], "chains": chain["chains"], "build_ms": chain["build_ms"],
                                          "hits_answered_from_copy": chain["hits_from_copy"],
