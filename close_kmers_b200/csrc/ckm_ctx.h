@@ -30,7 +30,7 @@ struct ckm_ctx {
     cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: second lane of the pipelined host path
     cudaEvent_t ev_ready = nullptr, ev_done2 = nullptr;
     uint64_t pipeline_chunk_bytes = 48ull << 20, pipeline_min_bytes = 32ull << 20;  // 48 MB: profiles/r1/tune_e2e_chunk_sizes_r1g.jsonl
-    uint32_t pipeline_ramp_div = 12, pipeline_tail_div = 8;   // first chunk = chunk/ramp_div (then doubling), last = chunk/tail_div
+    uint32_t pipeline_ramp_div = 6, pipeline_tail_div = 4;    // first chunk = chunk/ramp_div (then doubling), last = chunk/tail_div (profiles/r2/tune_e2e_r2c.jsonl)
     bool force_raw = false;
     uint32_t tuning = 0;  // TableView::tuning
     uint32_t probe_group_override = 0;  // CKM_PROBE_GROUP (read once at ctx creation)

@@ -29,7 +29,7 @@ api._check(L.ckm_host_alloc(C.byref(hp_pk), pk.nbytes + 64))
 api._check(L.ckm_host_alloc(C.byref(hp_woff), (batch.n + 1) * 8))
 C.memmove(hp_pk.value, pk.ctypes.data, pk.nbytes)
 C.memmove(hp_woff.value, woff.ctypes.data, (batch.n + 1) * 8)
-for chunk_kb, ramp, tail in ((49152, 12, 8), (49152, 24, 16), (32768, 16, 8), (32768, 32, 16), (24576, 12, 8), (24576, 24, 16), (16384, 8, 8), (16384, 16, 16), (12288, 8, 8), (8192, 8, 8)):
+for chunk_kb, ramp, tail in ((49152, 12, 8), (65536, 16, 8), (65536, 8, 4), (98304, 12, 6), (98304, 24, 8), (131072, 16, 8), (131072, 32, 16), (32768, 8, 8), (49152, 6, 4), (196608, 24, 12)):
     os.environ["CKM_PIPELINE_CHUNK_KB"] = str(chunk_kb)
     os.environ["CKM_PIPELINE_RAMP_DIV"] = str(ramp)
     os.environ["CKM_PIPELINE_TAIL_DIV"] = str(tail)
