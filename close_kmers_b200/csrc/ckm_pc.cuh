@@ -308,10 +308,15 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
         uint32_t e_last = 0;  // the step's last hit (window index)
         bool pre = false;     // the step's first hit completes a run-ending pair with the last hit of the step before
         bool simple = false;
+        uint32_t wz[4] = {0u, 0u, 0u, 0u};  // weights of this lane's four windows (whatever is there for windows that did not hit)
         if (anyb) {
             uint32_t fi[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) fi[j] = staged(4u * lane + j).y;  // (whatever is there for windows that did not hit)
+            for (int j = 0; j < 4; j++) {
+                const uint2 z = staged(4u * lane + j);
+                wz[j] = z.x;
+                fi[j] = z.y;
+            }
             const uint32_t fl = __ffs(anyb) - 1u, ll = 31u - __clz(anyb);  // first / last lane with a hit
             n_step = __reduce_add_sync(full, __popc(hm));
             const uint32_t e0 = 4u * fl + (__ffs(__shfl_sync(full, hm, fl)) - 1u);
@@ -432,9 +437,13 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
             // the run that ends here: a run-ending pair flushes unconditionally (852-856), a gap only a run of min_hits stored
             // hits (821-831), the end of the protein likewise (873-876); a call needs min_hits matching hits (753) and, by
             // the scan lane's judgement, its weighted sum
-            if (kind == 0u || (kind == 1u && !is_begin)) flags = (int)cnt >= min_hits ? kPcEmit : kPcReset;
-            else if (kind == 1u && num > 0u) flags = ((int)num >= min_hits && (int)cnt >= min_hits) ? kPcEmit : kPcReset;
-            else if (kind == 2u && last) flags = kPcEnd | ((int)num < min_hits ? 0u : (int)cnt >= min_hits ? kPcEmit : kPcReset);
+            if (kind == 2u) {
+                if (last) flags = kPcEnd | ((int)num < min_hits ? 0u : (int)cnt >= min_hits ? kPcEmit : kPcReset);
+            } else if (kind == 0u || !is_begin) {
+                flags = (int)cnt >= min_hits ? kPcEmit : kPcReset;
+            } else if (num > 0u) {
+                flags = ((int)num >= min_hits && (int)cnt >= min_hits) ? kPcEmit : kPcReset;
+            }
             if (flags || prepend || ab) {
                 // the record: this lane's weights of a4, compacted in position order (behind the carried hit's if `prepend`)
                 wait_slot();
@@ -453,7 +462,7 @@ probe_pc_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64
                     n_w += __shfl_sync(full, incl, 31);
 #pragma unroll
                     for (int j = 0; j < 4; j++)
-                        if (a4 & (1u << j)) W[o + __popc(a4 & ((1u << j) - 1u))] = __uint_as_float(stage[stage8_at(4u * lane + j)].x);
+                        if (a4 & (1u << j)) W[o + __popc(a4 & ((1u << j) - 1u))] = __uint_as_float(wz[j]);
                 }
                 if (lane < 4u) W[n_w + lane] = 0.0f;  // x + (+0) == x: the scan lane adds the weights four at a time
                 if (lane == 0) {
