@@ -405,7 +405,7 @@ static int build_chain(ckm_ctx *c) {
         RC(len.ensure(n * 4 + 64));
         RC(start.ensure((n + 1) * 8));
         RC(flag.ensure(64));
-        RC(c->cpos.ensure(n * 4 + 64));
+        RC(c->cpos.ensure(n * 8 + 64));
         const unsigned blocks = (unsigned)((n + 255) / 256);
         CU(cudaMemsetAsync(claim.p, 0xFF, n * 8, c->stream));
         CU(cudaMemsetAsync(len.p, 0, n * 4, c->stream));
@@ -438,7 +438,7 @@ static int build_chain(ckm_ctx *c) {
         RC(c->chain.ensure((total + 32) * sizeof(uint4)));
         CU(cudaMemsetAsync(c->chain.p, 0xFF, (total + 32) * sizeof(uint4), c->stream));
         chain_place_kernel<<<blocks, 256, 0, c->stream>>>(tv, (const uint64_t *)pd.p, (const uint64_t *)start.p, (uint4 *)c->chain.p,
-                                                          (uint32_t *)c->cpos.p, (unsigned long long *)flag.p + 1);
+                                                          (uint2 *)c->cpos.p, (unsigned long long *)flag.p + 1);
         RC(c->cres.ensure(total + 256));
         RC(c->cpay.ensure((total + 32) * sizeof(uint2)));
         CU(cudaMemsetAsync(c->cres.p, kCresNone, total + 256, c->stream));
@@ -895,7 +895,7 @@ static TableView table_view(const ckm_ctx *c) {
     tv.occupied = (const uint32_t *)c->occupied.p;
     tv.tuning = c->tuning;
     tv.chain = (const uint4 *)c->chain.p;
-    tv.cpos = (const uint32_t *)c->cpos.p;
+    tv.cpos = (const uint2 *)c->cpos.p;
     tv.cres = (const uint8_t *)c->cres.p;
     tv.cpay = (const uint2 *)c->cpay.p;
     tv.n_chain = c->n_chain;

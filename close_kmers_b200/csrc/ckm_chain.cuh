@@ -193,18 +193,20 @@ chain_compact_kernel(TableView tv, const uint64_t *__restrict__ pd, const uint64
 // step 3b: copy every member to chain[start[root] + distance]
 __global__ void __launch_bounds__(256)
 chain_place_kernel(TableView tv, const uint64_t *__restrict__ pd, const uint64_t *__restrict__ start, uint4 *__restrict__ chain,
-                   uint32_t *__restrict__ cpos, unsigned long long *__restrict__ n_roots) {
+                   uint2 *__restrict__ cpos, unsigned long long *__restrict__ n_roots) {
     const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool root = false;
     if (h < tv.num_sigs) {
         const uint64_t x = pd[h];
-        uint32_t pos = kNoSlot;
+        uint32_t pos = kNoSlot, tag = 0xFFFFFFFFu;
         if (x != kNoPd) {
             pos = (uint32_t)(start[(uint32_t)x] + (x >> 32));
-            chain[pos] = __ldg(reinterpret_cast<const uint4 *>(tv.slots) + h);
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(tv.slots) + h);
+            chain[pos] = v;
+            tag = v.x;
             root = x == h;
         }
-        cpos[h] = pos;
+        cpos[h] = make_uint2(tag, pos);
     }
     const uint32_t b = __ballot_sync(0xffffffffu, root);
     if ((threadIdx.x & 31u) == 0 && b) atomicAdd(n_roots, (unsigned long long)__popc(b));
@@ -327,7 +329,7 @@ probe_chain_kernel(TableView tv, const uint8_t *__restrict__ residues, const uin
                     if (spec) {
 #pragma unroll
                         for (int j = 0; j < 4; j++)
-                            if (anchors & (1u << j)) ab[j] = __ldg(tv.cpos + h[j]);
+                            if (anchors & (1u << j)) ab[j] = __ldg(tv.cpos + h[j]).y;
                     }
                     // linear probing, the lane's windows side by side: h = (h+1) % size_hash until match or empty (kguts.cc:585-602)
                     uint32_t pend = anchors, ah = 0, steps = 0;
@@ -366,7 +368,7 @@ probe_chain_kernel(TableView tv, const uint8_t *__restrict__ residues, const uin
                         t_anchor += __popc(ah);
 #pragma unroll
                         for (int j = 0; j < 4; j++)
-                            if ((ah & (1u << j)) && !(spec && (home & (1u << j)))) ab[j] = __ldg(tv.cpos + h[j]);
+                            if ((ah & (1u << j)) && !(spec && (home & (1u << j)))) ab[j] = __ldg(tv.cpos + h[j]).y;
                         uint32_t last = 0;
 #pragma unroll
                         for (int j = 0; j < 4; j++) {

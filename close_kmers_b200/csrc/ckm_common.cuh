@@ -42,7 +42,10 @@ struct TableView {
     uint32_t tuning;
     // Neighbour-ordered copy of the occupied slots and each slot's index in it (ckm_chain.cuh); NULL when not built.
     const uint4 *chain;
-    const uint32_t *cpos;
+    // per table slot: (low 32 bits of its k-mer, its index in the copy) -- what hint_kernel needs of a slot, in ONE 8-byte read
+    // instead of the slot and the index from two arrays; .y == 0xFFFFFFFF: an empty slot.  Hints steer, keys decide: a k-mer
+    // that differs from the sampled one in its top three bits only yields a useless hint, never a wrong answer.
+    const uint2 *cpos;
     // the compact form of the copy (chain_compact_kernel): residue string and (weight, function word) per index
     const uint8_t *cres;
     const uint2 *cpay;

@@ -55,7 +55,6 @@ hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64_t *
     const uint32_t sub = threadIdx.x & (kHintLanes - 1);
     const uint32_t g0 = (blockIdx.x * blockDim.x + threadIdx.x) / kHintLanes;
     const uint32_t n_groups = (gridDim.x * blockDim.x) / kHintLanes;
-    const uint4 *__restrict__ slots = reinterpret_cast<const uint4 *>(tv.slots);
     const uint32_t nsig = (uint32_t)tv.num_sigs;
     for (uint32_t i = g0; i < n; i += n_groups) {
         const uint64_t seq_base = __ldg(offsets + i);
@@ -81,13 +80,12 @@ hint_kernel(TableView tv, const uint8_t *__restrict__ residues, const uint64_t *
                 uint32_t h = (uint32_t)table_home(tv, key);
                 for (uint32_t steps = 0; steps < nsig; steps++) {
                     if (tv.occupied && !((__ldg(tv.occupied + (h >> 5)) >> (h & 31u)) & 1u)) break;
-                    const uint4 v = __ldg(slots + h);
-                    const uint32_t cp = __ldg(tv.cpos + h);  // requested with the slot: one round trip instead of two on a hit
-                    if (packed_match(v, key)) {
-                        hint = cp - p;
+                    const uint2 t = __ldg(tv.cpos + h);  // (k-mer low word, index in the copy): one DRAM access per slot looked at
+                    if (t.y == kNoSlot) break;           // an empty slot (or one no lookup ends at)
+                    if (t.x == (uint32_t)key) {
+                        hint = t.y - p;
                         break;
                     }
-                    if (v.y & 0x8u) break;
                     h = (h + 1u == nsig) ? 0u : h + 1u;
                 }
             }
