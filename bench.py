@@ -10,7 +10,7 @@ is BASELINE.json configs[1] ("c2": 1M proteins, mean 300 aa, vs a 100M-k-mer ima
 
 Keys of the JSON line: see DESIGN.md "Measurement".  `value` is kernel-resident (inputs already in HBM); `e2e` goes
 through the C ABI with pinned HOST buffers (H2D + kernels + D2H inside the timed region) -- ckm_call_batch_packed, the
-entry point a parser feeds (5 bits per residue), with `e2e_ascii` (ckm_call_batch, the reference's char* strings) beside it.
+entry point a parser feeds (seven residues per 32-bit word), with `e2e_ascii` (ckm_call_batch, the reference's char* strings) beside it.
 Sub-records of the same line: `sparse_signatures` (a signature set that is a sparse subset of the windows: the neighbour copy
 pinned on, plain probing, and what the automatic fall-back picks), `c3_stream` (BASELINE configs[2]: 100M proteins streamed against an 80M-k-mer image, strong-scaled
 over the ranks), `fq` (configs[3]: reads -> 6 frames -> calling -> family voting -> best frame) and `matrix` (configs[4]: 50k
@@ -261,7 +261,7 @@ def emit(line: dict):
 
 
 class Pinned:
-    """A batch in page-locked host memory: ASCII residues + offsets, and the 5-bit packed form + word offsets."""
+    """A batch in page-locked host memory: ASCII residues + offsets, and the packed form (seven residues per word) + word offsets."""
 
     def __init__(self, api, batch, packed=True):
         self.api, self.L = api, api.lib()
@@ -849,7 +849,7 @@ def main():
                                                         "(DESIGN.md section 6); probes/s / accesses_per_s = fraction of it"}},
             "e2e": {"value": prot_all * K / (ms_packed * 1e-3), "unit": "proteins/s", "ms_per_step": ms_packed / K,
                     "h2d_bytes_per_step": h2d_packed, "d2h_bytes_per_step": n * 28 + 64,
-                    "entry": "ckm_call_batch_packed: residues packed five bits apiece in pinned host memory (what a parser emits in the "
+                    "entry": "ckm_call_batch_packed: residues packed seven to a 32-bit word (base 22) in pinned host memory (what a parser emits in the "
                              "pass it makes over every byte), unpacked on the device behind each chunk's copy",
                     "host_read_GBps_per_rank": h2d_packed / (ms_packed / K * 1e-3) / 1e9},
             "e2e_ascii": {"value": prot_all * K / (ms_ascii * 1e-3), "unit": "proteins/s", "ms_per_step": ms_ascii / K,

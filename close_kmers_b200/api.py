@@ -167,13 +167,13 @@ def lib() -> C.CDLL:
 
 
 def pack_residues(residues: np.ndarray, offsets: np.ndarray) -> tuple:
-    """ASCII batch -> (packed uint32 words, word offsets): five bits per residue, every sequence from a word boundary
-    (csrc/ckm_packed.cuh)."""
+    """ASCII batch -> (packed uint32 words, word offsets): seven residues per word (base 22), every sequence from a word
+    boundary (csrc/ckm_packed.cuh)."""
     residues = np.ascontiguousarray(residues, np.uint8)
     offsets = np.ascontiguousarray(offsets, np.uint64)
     n = len(offsets) - 1
     lens = np.diff(offsets.astype(np.int64))
-    cap = int(((5 * lens + 31) // 32).sum()) if n else 0
+    cap = int(((lens + 6) // 7).sum()) if n else 0
     packed = np.zeros(cap + 2, np.uint32)
     woff = np.zeros(n + 1, np.uint64)
     _check(lib().ckm_pack_residues(residues.ctypes.data, offsets.ctypes.data, n, packed.ctypes.data, cap, woff.ctypes.data))
@@ -555,7 +555,7 @@ class KmerGuts:
         return r
 
     def process_packed_batch(self, packed: np.ndarray, word_offsets: np.ndarray, flags: int) -> dict:
-        """process_aa_seq_batch for residues packed five bits apiece (pack_residues below; ckm_call_batch_packed)."""
+        """process_aa_seq_batch for residues packed seven to a 32-bit word (pack_residues; ckm_call_batch_packed)."""
         packed = np.ascontiguousarray(packed, np.uint32)
         word_offsets = np.ascontiguousarray(word_offsets, np.uint64)
         n = len(word_offsets) - 1

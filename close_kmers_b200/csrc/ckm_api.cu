@@ -1245,7 +1245,7 @@ static int pipeline_abort(ckm_ctx *c, int rc) {
 // pipeline_chunk_bytes residues that alternate between two CUDA streams, so that the H2D copy of chunk k+1 and the
 // D2H copy of chunk k-1 overlap the kernels of chunk k.  All chunks share the per-batch regions (indexed by residue
 // offset / sequence index, hence disjoint), so nothing is double-buffered.
-// `packed` != NULL: `offsets` are word offsets into the 5-bit packed stream (ckm_packed.cuh); every chunk is unpacked on the
+// `packed` != NULL: `offsets` are word offsets into the packed words (ckm_packed.cuh); every chunk is unpacked on the
 // device behind its copy, and one sequence takes 8 residue slots per word there.
 static int call_batch_pipelined(ckm_ctx *c, const char *residues, const uint32_t *packed, const uint64_t *offsets, uint32_t n,
                                 ckm_batch_out_t *out) {
@@ -1338,7 +1338,7 @@ static int call_batch_pipelined(ckm_ctx *c, const char *residues, const uint32_t
             CU(cudaMemcpyAsync((uint64_t *)c->in_woff.p + i0, src_off + i0, ((size_t)(i1 - i0) + 1) * 8, cudaMemcpyHostToDevice, st));
             if (nw) CU(cudaMemcpyAsync((uint32_t *)c->in_packed.p + w0, packed + base0 + w0, nw * 4, cudaMemcpyHostToDevice, st));
             const unsigned ub = (unsigned)std::min<uint64_t>(((uint64_t)(i1 - i0) + 1 + 7) / 8, (uint64_t)c->sm_count * 32);
-            unpack5_kernel<<<ub, 256, 0, st>>>((const uint32_t *)c->in_packed.p, (const uint64_t *)c->in_woff.p + i0, i1 - i0, 0ull,
+            unpack7_kernel<<<ub, kUnpackThreads, 0, st>>>((const uint32_t *)c->in_packed.p, (const uint64_t *)c->in_woff.p + i0, i1 - i0, 0ull,
                                                (uint8_t *)c->in_res.p, (uint64_t *)c->in_off.p + i0);
             c->launches++;
         } else {
@@ -1384,8 +1384,8 @@ extern "C" int ckm_call_batch(ckm_ctx *c, const char *residues, const uint64_t *
     return finish_batch(c, n, flags, out);
 }
 
-// ---- 5-bit packed input (ckm_packed.cuh) ----
-extern "C" uint64_t ckm_packed_words(uint64_t n_residues) { return (5 * n_residues + 31) / 32; }
+// ---- packed input: seven residues per 32-bit word, base 22 (ckm_packed.cuh) ----
+extern "C" uint64_t ckm_packed_words(uint64_t n_residues) { return (n_residues + kPackPerWord - 1) / kPackPerWord; }
 
 extern "C" int ckm_pack_residues(const char *residues, const uint64_t *offsets, uint32_t n, uint32_t *packed, uint64_t packed_capacity_words,
                                  uint64_t *word_offsets) {
@@ -1402,26 +1402,20 @@ extern "C" int ckm_pack_residues(const char *residues, const uint64_t *offsets, 
         if (w + words > packed_capacity_words) return ckm_fail(CKM_EINVAL, "packed buffer too small (%llu words needed so far)", (unsigned long long)(w + words));
         const unsigned char *p = (const unsigned char *)residues + offsets[i];
         uint32_t *dst = packed + w;
-        uint64_t acc = 0;  // bits not yet written, low bits first
-        uint32_t nb = 0;
-        uint64_t r = 0, wi = 0;
         bool ended = false;
-        const uint64_t slots = (32 * words) / 5;  // codes the sequence's words hold: the ones behind the last residue are "end"
-        for (; r < slots; r++) {
-            uint32_t cd = kPackEnd;
-            if (r < len && !ended) {
-                cd = code[p[r]];
-                ended = cd == kPackEnd;
+        for (uint64_t wi = 0; wi < words; wi++) {  // digit k of a word = residue 7 wi + k; behind the last residue: "end"
+            uint32_t x = 0, mul = 1;
+            for (uint32_t k = 0; k < kPackPerWord; k++, mul *= kPackBase) {
+                const uint64_t r = kPackPerWord * wi + k;
+                uint32_t cd = kPackEnd;
+                if (r < len && !ended) {
+                    cd = code[p[r]];
+                    ended = cd == kPackEnd;
+                }
+                x += cd * mul;
             }
-            acc |= (uint64_t)cd << nb;
-            nb += 5;
-            if (nb >= 32) {
-                dst[wi++] = (uint32_t)acc;
-                acc >>= 32;
-                nb -= 32;
-            }
+            dst[wi] = x;
         }
-        if (wi < words) dst[wi++] = (uint32_t)acc;  // the last word's spare bits (fewer than five) stay zero
         w += words;
     }
     word_offsets[n] = w;
@@ -1460,7 +1454,7 @@ extern "C" int ckm_call_batch_packed(ckm_ctx *c, const uint32_t *packed, const u
     CU(cudaMemsetAsync((uint8_t *)c->in_res.p + total, 0, 32, c->stream));
     {
         const unsigned ub = (unsigned)std::min<uint64_t>(((uint64_t)n + 1 + 7) / 8, (uint64_t)c->sm_count * 32);
-        unpack5_kernel<<<ub, 256, 0, c->stream>>>((const uint32_t *)c->in_packed.p, (const uint64_t *)c->in_woff.p, n, 0ull, (uint8_t *)c->in_res.p,
+        unpack7_kernel<<<ub, kUnpackThreads, 0, c->stream>>>((const uint32_t *)c->in_packed.p, (const uint64_t *)c->in_woff.p, n, 0ull, (uint8_t *)c->in_res.p,
                                                   (uint64_t *)c->in_off.p);
         c->launches++;
     }

@@ -74,7 +74,7 @@ struct ckm_ctx {
     const uint64_t *cur_off = nullptr;
 
     // device work buffers
-    DevBuf in_packed, in_woff;  // 5-bit packed input of ckm_call_batch_packed and its word offsets
+    DevBuf in_packed, in_woff;  // packed input of ckm_call_batch_packed (seven residues per word) and its word offsets
     DevBuf in_res, in_off, totals, hits, hit_keys, hit_avg, n_hits, stored_idx, calls, calls_work, n_calls;
     DevBuf work;   // work counters of probe_pc_kernel
     DevBuf hints;  // per 32-window segment: where the protein sits in chain[] (ckm_hint.cuh)

@@ -1,56 +1,66 @@
-// 5-bit packed residues: the host-side form of a batch for callers that pass every residue through a parser anyway
-// (host/seq_parser.cc does) and want to move 5 bits instead of 8 per residue over PCIe -- end to end the calling path is
-// bound by that copy, and several GPUs share one host's memory bandwidth.
+// Packed residues: the host-side form of a batch for callers that pass every residue through a parser anyway
+// (host/seq_parser.cc does) and want to move fewer than 8 bits per residue over PCIe -- end to end the calling path is bound
+// by that copy, and several GPUs share one host's memory bandwidth.
 //
-// Format.  Sequence i is the bit stream in words [word_offsets[i], word_offsets[i+1]) of `packed` (32-bit little-endian
-// words, residue r in bits [5r, 5r+5) of the stream): codes 0..19 = ACDEFGHIKLMNPQRSTVWY (kguts.cc:273-339), 31 = any other
-// character, 30 = end of the sequence (an embedded NUL ends the reference's scan, kguts.cc:791; the packer also writes it
-// into the slots left over in the last word).  A sequence of L residues takes ceil(5 L / 32) words.
+// Format.  Sequence i is the 32-bit words [word_offsets[i], word_offsets[i+1]) of `packed`; a word holds SEVEN residues as
+// the digits of a base-22 number, residue 7 w + k of the sequence = (word_w / 22^k) % 22 (22^7 < 2^32: 4.57 bits per residue,
+// a quarter of a bit above the entropy of twenty letters): 0..19 = ACDEFGHIKLMNPQRSTVWY (kguts.cc:273-339), 20 = any other
+// character, 21 = end of the sequence (an embedded NUL ends the reference's scan, kguts.cc:791; the packer also writes it
+// into the digits left over in the last word).  A sequence of L residues takes ceil(L / 7) words.
 //
-// On the device the stream is unpacked to the ASCII layout every kernel reads, one warp per sequence: sequence i lands at
-// residue offset 8 * word_offsets[i] (a word holds 6.4 residues, so eight slots per word always suffice), real residues
-// first, NULs behind them -- which is exactly how the kernels already see a protein that ends early (strlen semantics), so
-// neither true lengths nor residue offsets have to be uploaded.  0.1 ms per million proteins.
+// On the device the words are unpacked to the ASCII layout every kernel reads: sequence i lands at residue offset
+// 8 * word_offsets[i] (eight slots per word always suffice), real residues first, NULs behind them -- which is exactly how
+// the kernels already see a protein that ends early (strlen semantics), so neither true lengths nor residue offsets have to
+// be uploaded.  A lane decodes one word (seven divisions by 22 as multiplications), the warp's 32 x 7 bytes are put in order in
+// shared memory and leave as aligned 4-byte stores.
 #pragma once
 #include "ckm_common.cuh"
 
 namespace ckm {
 
-constexpr uint32_t kPackEnd = 30u, kPackInvalid = 31u;
+constexpr uint32_t kPackBase = 22u, kPackPerWord = 7u, kPackInvalid = 20u, kPackEnd = 21u;
+constexpr int kUnpackThreads = 256;
 
-__global__ void __launch_bounds__(256)
-unpack5_kernel(const uint32_t *__restrict__ packed, const uint64_t *__restrict__ woff /* n + 1, rebased to word 0 of `packed` */,
+__global__ void __launch_bounds__(kUnpackThreads)
+unpack7_kernel(const uint32_t *__restrict__ packed, const uint64_t *__restrict__ woff /* n + 1, rebased to word 0 of `packed` */,
                uint32_t n, uint64_t woff_base /* device word offset of woff[0]'s sequence */, uint8_t *__restrict__ residues,
                uint64_t *__restrict__ offsets /* n + 1 residue offsets, written here */) {
-    const uint32_t lane = threadIdx.x & 31u;
+    __shared__ __align__(16) uint8_t s_bytes[kUnpackThreads / 32][32 * kPackPerWord + 4];
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    // code -> ASCII, four codes at a time from a 32-byte table in registers would cost more than this switch-free form:
-    // "ACDEFGHIKLMNPQRSTVWY" + 10 x 'X' + NUL (30) + 'X' (31)
-    for (uint32_t i = warp0; i <= n; i += n_warps) {
+    uint8_t *sb = s_bytes[wid];
+    for (uint32_t i = warp0; i <= n; i += n_warps) {  // one warp per sequence
         const uint64_t w0 = __ldg(woff + i);
         if (lane == 0) offsets[i] = 8ull * (woff_base + w0);
         if (i == n) break;
         const uint32_t words = (uint32_t)(__ldg(woff + i + 1) - w0);
-        const uint32_t slots = 8u * words, coded = (32u * words) / 5u;  // residue slots on the device; codes the stream holds
+        const uint32_t slots = 8u * words, coded = kPackPerWord * words;  // residue slots on the device; digits the words hold
         const uint32_t *src = packed + w0;
         uint32_t *dst = reinterpret_cast<uint32_t *>(residues + 8ull * (woff_base + w0));
-        for (uint32_t r0 = 4u * lane; r0 < slots; r0 += 128u) {
-            uint32_t out = 0;
-            if (r0 < coded) {
-                const uint32_t bit = 5u * r0, wi = bit >> 5, sh = bit & 31u;
-                const uint32_t a = __ldg(src + wi), b = (wi + 1u < words) ? __ldg(src + wi + 1u) : 0u;
-                const uint32_t x = __funnelshift_r(a, b, sh);  // 20 bits: four codes
+        // 32 words = 224 residues = 56 output words per round (7 * 32 is a multiple of four: rounds start word-aligned)
+        for (uint32_t wb = 0; wb < words; wb += 32u) {
+            uint32_t x = wb + lane < words ? __ldg(src + wb + lane) : 0u;
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t c = (x >> (5 * k)) & 31u;
-                    uint32_t ch = 'X';
-                    if (c < 20u) ch = (uint32_t)"ACDEFGHIKLMNPQRSTVWY"[c];
-                    if (c == kPackEnd || r0 + k >= coded) ch = 0u;
-                    out |= ch << (8 * k);
-                }
+            for (int k = 0; k < (int)kPackPerWord; k++) {
+                const uint32_t q = __umulhi(x, 0xBA2E8BA3u) >> 4;  // x / 22
+                const uint32_t c = x - q * kPackBase;
+                x = q;
+                uint32_t ch = 'X';
+                if (c < 20u) ch = (uint32_t)"ACDEFGHIKLMNPQRSTVWY"[c];
+                if (c == kPackEnd || wb + lane >= words) ch = 0u;  // (lanes past the last word: the NULs behind the sequence)
+                sb[kPackPerWord * lane + k] = (uint8_t)ch;
             }
-            dst[r0 >> 2] = out;
+            __syncwarp();
+            const uint32_t r_base = kPackPerWord * wb;
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                const uint32_t o = lane + 32u * t, r0 = r_base + 4u * o;  // output word within the round, its first residue slot
+                if (o < 56u && r0 < coded) dst[r0 >> 2] = reinterpret_cast<const uint32_t *>(sb)[o];
+            }
+            __syncwarp();
         }
+        // eight slots per word, seven digits: the slots behind them are NULs
+        for (uint32_t r0 = ((coded + 3u) & ~3u) + 4u * lane; r0 < slots; r0 += 128u) dst[r0 >> 2] = 0u;
     }
 }
 

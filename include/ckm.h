@@ -197,15 +197,16 @@ void ckm_decoded_kmer(uint64_t encoded, char decoded[9]); /* NUL-terminated */
 int ckm_call_batch(ckm_ctx *ctx, const char *residues, const uint64_t *offsets, uint32_t n, uint32_t flags,
                    ckm_batch_out_t *out);
 
-/* The same call for residues packed five bits apiece (csrc/ckm_packed.cuh): sequence i is the bit stream in the 32-bit words
- * [word_offsets[i], word_offsets[i+1]) of `packed`, residue r in bits [5r, 5r+5): 0..19 = ACDEFGHIKLMNPQRSTVWY, 31 = any other
- * character, 30 = end of the sequence (what an embedded NUL is to the reference, kguts.cc:791; the unused slots of a
- * sequence's last word hold it too).  Results are those of ckm_call_batch on the unpacked strings; hit offsets count residues.
- * Moves 0.64 of the bytes over PCIe.  A parser can emit this form in the pass it makes over every byte anyway;
- * ckm_pack_residues converts an ASCII batch (`packed` must hold the sum of ckm_packed_words(len_i) words). */
+/* The same call for packed residues (csrc/ckm_packed.cuh): sequence i is the 32-bit words [word_offsets[i], word_offsets[i+1])
+ * of `packed`, SEVEN residues to a word as the digits of a base-22 number -- residue 7 w + k = (word_w / 22^k) % 22: 0..19 =
+ * ACDEFGHIKLMNPQRSTVWY, 20 = any other character, 21 = end of the sequence (what an embedded NUL is to the reference,
+ * kguts.cc:791; the unused digits of a sequence's last word hold it too).  Results are those of ckm_call_batch on the unpacked
+ * strings; hit offsets count residues.  Moves 0.58 of the bytes over PCIe (4.57 bits per residue).  A parser can emit this form
+ * in the pass it makes over every byte anyway; ckm_pack_residues converts an ASCII batch (`packed` must hold the sum of
+ * ckm_packed_words(len_i) words). */
 int ckm_call_batch_packed(ckm_ctx *ctx, const uint32_t *packed, const uint64_t *word_offsets, uint32_t n, uint32_t flags,
                           ckm_batch_out_t *out);
-uint64_t ckm_packed_words(uint64_t n_residues); /* ceil(5 n / 32) */
+uint64_t ckm_packed_words(uint64_t n_residues); /* ceil(n / 7) */
 int ckm_pack_residues(const char *residues, const uint64_t *offsets, uint32_t n, uint32_t *packed, uint64_t packed_capacity_words,
                       uint64_t *word_offsets /* n + 1 */);
 

@@ -166,7 +166,7 @@ def test_packed_residue_entry_matches_ascii_entry(checkers):
     extra = synth.batch_from_strings([aa[rng.integers(0, 20, L)].tobytes() for L in lens])
     batch = wl.concat_batches(wl.concat_batches(wl.edge_batch(protos), extra), synth.make_proteins(9, protos, 4000))
     packed, woff = api.pack_residues(batch.residues, batch.offsets)
-    assert int(woff[-1]) == int(((5 * np.diff(batch.offsets.astype(np.int64)) + 31) // 32).sum())
+    assert int(woff[-1]) == int(((np.diff(batch.offsets.astype(np.int64)) + 6) // 7).sum())
     try:
         for chain in ("0", "1"):
             g = _open(img, synth.function_names(sig.n_functions), chain)

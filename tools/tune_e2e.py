@@ -1,5 +1,5 @@
 """End-to-end (host buffers in, best calls out) sweep over pipeline chunk sizes on the C2 workload (GPU box), through the ASCII
-entry point and the 5-bit packed one.  python tools/tune_e2e.py [n_proteins] [n_sigs]"""
+entry point and the packed one.  python tools/tune_e2e.py [n_proteins] [n_sigs]"""
 import ctypes as C
 import json
 import os
