@@ -672,8 +672,12 @@ extern "C" void ckm_close(ckm_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream2) cudaStreamSynchronize(c->stream2);
     c->free_all();
+    if (c->stream_h2d) cudaStreamSynchronize(c->stream_h2d);
     if (c->ev_ready) cudaEventDestroy(c->ev_ready);
     if (c->ev_done2) cudaEventDestroy(c->ev_done2);
+    for (auto &e : c->ev_copy)
+        if (e) cudaEventDestroy(e);
+    if (c->stream_h2d) cudaStreamDestroy(c->stream_h2d);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -1235,6 +1239,7 @@ static int upload_batch(ckm_ctx *c, const char *residues, const uint64_t *offset
 
 // error exit of the pipelined path after work was enqueued: nothing of the aborted batch may still run when the next one starts
 static int pipeline_abort(ckm_ctx *c, int rc) {
+    if (c->stream_h2d) cudaStreamSynchronize(c->stream_h2d);
     if (c->stream2) cudaStreamSynchronize(c->stream2);
     cudaStreamSynchronize(c->stream);
     (void)cudaGetLastError();
@@ -1277,12 +1282,19 @@ static int call_batch_pipelined(ckm_ctx *c, const char *residues, const uint32_t
     }
     if (!c->ev_ready) CU(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
     if (!c->ev_done2) CU(cudaEventCreateWithFlags(&c->ev_done2, cudaEventDisableTiming));
+    // The copies of all chunks go down a stream of their own, back to back: on the compute streams a chunk's copy would sit behind
+    // the kernels of the chunk two before it (a stream is in-order) although the copy engine is idle.  A chunk's kernels wait for
+    // its event.
+    if (!c->stream_h2d) CU(cudaStreamCreateWithFlags(&c->stream_h2d, cudaStreamNonBlocking));
+    for (auto &e : c->ev_copy)
+        if (!e) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     c->cur_off = (const uint64_t *)c->in_off.p;
     // stream 0: counters and slack; stream 1 waits for them.  Offsets travel with their chunk.
     CU(cudaMemsetAsync(c->totals.p, 0, 64, c->stream));
     CU(cudaMemsetAsync((uint8_t *)c->in_res.p + total, 0, 32, c->stream));
     CU(cudaEventRecord(c->ev_ready, c->stream));
     CU(cudaStreamWaitEvent(c->stream2, c->ev_ready, 0));
+    CU(cudaStreamWaitEvent(c->stream_h2d, c->ev_ready, 0));  // (whatever the context's stream still had queued reads the old input)
     uint64_t *reb = nullptr;
     if (base0 != 0) {
         RC(c->h_off.ensure(((size_t)n + 1) * 8));
@@ -1332,18 +1344,25 @@ static int call_batch_pipelined(ckm_ctx *c, const char *residues, const uint32_t
             }
         }
         cudaStream_t st = (k & 1) ? c->stream2 : c->stream;
+        cudaStream_t sc = c->stream_h2d;
+        cudaEvent_t landed = c->ev_copy[k % ckm_ctx::kCopyEvents];
+        if (k >= ckm_ctx::kCopyEvents) CU(cudaStreamSynchronize(k & 1 ? c->stream2 : c->stream));  // the event's last user has passed it
         const uint64_t *src_off = reb ? reb : offsets;
         if (packed) {
             const uint64_t w0 = offsets[i0] - base0, nw = offsets[i1] - offsets[i0];
-            CU(cudaMemcpyAsync((uint64_t *)c->in_woff.p + i0, src_off + i0, ((size_t)(i1 - i0) + 1) * 8, cudaMemcpyHostToDevice, st));
-            if (nw) CU(cudaMemcpyAsync((uint32_t *)c->in_packed.p + w0, packed + base0 + w0, nw * 4, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync((uint64_t *)c->in_woff.p + i0, src_off + i0, ((size_t)(i1 - i0) + 1) * 8, cudaMemcpyHostToDevice, sc));
+            if (nw) CU(cudaMemcpyAsync((uint32_t *)c->in_packed.p + w0, packed + base0 + w0, nw * 4, cudaMemcpyHostToDevice, sc));
+            CU(cudaEventRecord(landed, sc));
+            CU(cudaStreamWaitEvent(st, landed, 0));
             const unsigned ub = (unsigned)std::min<uint64_t>(((uint64_t)(i1 - i0) + 1 + 7) / 8, (uint64_t)c->sm_count * 32);
             unpack7_kernel<<<ub, kUnpackThreads, 0, st>>>((const uint32_t *)c->in_packed.p, (const uint64_t *)c->in_woff.p + i0, i1 - i0, 0ull,
                                                (uint8_t *)c->in_res.p, (uint64_t *)c->in_off.p + i0);
             c->launches++;
         } else {
-            CU(cudaMemcpyAsync((uint64_t *)c->in_off.p + i0, src_off + i0, ((size_t)(i1 - i0) + 1) * 8, cudaMemcpyHostToDevice, st));
-            if (bytes) CU(cudaMemcpyAsync((uint8_t *)c->in_res.p + start, residues + base0 + start, bytes, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync((uint64_t *)c->in_off.p + i0, src_off + i0, ((size_t)(i1 - i0) + 1) * 8, cudaMemcpyHostToDevice, sc));
+            if (bytes) CU(cudaMemcpyAsync((uint8_t *)c->in_res.p + start, residues + base0 + start, bytes, cudaMemcpyHostToDevice, sc));
+            CU(cudaEventRecord(landed, sc));
+            CU(cudaStreamWaitEvent(st, landed, 0));
         }
         RC(launch_range(c, st, (const uint8_t *)c->in_res.p, (const uint64_t *)c->in_off.p, i0, i1 - i0, CKM_WANT_BEST, cp, nullptr));
         CU(cudaMemcpyAsync((ckm_best_t *)c->h_best.p + i0, (const ckm_best_t *)c->best.p + i0, (size_t)(i1 - i0) * sizeof(ckm_best_t),

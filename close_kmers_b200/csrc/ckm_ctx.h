@@ -28,6 +28,9 @@ struct ckm_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: second lane of the pipelined host path
+    cudaStream_t stream_h2d = nullptr;                 // the pipelined path's host-to-device copies: never queued behind a kernel
+    static constexpr int kCopyEvents = 64;
+    cudaEvent_t ev_copy[kCopyEvents] = {};             // chunk k's copy has landed (ring)
     cudaEvent_t ev_ready = nullptr, ev_done2 = nullptr;
     uint64_t pipeline_chunk_bytes = 48ull << 20, pipeline_min_bytes = 32ull << 20;  // 48 MB: profiles/r1/tune_e2e_chunk_sizes_r1g.jsonl
     uint32_t pipeline_ramp_div = 6, pipeline_tail_div = 4;    // first chunk = chunk/ramp_div (then doubling), last = chunk/tail_div (profiles/r2/tune_e2e_r2c.jsonl)
