@@ -134,9 +134,12 @@ rehash_kernel(const uint64_t *__restrict__ raw /* 3 x u64 per slot */, uint64_t 
     if (i >= image_buckets) return;
     const uint64_t k = raw[3 * i], a = raw[3 * i + 1], b = raw[3 * i + 2];
     if (k > CKM_MAX_ENCODED) return;
-    // is slot i where the reference's lookup of k ends?  (every slot between k's home and i is taken: k was inserted past them)
-    for (uint64_t h = fast_mod(k, image_buckets, image_magic); h != i; h = (h + 1 == image_buckets) ? 0 : h + 1)
-        if (raw[3 * h] == k) return;
+    // is slot i where the reference's lookup of k ends?  Not if the k-mer sits in an earlier slot of its probe sequence, and not
+    // if an empty slot comes first (a builder never leaves one there; a hand-made image might: the reference would not find k)
+    for (uint64_t h = fast_mod(k, image_buckets, image_magic); h != i; h = (h + 1 == image_buckets) ? 0 : h + 1) {
+        const uint64_t kh = raw[3 * h];
+        if (kh == k || kh > CKM_MAX_ENCODED) return;
+    }
     const int32_t oI = (int32_t)(uint32_t)a;
     const uint32_t avg = (uint32_t)(a >> 32) & 0xFFFFu, fI = (uint32_t)b, wt = (uint32_t)(b >> 32), o1 = (uint32_t)(oI + 1);
     if (fI >= kPackedFieldLimit || oI < -1 || o1 >= kPackedFieldLimit) {

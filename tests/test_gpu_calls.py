@@ -320,3 +320,41 @@ def test_reference_hash_layout_and_own_table_agree(checkers, world, chain):
         wl.assert_results_equal(few, {k: want[k] for k in ("call_offsets", "calls", "best")}, f"reference hash fused, chain={chain}")
     finally:
         g.close()
+
+
+def test_kmers_the_reference_cannot_reach_stay_unreachable(checkers):
+    """A hand-made image: signature k-mers moved two buckets past their home with an empty bucket in between.  lookup_hash_entry
+    (kguts.cc:585-602) stops at the empty home bucket and never sees them; the library's own table (rehash_kernel re-inserts
+    every k-mer of the image) must not find them either."""
+    protos, sig, img = wl.small_world(seed=29, n_protos=120, n_sigs=30_000)
+    img = img.copy()
+    slots = np.frombuffer(img, api.SLOT_DT, offset=24)  # a writable view
+    nb = len(slots)
+    occ = slots["which_kmer"] <= 20**8
+    moved = 0
+    for s in np.flatnonzero(occ)[::7]:
+        k = int(slots["which_kmer"][s])
+        if k % nb != s or s + 2 >= nb or occ[s + 1] or occ[s + 2]:
+            continue
+        slots[s + 2] = slots[s]
+        slots[s]["which_kmer"] = 20**8 + 1
+        occ[s], occ[s + 2] = False, True
+        moved += 1
+    assert moved > 500
+    orc = checkers.Oracle().open_image(img)
+    batch = wl.concat_batches(wl.edge_batch(protos), synth.make_proteins(30, protos, 1500, mix=(1.0, 0.0, 0.0, 0.0), sub_rate=0.0))
+    want = orc.call_batch(batch, ALL)
+    for env in ({}, {"CKM_REFERENCE_HASH": "1"}, {"CKM_CHAIN": "1", "CKM_OCCUPANCY_BITMAP": "1"}):
+        os.environ.update(env)
+        try:
+            g = api.KmerGuts(image=img, function_names=synth.function_names(sig.n_functions))
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+        try:
+            wl.assert_results_equal(g.process_aa_seq_batch(batch.residues, batch.offsets, ALL), want, f"unreachable k-mers {env}")
+            few = g.process_aa_seq_batch(batch.residues, batch.offsets, api.WANT_CALLS | api.WANT_BEST)
+            wl.assert_results_equal(few, {k: want[k] for k in ("call_offsets", "calls", "best")}, f"unreachable k-mers fused {env}")
+        finally:
+            g.close()
+    orc.close()
