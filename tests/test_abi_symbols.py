@@ -115,3 +115,32 @@ def test_image_header_validation_rejects_crafted_sizes():
         with pytest.raises(api.CkmError) as ei:
             api.KmerGuts(image=np.ascontiguousarray(bad))
         assert ei.value.code == -3, ei.value
+
+
+def test_packed_residue_format_round_trip():
+    """ckm_pack_residues (host code): seven residues to a 32-bit word as base-22 digits, every sequence from a word boundary,
+    'end' behind the last residue and from an embedded NUL on (strlen, kguts.cc:791), 'other' for anything that is not one of
+    the twenty letters.  Decoded here in numpy."""
+    seqs = [b"", b"A", b"ACDEFGH", b"ACDEFGHI", b"ACDEFGHIKLMNPQRSTVWY" * 3, b"MKXacd*-BJOUZ", b"MKV\x00ACDEFGHIKL", b"Y" * 15]
+    batch = synth.batch_from_strings(seqs)
+    packed, woff = api.pack_residues(batch.residues, batch.offsets)
+    assert list(np.diff(woff.astype(np.int64))) == [(len(s) + 6) // 7 for s in seqs] == [api.lib().ckm_packed_words(len(s)) for s in seqs]
+    alpha = b"ACDEFGHIKLMNPQRSTVWY"
+    for i, s in enumerate(seqs):
+        digits = []
+        for w in packed[int(woff[i]): int(woff[i + 1])]:
+            x = int(w)
+            assert x < 22**7
+            for _ in range(7):
+                digits.append(x % 22)
+                x //= 22
+        want = []
+        ended = False
+        for ch in s:
+            if ended or ch == 0:
+                ended = True
+                want.append(21)
+            else:
+                want.append(alpha.index(bytes([ch])) if bytes([ch]) in alpha else 20)
+        want += [21] * (len(digits) - len(want))
+        assert digits == want, (s, digits, want)
